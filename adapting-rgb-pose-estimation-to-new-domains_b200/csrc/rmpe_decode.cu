@@ -1,0 +1,945 @@
+// Inference decode on sm_100a, from the network's output blobs to (candidate, subset).
+//
+// Reference path replaced (eval/eval_coco2014_multi_modes.py, relative to the reference root):
+//   :277-278 / :79-92   cv2.resize of the blobs (+ 4-scale f64 average)  -> k_resize_h / k_resize_v (heat),
+//                                                                           paf_point() on the fly (PAF)
+//   :283-304 / :97-118  gaussian_filter(sigma=3) + 4-neighbour peaks      -> k_smooth_peaks, k_peaks_finalize
+//   :310-360 / :126-176 PAF line integral, criteria, sort, greedy         -> k_limbs
+//   :364-415 / :180-231 person assembly + prune                            -> k_assemble
+//
+// All float arithmetic follows the order of operations of OpenCV 4.13 (resize.cpp, SSE baseline:
+// no FMA) and SciPy (ni_filters.c symmetric correlate, f64 accumulate), see oracle/decode_oracle.py.
+#include <vector>
+
+#include "rmpe_common.cuh"
+
+namespace rmpe {
+
+constexpr int kMaxPeaksCap = 1024;
+constexpr int kMaxCandCap = 4096;
+constexpr int kMaxSubsetCap = 128;
+constexpr int kChunkFrames = 32;
+constexpr int kHeatC = 19;
+constexpr int kPafC = 38;
+
+// scipy _gaussian_kernel1d(sigma=3, radius=12) as produced by numpy on x86-64 (checked against the
+// live scipy weights in tests/test_oracle_pin.py); index 0..12 = offsets -12..0, symmetric.
+__constant__ double c_gauss[13] = {
+    0x1.763a210dfb306p-15, 0x1.4fbe39149e277p-13, 0x1.0d8a5ad43c165p-11, 0x1.8345966f69518p-10,
+    0x1.f1e9915139406p-9,  0x1.1e6bccad344bap-7,  0x1.26defcaeb0202p-6,  0x1.0fa58939b528fp-5,
+    0x1.bfde9c12bec92p-5,  0x1.4a614d1afd337p-4,  0x1.b42a57d56c0bep-4,  0x1.01a25f86eb137p-3,
+    0x1.105a329f98197p-3};
+
+// ------------------------------------------------------------------------------------------
+// cv2.resize INTER_CUBIC coordinate of one destination index (resize.cpp):
+//   scale = 1/inv_scale (double); f = float((d+0.5)*scale-0.5); s = floor(f); t = f - s
+// ------------------------------------------------------------------------------------------
+__device__ inline double resize_scale(int dst_full, int src_len, double inv_fx) {
+    double inv = (inv_fx > 0.0) ? inv_fx : __ddiv_rn((double)dst_full, (double)src_len);
+    return __ddiv_rn(1.0, inv);
+}
+__device__ inline int resize_axis(int d, double scale, float co[4]) {
+    float f = __double2float_rn(__dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5));
+    float fl = floorf(f);
+    cubic_coeffs(__fsub_rn(f, fl), co);
+    return (int)fl;
+}
+__device__ inline int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+// horizontal pass: ((S0*a0 + S1*a1) + S2*a2) + S3*a3
+__device__ inline float tap_ltr(float s0, float s1, float s2, float s3, const float a[4]) {
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s0, a[0]), __fmul_rn(s1, a[1])), __fmul_rn(s2, a[2])),
+                     __fmul_rn(s3, a[3]));
+}
+// vertical pass, vector body: S0*b0 + (S1*b1 + (S2*b2 + S3*b3))
+__device__ inline float tap_rtl(float s0, float s1, float s2, float s3, const float b[4]) {
+    return __fadd_rn(__fmul_rn(s0, b[0]),
+                     __fadd_rn(__fmul_rn(s1, b[1]), __fadd_rn(__fmul_rn(s2, b[2]), __fmul_rn(s3, b[3]))));
+}
+// the last (W*C mod 4) floats of a destination row are produced by the scalar (left-to-right) tail loop
+__device__ inline bool in_row_tail(int x, int c, int W, int C) {
+    int n = W * C;
+    return (x * C + c) >= n - (n & 3);
+}
+
+// ------------------------------------------------------------------------------------------
+// separable resize passes over planar / strided float maps (heat path)
+// ------------------------------------------------------------------------------------------
+struct RJob {
+    const float *src;
+    float *dst;        // plain store target (planar, col stride 1) or null
+    void *acc;         // accumulate target (float for single-scale store, double for the average)
+    long long src_cs, src_rs, src_xs;
+    long long dst_cs, dst_rs;
+    int n_rows, n_cols;    // extent to compute
+    int src_len;           // source length along the resized axis (clamp bound)
+    int dst_full;          // full destination length along the resized axis
+    double inv_fx;         // explicit scale factor (fx=fy=stride call) or 0
+    int tail_w, tail_c;    // vertical pass: destination row width / channels of the cv2 call
+    int ndiv;              // >0: acc[...] (+)= double(v / ndiv)
+    int first;             // first scale of the average: store, do not add
+};
+struct RJobs {
+    RJob j[kChunkFrames];
+};
+
+__global__ void __launch_bounds__(128) k_resize_h(const __grid_constant__ RJobs jobs) {
+    const RJob &J = jobs.j[blockIdx.z];
+    const int x = blockIdx.x * 128 + threadIdx.x;
+    const int r = blockIdx.y;
+    if (x >= J.n_cols || r >= J.n_rows) return;
+    float a[4];
+    const int sx = resize_axis(x, resize_scale(J.dst_full, J.src_len, J.inv_fx), a);
+    const long long o0 = clampi(sx - 1, 0, J.src_len - 1) * J.src_xs, o1 = clampi(sx, 0, J.src_len - 1) * J.src_xs;
+    const long long o2 = clampi(sx + 1, 0, J.src_len - 1) * J.src_xs, o3 = clampi(sx + 2, 0, J.src_len - 1) * J.src_xs;
+#pragma unroll 6
+    for (int c = 0; c < kParts; c++) {
+        const float *row = J.src + c * J.src_cs + r * J.src_rs;
+        J.dst[c * J.dst_cs + r * J.dst_rs + x] = tap_ltr(row[o0], row[o1], row[o2], row[o3], a);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_resize_v(const __grid_constant__ RJobs jobs) {
+    const RJob &J = jobs.j[blockIdx.z];
+    const int x = blockIdx.x * 128 + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= J.n_cols || y >= J.n_rows) return;
+    float b[4];
+    const int sy = resize_axis(y, resize_scale(J.dst_full, J.src_len, J.inv_fx), b);
+    const long long o0 = clampi(sy - 1, 0, J.src_len - 1) * J.src_rs, o1 = clampi(sy, 0, J.src_len - 1) * J.src_rs;
+    const long long o2 = clampi(sy + 1, 0, J.src_len - 1) * J.src_rs, o3 = clampi(sy + 2, 0, J.src_len - 1) * J.src_rs;
+#pragma unroll 6
+    for (int c = 0; c < kParts; c++) {
+        const float *col = J.src + c * J.src_cs + x * J.src_xs;
+        float s0 = col[o0], s1 = col[o1], s2 = col[o2], s3 = col[o3];
+        float v = in_row_tail(x, c, J.tail_w, J.tail_c) ? tap_ltr(s0, s1, s2, s3, b) : tap_rtl(s0, s1, s2, s3, b);
+        long long o = c * J.dst_cs + y * J.dst_rs + x;
+        if (J.ndiv > 0) {
+            double add = (double)__fdiv_rn(v, (float)J.ndiv);
+            double *acc = reinterpret_cast<double *>(J.acc);
+            acc[o] = J.first ? __dadd_rn(0.0, add) : __dadd_rn(acc[o], add);
+        } else {
+            J.dst[o] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// PAF value at an integer point of the up-sampled (single) / scale-averaged (multi) field,
+// evaluated on the fly from the blob(s) with the exact per-pixel arithmetic of cv2.resize.
+// ------------------------------------------------------------------------------------------
+// one bicubic resize (src h x w, NHWC with C channels) evaluated at destination (y, x), channel c
+__device__ inline float resize_point_blob(const float *__restrict__ blob, int h, int w, int C, int c, int y, int x,
+                                          int H, int W, double inv_f) {
+    float a[4], b[4];
+    int sx = resize_axis(x, resize_scale(W, w, inv_f), a);
+    int sy = resize_axis(y, resize_scale(H, h, inv_f), b);
+    float hp[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float *row = blob + ((size_t)clampi(sy - 1 + j, 0, h - 1) * w) * C + c;
+        hp[j] = tap_ltr(row[(size_t)clampi(sx - 1, 0, w - 1) * C], row[(size_t)clampi(sx, 0, w - 1) * C],
+                        row[(size_t)clampi(sx + 1, 0, w - 1) * C], row[(size_t)clampi(sx + 2, 0, w - 1) * C], a);
+    }
+    return in_row_tail(x, c, W, C) ? tap_ltr(hp[0], hp[1], hp[2], hp[3], b) : tap_rtl(hp[0], hp[1], hp[2], hp[3], b);
+}
+
+// multi-scale chain for one scale: blob -> x stride (fx=fy=stride) -> crop (Hc,Wc) -> (H,W)
+__device__ inline float resize_chain_point(const float *__restrict__ blob, int hs, int ws, int C, int c, int y, int x,
+                                           int H, int W, int Hc, int Wc, int stride) {
+    float a[4], b[4];
+    int sx = resize_axis(x, resize_scale(W, Wc, 0.0), a);
+    int sy = resize_axis(y, resize_scale(H, Hc, 0.0), b);
+    float hp[4];
+#pragma unroll 1
+    for (int j = 0; j < 4; j++) {
+        int r = clampi(sy - 1 + j, 0, Hc - 1);
+        float t[4];
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) {
+            int q = clampi(sx - 1 + k, 0, Wc - 1);
+            t[k] = resize_point_blob(blob, hs, ws, C, c, r, q, hs * stride, ws * stride, (double)stride);
+        }
+        hp[j] = tap_ltr(t[0], t[1], t[2], t[3], a);
+    }
+    return in_row_tail(x, c, W, C) ? tap_ltr(hp[0], hp[1], hp[2], hp[3], b) : tap_rtl(hp[0], hp[1], hp[2], hp[3], b);
+}
+
+__device__ inline double paf_point(const RmpeFrameDesc &f, const float *__restrict__ paf, int stride, int c, int y,
+                                   int x) {
+    if (f.n_scales == 1)
+        return (double)resize_point_blob(paf + f.paf_offset[0], f.grid_h[0], f.grid_w[0], kPafC, c, y, x, f.height,
+                                         f.width, 0.0);
+    double acc = 0.0;
+    for (int s = 0; s < f.n_scales; s++) {
+        int Hc = f.grid_h[s] * stride - f.pad_down[s], Wc = f.grid_w[s] * stride - f.pad_right[s];
+        float v = resize_chain_point(paf + f.paf_offset[s], f.grid_h[s], f.grid_w[s], kPafC, c, y, x, f.height,
+                                     f.width, Hc, Wc, stride);
+        acc = __dadd_rn(acc, (double)__fdiv_rn(v, (float)f.n_scales));
+    }
+    return acc;
+}
+
+__global__ void k_paf_points(RmpeFrameDesc f, const float *paf, int stride, int n, const int32_t *cyx, double *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = paf_point(f, paf, stride, cyx[3 * i], cyx[3 * i + 1], cyx[3 * i + 2]);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_smooth_peaks: per (tile, part, frame): U tile + 13-px halo -> shared memory; scipy's
+// separable 25-tap Gaussian (axis 0, store in T, axis 1, store in T; f64 accumulation in the
+// reference's order; 'reflect' boundary); zero-padded 4-neighbour >= test and > thre1;
+// peaks leave through a warp-aggregated atomic slot grab (order restored in k_peaks_finalize).
+// ------------------------------------------------------------------------------------------
+constexpr int kST = 32;          // tile edge
+constexpr int kSR = 12;          // gaussian radius
+constexpr int kSU = kST + 2 * kSR + 2;  // 58: U region edge
+constexpr int kSA = kST + 2;            // 34: rows/cols that need smoothed values (tile + 1)
+constexpr int kSmoothThreads = 256;
+
+struct SmoothJob {
+    const void *U;     // planar [18][H][W] of T
+    int H, W;
+    int frame;         // global frame index (for the counters / lists)
+    void *S_out;       // optional: smoothed map out (debug), planar like U
+};
+struct SmoothJobs {
+    SmoothJob j[kChunkFrames];
+};
+
+__device__ inline int reflect_idx(int i, int n) {
+    int p = 2 * n;
+    int m = i % p;
+    if (m < 0) m += p;
+    return m < n ? m : p - 1 - m;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kSmoothThreads) k_smooth_peaks(const __grid_constant__ SmoothJobs jobs, T thre1,
+                                                                  int max_peaks, int32_t *__restrict__ raw_key,
+                                                                  double *__restrict__ raw_score,
+                                                                  int32_t *__restrict__ raw_count,
+                                                                  int32_t *__restrict__ status) {
+    const SmoothJob &J = jobs.j[blockIdx.z];
+    const int H = J.H, W = J.W;
+    const int tiles_x = (W + kST - 1) / kST, tiles_y = (H + kST - 1) / kST;
+    if ((int)blockIdx.x >= tiles_x * tiles_y) return;
+    const int part = blockIdx.y;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int y0 = ty * kST, x0 = tx * kST;
+    const int tid = threadIdx.x;
+
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    T *sU = reinterpret_cast<T *>(sm_raw);   // [kSU][kSU]
+    T *sA = sU + kSU * kSU;                  // [kSA][kSU]
+    T *sS = sA + kSA * kSU;                  // [kSA][kSA]
+
+    // region of U this tile can touch (clipped); reflect() of any needed index lands inside it
+    const int ry0 = max(0, y0 - kSR - 1), ry1 = min(H - 1, y0 + kST + kSR);
+    const int rx0 = max(0, x0 - kSR - 1), rx1 = min(W - 1, x0 + kST + kSR);
+    const int rh = ry1 - ry0 + 1, rw = rx1 - rx0 + 1;
+    const T *U = reinterpret_cast<const T *>(J.U) + (size_t)part * H * W;
+    for (int i = tid; i < rh * rw; i += kSmoothThreads) {
+        int r = i / rw, c = i - r * rw;
+        sU[r * kSU + c] = U[(size_t)(ry0 + r) * W + rx0 + c];
+    }
+    __syncthreads();
+
+    // rows / cols that need smoothed values: tile +-1, clipped
+    const int ay0 = max(0, y0 - 1), ay1 = min(H - 1, y0 + kST);
+    const int ax0 = max(0, x0 - 1), ax1 = min(W - 1, x0 + kST);
+    const int ah = ay1 - ay0 + 1, aw = ax1 - ax0 + 1;
+
+    // axis 0 (along y) for every region column
+    for (int i = tid; i < ah * rw; i += kSmoothThreads) {
+        int r = i / rw, c = i - r * rw;
+        int y = ay0 + r;
+        double tmp = __dmul_rn((double)sU[(y - ry0) * kSU + c], c_gauss[12]);
+#pragma unroll
+        for (int j = -kSR; j < 0; j++) {
+            int ya = reflect_idx(y + j, H) - ry0, yb = reflect_idx(y - j, H) - ry0;
+            double pair = __dadd_rn((double)sU[ya * kSU + c], (double)sU[yb * kSU + c]);
+            tmp = __dadd_rn(tmp, __dmul_rn(pair, c_gauss[12 + j]));
+        }
+        sA[r * kSU + c] = (T)tmp;
+    }
+    __syncthreads();
+    // axis 1 (along x)
+    for (int i = tid; i < ah * aw; i += kSmoothThreads) {
+        int r = i / aw, c = i - r * aw;
+        int x = ax0 + c;
+        double tmp = __dmul_rn((double)sA[r * kSU + (x - rx0)], c_gauss[12]);
+#pragma unroll
+        for (int j = -kSR; j < 0; j++) {
+            int xa = reflect_idx(x + j, W) - rx0, xb = reflect_idx(x - j, W) - rx0;
+            double pair = __dadd_rn((double)sA[r * kSU + xa], (double)sA[r * kSU + xb]);
+            tmp = __dadd_rn(tmp, __dmul_rn(pair, c_gauss[12 + j]));
+        }
+        sS[r * kSA + c] = (T)tmp;
+    }
+    __syncthreads();
+
+    // 4-neighbour test with zero padding outside the image
+    const int th = min(kST, H - y0), tw = min(kST, W - x0);
+    for (int base = 0; base < th * kST; base += kSmoothThreads) {
+        int i = base + tid;
+        int ly = i / kST, lx = i - ly * kST;
+        bool peak = false;
+        int y = y0 + ly, x = x0 + lx;
+        if (ly < th && lx < tw) {
+            int r = y - ay0, c = x - ax0;
+            T s = sS[r * kSA + c];
+            T up = (y > 0) ? sS[(r - 1) * kSA + c] : (T)0;
+            T dn = (y < H - 1) ? sS[(r + 1) * kSA + c] : (T)0;
+            T lf = (x > 0) ? sS[r * kSA + c - 1] : (T)0;
+            T rt = (x < W - 1) ? sS[r * kSA + c + 1] : (T)0;
+            peak = (s >= up) && (s >= dn) && (s >= lf) && (s >= rt) && (s > thre1);
+            if (J.S_out) reinterpret_cast<T *>(J.S_out)[((size_t)part * H + y) * W + x] = s;
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, peak);
+        if (bal) {
+            int lane = tid & 31;
+            int leader = __ffs(bal) - 1;
+            int slot0 = 0;
+            if (lane == leader) slot0 = atomicAdd(raw_count + J.frame * kParts + part, __popc(bal));
+            slot0 = __shfl_sync(0xffffffffu, slot0, leader);
+            if (peak) {
+                int slot = slot0 + __popc(bal & ((1u << lane) - 1));
+                if (slot < max_peaks) {
+                    size_t o = ((size_t)J.frame * kParts + part) * max_peaks + slot;
+                    raw_key[o] = y * W + x;
+                    raw_score[o] = (double)sU[(y - ry0) * kSU + (x - rx0)];
+                } else {
+                    atomicOr(status + J.frame, RMPE_ST_PEAK_OVERFLOW);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_peaks_finalize: restore np.nonzero order (ascending y*W+x) per part, assign consecutive ids
+// across parts, write candidate rows [x, y, score, id] and the per-part peak tables.
+// ------------------------------------------------------------------------------------------
+struct FinalizeJobs {
+    int W[kChunkFrames];
+};
+__global__ void __launch_bounds__(256) k_peaks_finalize(const __grid_constant__ FinalizeJobs fj, int first_frame,
+                                                        int max_peaks, const int32_t *__restrict__ raw_key,
+                                                        const double *__restrict__ raw_score,
+                                                        const int32_t *__restrict__ raw_count,
+                                                        double *__restrict__ candidate, int32_t *__restrict__ n_peaks,
+                                                        int32_t *__restrict__ pk_x, int32_t *__restrict__ pk_y,
+                                                        double *__restrict__ pk_s) {
+    const int part = blockIdx.x, frame = first_frame + blockIdx.y;
+    const int W = fj.W[blockIdx.y];
+    __shared__ int s_key[kMaxPeaksCap];
+    __shared__ double s_sc[kMaxPeaksCap];
+    const int n = min(raw_count[frame * kParts + part], max_peaks);
+    int npow = 1;
+    while (npow < n) npow <<= 1;
+    const size_t base = ((size_t)frame * kParts + part) * max_peaks;
+    for (int i = threadIdx.x; i < npow; i += blockDim.x) {
+        s_key[i] = (i < n) ? raw_key[base + i] : INT_MAX;
+        s_sc[i] = (i < n) ? raw_score[base + i] : 0.0;
+    }
+    __syncthreads();
+    for (int k = 2; k <= npow; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npow; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    bool up = ((i & k) == 0);
+                    int a = s_key[i], b = s_key[ixj];
+                    if ((a > b) == up) {
+                        s_key[i] = b; s_key[ixj] = a;
+                        double t = s_sc[i]; s_sc[i] = s_sc[ixj]; s_sc[ixj] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    int id0 = 0;
+    for (int q = 0; q < part; q++) id0 += min(raw_count[frame * kParts + q], max_peaks);
+    if (threadIdx.x == 0) n_peaks[frame * kParts + part] = n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int key = s_key[i];
+        int y = key / W, x = key - y * W;
+        double sc = s_sc[i];
+        double *row = candidate + ((size_t)frame * kParts * max_peaks + id0 + i) * 4;
+        row[0] = (double)x; row[1] = (double)y; row[2] = sc; row[3] = (double)(id0 + i);
+        pk_x[base + i] = x; pk_y[base + i] = y; pk_s[base + i] = sc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_limbs: one CTA per (limb, frame).  All nA x nB pairs in (i-major, j-minor) order, 10-point
+// PAF line integral in f64, criteria, ordered ballot/scan compaction, stable descending sort
+// (bitonic on (score desc, generation index asc)), greedy one-to-one pick.
+// ------------------------------------------------------------------------------------------
+constexpr int kLimbThreads = 256;
+
+__global__ void __launch_bounds__(kLimbThreads) k_limbs(const RmpeFrameDesc *__restrict__ frames, int first_frame,
+                                                        const float *__restrict__ paf, int stride, double thre2,
+                                                        int max_peaks, int max_cand,
+                                                        const int32_t *__restrict__ n_peaks,
+                                                        const int32_t *__restrict__ pk_x,
+                                                        const int32_t *__restrict__ pk_y,
+                                                        const double *__restrict__ pk_s,
+                                                        double *__restrict__ limb_cand, int32_t *__restrict__ n_limb_cand,
+                                                        double *__restrict__ connections, int32_t *__restrict__ n_conn,
+                                                        double *__restrict__ ws_cand, int32_t *__restrict__ status) {
+    const int k = blockIdx.x, frame = first_frame + blockIdx.y;
+    const RmpeFrameDesc f = frames[frame];
+    const int pa = c_dec_a[k], pb = c_dec_b[k], pc = c_dec_paf[k];
+    const int nA = n_peaks[frame * kParts + pa], nB = n_peaks[frame * kParts + pb];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (nA == 0 || nB == 0) {   // special_k
+        if (tid == 0) { n_conn[frame * kLimbs + k] = -1; if (n_limb_cand) n_limb_cand[frame * kLimbs + k] = 0; }
+        return;
+    }
+    const size_t tA = ((size_t)frame * kParts + pa) * max_peaks, tB = ((size_t)frame * kParts + pb) * max_peaks;
+    // candidate rows (i, j, score, score + sA + sB) in generation order
+    double *cand = (limb_cand ? limb_cand : ws_cand) + ((size_t)frame * kLimbs + k) * max_cand * 4;
+
+    __shared__ int s_warp_cnt[kLimbThreads / 32];
+    __shared__ int s_total;
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    double *s_score = reinterpret_cast<double *>(sm_raw);          // [npow]
+    int *s_seq = reinterpret_cast<int *>(s_score + max_cand);       // [npow]
+    uint8_t *s_usedA = reinterpret_cast<uint8_t *>(s_seq + max_cand);
+    uint8_t *s_usedB = s_usedA + kMaxPeaksCap;
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+
+    const int total = nA * nB;
+    const double halfH = __dmul_rn(0.5, (double)f.height);
+    for (int base = 0; base < total; base += kLimbThreads) {
+        int idx = base + tid;
+        bool pass = false;
+        double score = 0.0, score2 = 0.0;
+        int i = 0, j = 0;
+        if (idx < total) {
+            i = idx / nB; j = idx - i * nB;
+            int ax = pk_x[tA + i], ay = pk_y[tA + i], bx = pk_x[tB + j], by = pk_y[tB + j];
+            int vx = bx - ax, vy = by - ay;
+            double norm = __dsqrt_rn((double)(vx * vx + vy * vy));
+            if (norm != 0.0) {
+                double ux = __ddiv_rn((double)vx, norm), uy = __ddiv_rn((double)vy, norm);
+                // np.linspace(a, b, 10): step = (b-a)/9; p_I = I*step + a, p_9 = b
+                double stepx = __ddiv_rn((double)vx, 9.0), stepy = __ddiv_rn((double)vy, 9.0);
+                double sum = 0.0;
+                int nok = 0;
+#pragma unroll 1
+                for (int I = 0; I < 10; I++) {
+                    double px = (I == 9) ? (double)bx : __dadd_rn(__dmul_rn((double)I, stepx), (double)ax);
+                    double py = (I == 9) ? (double)by : __dadd_rn(__dmul_rn((double)I, stepy), (double)ay);
+                    int xi = __double2int_rn(px), yi = __double2int_rn(py);   // round half to even
+                    double vxp = paf_point(f, paf, stride, pc, yi, xi);
+                    double vyp = paf_point(f, paf, stride, pc + 1, yi, xi);
+                    double s = __dadd_rn(__dmul_rn(vxp, ux), __dmul_rn(vyp, uy));
+                    sum = __dadd_rn(sum, s);
+                    nok += (s > thre2) ? 1 : 0;
+                }
+                double prior = __dsub_rn(__ddiv_rn(halfH, norm), 1.0);
+                prior = prior < 0.0 ? prior : 0.0;
+                score = __dadd_rn(__ddiv_rn(sum, 10.0), prior);
+                pass = (nok > 8) && (score > 0.0);
+                score2 = __dadd_rn(__dadd_rn(score, pk_s[tA + i]), pk_s[tB + j]);
+            }
+        }
+        // ordered compaction
+        unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = s_total;
+        for (int w = 0; w < warp; w++) off += s_warp_cnt[w];
+        if (pass) {
+            int slot = off + __popc(bal & ((1u << lane) - 1));
+            if (slot < max_cand) {
+                double *row = cand + (size_t)slot * 4;
+                row[0] = (double)i; row[1] = (double)j; row[2] = score; row[3] = score2;
+            } else {
+                atomicOr(status + frame, RMPE_ST_CAND_OVERFLOW);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int t = s_total;
+            for (int w = 0; w < kLimbThreads / 32; w++) t += s_warp_cnt[w];
+            s_total = t;
+        }
+        __syncthreads();
+    }
+    const int nc = min(s_total, max_cand);
+    if (tid == 0 && n_limb_cand) n_limb_cand[frame * kLimbs + k] = nc;
+    __threadfence_block();
+    __syncthreads();
+
+    // stable descending sort by score
+    int npow = 1;
+    while (npow < nc) npow <<= 1;
+    for (int t = tid; t < npow; t += kLimbThreads) {
+        s_score[t] = (t < nc) ? cand[(size_t)t * 4 + 2] : -1.0e300;
+        s_seq[t] = t;
+    }
+    for (int t = tid; t < kMaxPeaksCap; t += kLimbThreads) { s_usedA[t] = 0; s_usedB[t] = 0; }
+    __syncthreads();
+    for (int kk = 2; kk <= npow; kk <<= 1)
+        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+            for (int t = tid; t < npow; t += kLimbThreads) {
+                int u = t ^ jj;
+                if (u > t) {
+                    bool up = ((t & kk) == 0);
+                    double sa = s_score[t], sb = s_score[u];
+                    int qa = s_seq[t], qb = s_seq[u];
+                    // "a after b" in the wanted order (score desc, seq asc)
+                    bool a_after_b = (sa < sb) || (sa == sb && qa > qb);
+                    if (a_after_b == up) { s_score[t] = sb; s_score[u] = sa; s_seq[t] = qb; s_seq[u] = qa; }
+                }
+            }
+            __syncthreads();
+        }
+    // greedy pick (sequential, tiny)
+    if (tid == 0) {
+        int n = 0;
+        const int lim = min(nA, nB);
+        double *conn = connections + ((size_t)frame * kLimbs + k) * max_peaks * 5;
+        int idA0 = 0, idB0 = 0;
+        for (int q = 0; q < pa; q++) idA0 += n_peaks[frame * kParts + q];
+        for (int q = 0; q < pb; q++) idB0 += n_peaks[frame * kParts + q];
+        for (int t = 0; t < nc && n < lim; t++) {
+            const double *row = cand + (size_t)s_seq[t] * 4;
+            int i = (int)row[0], j = (int)row[1];
+            if (!s_usedA[i] && !s_usedB[j]) {
+                s_usedA[i] = 1; s_usedB[j] = 1;
+                double *o = conn + (size_t)n * 5;
+                o[0] = (double)(idA0 + i); o[1] = (double)(idB0 + j); o[2] = row[2]; o[3] = (double)i; o[4] = (double)j;
+                n++;
+            }
+        }
+        n_conn[frame * kLimbs + k] = n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_assemble: one warp per frame; sequential person assembly, merge and prune.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks, int max_persons,
+                                                 const double *__restrict__ candidate,
+                                                 const double *__restrict__ connections,
+                                                 const int32_t *__restrict__ n_conn, double *__restrict__ subset,
+                                                 int32_t *__restrict__ n_subset, int32_t *__restrict__ status) {
+    const int frame = first_frame + blockIdx.x, lane = threadIdx.x;
+    __shared__ double s_sub[kMaxSubsetCap + 1][20];
+    const double *cand = candidate + (size_t)frame * kParts * max_peaks * 4;
+    int nrows = 0;
+    int st = 0;
+    for (int k = 0; k < kLimbs; k++) {
+        const int nc = n_conn[frame * kLimbs + k];
+        if (nc < 0) continue;
+        const int ia = c_dec_a[k], ib = c_dec_b[k];
+        const double *conn = connections + ((size_t)frame * kLimbs + k) * max_peaks * 5;
+        for (int i = 0; i < nc; i++) {
+            const double pA = conn[i * 5 + 0], pB = conn[i * 5 + 1], sc = conn[i * 5 + 2];
+            int found = 0, j1 = -1, j2 = -1;
+            for (int j0 = 0; j0 < nrows; j0 += 32) {
+                int j = j0 + lane;
+                bool hit = (j < nrows) && (s_sub[j][ia] == pA || s_sub[j][ib] == pB);
+                unsigned bal = __ballot_sync(0xffffffffu, hit);
+                while (bal) {
+                    int b = __ffs(bal) - 1;
+                    bal &= bal - 1;
+                    if (found == 0) j1 = j0 + b;
+                    else if (found == 1) j2 = j0 + b;
+                    found++;
+                }
+            }
+            if (found > 2) { st |= RMPE_ST_FOUND_GT2; found = 2; }
+            __syncwarp();
+            if (found == 1) {
+                if (lane == 0 && s_sub[j1][ib] != pB) {
+                    s_sub[j1][ib] = pB;
+                    s_sub[j1][19] = __dadd_rn(s_sub[j1][19], 1.0);
+                    s_sub[j1][18] = __dadd_rn(s_sub[j1][18], __dadd_rn(cand[(size_t)(int)pB * 4 + 2], sc));
+                }
+            } else if (found == 2) {
+                bool both = (lane < kParts) && (s_sub[j1][lane] >= 0.0) && (s_sub[j2][lane] >= 0.0);
+                unsigned overlap = __ballot_sync(0xffffffffu, both);
+                if (overlap == 0) {
+                    if (lane < kParts) s_sub[j1][lane] = __dadd_rn(s_sub[j1][lane], __dadd_rn(s_sub[j2][lane], 1.0));
+                    if (lane == 18) s_sub[j1][18] = __dadd_rn(__dadd_rn(s_sub[j1][18], s_sub[j2][18]), sc);
+                    if (lane == 19) s_sub[j1][19] = __dadd_rn(s_sub[j1][19], s_sub[j2][19]);
+                    __syncwarp();
+                    for (int r = j2; r < nrows - 1; r++) {   // np.delete(subset, j2, 0)
+                        double v = (lane < 20) ? s_sub[r + 1][lane] : 0.0;
+                        __syncwarp();
+                        if (lane < 20) s_sub[r][lane] = v;
+                        __syncwarp();
+                    }
+                    nrows--;
+                } else if (lane == 0) {
+                    s_sub[j1][ib] = pB;
+                    s_sub[j1][19] = __dadd_rn(s_sub[j1][19], 1.0);
+                    s_sub[j1][18] = __dadd_rn(s_sub[j1][18], __dadd_rn(cand[(size_t)(int)pB * 4 + 2], sc));
+                }
+            } else if (found == 0 && k < 17) {
+                if (nrows < max_persons && nrows < kMaxSubsetCap) {
+                    if (lane < 20) s_sub[nrows][lane] = -1.0;
+                    __syncwarp();
+                    if (lane == 0) {
+                        s_sub[nrows][ia] = pA;
+                        s_sub[nrows][ib] = pB;
+                        s_sub[nrows][19] = 2.0;
+                        double s2 = __dadd_rn(__dadd_rn(0.0, cand[(size_t)(int)pA * 4 + 2]), cand[(size_t)(int)pB * 4 + 2]);
+                        s_sub[nrows][18] = __dadd_rn(s2, sc);
+                    }
+                    nrows++;
+                } else {
+                    st |= RMPE_ST_PERSON_OVERFLOW;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    // prune: fewer than 4 parts or mean score < 0.4
+    int nout = 0;
+    double *out = subset + (size_t)frame * max_persons * 20;
+    for (int r = 0; r < nrows; r++) {
+        bool drop = (s_sub[r][19] < 4.0) || (__ddiv_rn(s_sub[r][18], s_sub[r][19]) < 0.4);
+        if (!drop) {
+            if (lane < 20) out[(size_t)nout * 20 + lane] = s_sub[r][lane];
+            nout++;
+        }
+    }
+    if (lane == 0) {
+        n_subset[frame] = nout;
+        if (st) atomicOr(status + frame, st);
+    }
+}
+
+// ==========================================================================================
+// host side
+// ==========================================================================================
+struct FramePlan {
+    bool multi;
+    size_t u_elems;      // 18*H*W (T)
+    size_t p1_elems;     // floats
+    size_t i1_elems;
+    size_t p2_elems;
+    size_t bytes;        // total workspace of the frame (256-aligned parts)
+};
+
+static size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+static FramePlan plan_frame(const RmpeFrameDesc &f, int stride) {
+    FramePlan p{};
+    p.multi = f.n_scales > 1;
+    p.u_elems = (size_t)kParts * f.height * f.width;
+    if (!p.multi) {
+        p.p1_elems = (size_t)kParts * f.grid_h[0] * f.width;
+    } else {
+        for (int s = 0; s < f.n_scales; s++) {
+            size_t Hc = (size_t)f.grid_h[s] * stride - f.pad_down[s], Wc = (size_t)f.grid_w[s] * stride - f.pad_right[s];
+            size_t p1 = (size_t)kParts * f.grid_h[s] * Wc, i1 = (size_t)kParts * Hc * Wc, p2 = (size_t)kParts * Hc * f.width;
+            if (p1 > p.p1_elems) p.p1_elems = p1;
+            if (i1 > p.i1_elems) p.i1_elems = i1;
+            if (p2 > p.p2_elems) p.p2_elems = p2;
+        }
+    }
+    p.bytes = al256(p.u_elems * (p.multi ? 8 : 4)) + al256(p.p1_elems * 4) + al256(p.i1_elems * 4) + al256(p.p2_elems * 4);
+    return p;
+}
+
+static size_t fixed_ws_bytes(int batch, int max_peaks, int max_cand) {
+    size_t per_list = (size_t)batch * kParts * max_peaks;
+    return al256(per_list * 4) /*raw_key*/ + al256(per_list * 8) /*raw_score*/ + al256((size_t)batch * kParts * 4) /*raw_count*/ +
+           al256(per_list * 4) * 2 /*pk_x, pk_y*/ + al256(per_list * 8) /*pk_s*/ +
+           al256((size_t)batch * kLimbs * max_cand * 4 * 8) /*ws_cand*/ + 4096;
+}
+
+static bool frame_ok(const RmpeFrameDesc &f, int stride) {
+    if (f.height <= 0 || f.width <= 0 || f.n_scales < 1 || f.n_scales > RMPE_MAX_SCALES) return false;
+    for (int s = 0; s < f.n_scales; s++) {
+        if (f.grid_h[s] <= 0 || f.grid_w[s] <= 0) return false;
+        if (f.n_scales > 1 && (f.grid_h[s] * stride - f.pad_down[s] <= 0 || f.grid_w[s] * stride - f.pad_right[s] <= 0))
+            return false;
+    }
+    return true;
+}
+
+// heat maps of a chunk of frames -> U (planar [18][H][W], float single-scale / double multi-scale)
+static int launch_heat_up(const RmpeFrameDesc *fr, int n, const float *heat, int stride, uint8_t *const *u_ptr,
+                          float *const *p1_ptr, float *const *i1_ptr, float *const *p2_ptr, cudaStream_t st) {
+    // single-scale frames: blob -> (h x W) -> (H x W)
+    {
+        RJobs jh{}, jv{};
+        int m = 0, maxc = 0, maxr_h = 0, maxr_v = 0;
+        for (int i = 0; i < n; i++) {
+            const RmpeFrameDesc &f = fr[i];
+            if (f.n_scales != 1) continue;
+            int h = f.grid_h[0], w = f.grid_w[0];
+            RJob &a = jh.j[m];
+            a.src = heat + f.heat_offset[0]; a.dst = p1_ptr[i]; a.acc = nullptr;
+            a.src_cs = 1; a.src_rs = (long long)w * kHeatC; a.src_xs = kHeatC;
+            a.dst_cs = (long long)h * f.width; a.dst_rs = f.width;
+            a.n_rows = h; a.n_cols = f.width; a.src_len = w; a.dst_full = f.width; a.inv_fx = 0.0;
+            RJob &b = jv.j[m];
+            b.src = p1_ptr[i]; b.dst = reinterpret_cast<float *>(u_ptr[i]); b.acc = nullptr;
+            b.src_cs = (long long)h * f.width; b.src_rs = f.width; b.src_xs = 1;
+            b.dst_cs = (long long)f.height * f.width; b.dst_rs = f.width;
+            b.n_rows = f.height; b.n_cols = f.width; b.src_len = h; b.dst_full = f.height; b.inv_fx = 0.0;
+            b.tail_w = f.width; b.tail_c = kHeatC; b.ndiv = 0; b.first = 0;
+            maxc = max(maxc, f.width); maxr_h = max(maxr_h, h); maxr_v = max(maxr_v, f.height);
+            m++;
+        }
+        if (m) {
+            k_resize_h<<<dim3((maxc + 127) / 128, maxr_h, m), 128, 0, st>>>(jh);
+            k_resize_v<<<dim3((maxc + 127) / 128, maxr_v, m), 128, 0, st>>>(jv);
+            count_launch(2);
+        }
+    }
+    // multi-scale frames: per scale  blob -> x stride -> crop -> (H,W), accumulated in f64
+    for (int s = 0; s < RMPE_MAX_SCALES; s++) {
+        RJobs j1{}, j2{}, j3{}, j4{};
+        int m = 0, c1 = 0, r1 = 0, r2 = 0, c3 = 0, r4 = 0;
+        for (int i = 0; i < n; i++) {
+            const RmpeFrameDesc &f = fr[i];
+            if (f.n_scales <= 1 || s >= f.n_scales) continue;
+            int hs = f.grid_h[s], ws = f.grid_w[s];
+            int Hc = hs * stride - f.pad_down[s], Wc = ws * stride - f.pad_right[s];
+            // (1) horizontal x stride: blob (hs, ws) -> P1 (hs, Wc)   [columns beyond the crop never read]
+            RJob &a = j1.j[m];
+            a.src = heat + f.heat_offset[s]; a.dst = p1_ptr[i];
+            a.src_cs = 1; a.src_rs = (long long)ws * kHeatC; a.src_xs = kHeatC;
+            a.dst_cs = (long long)hs * Wc; a.dst_rs = Wc;
+            a.n_rows = hs; a.n_cols = Wc; a.src_len = ws; a.dst_full = ws * stride; a.inv_fx = (double)stride;
+            // (2) vertical x stride: P1 -> I1 (Hc, Wc); full row = ws*stride*19 floats, a multiple of 4
+            RJob &b = j2.j[m];
+            b.src = p1_ptr[i]; b.dst = i1_ptr[i];
+            b.src_cs = (long long)hs * Wc; b.src_rs = Wc; b.src_xs = 1;
+            b.dst_cs = (long long)Hc * Wc; b.dst_rs = Wc;
+            b.n_rows = Hc; b.n_cols = Wc; b.src_len = hs; b.dst_full = hs * stride; b.inv_fx = (double)stride;
+            b.tail_w = ws * stride; b.tail_c = kHeatC; b.ndiv = 0; b.first = 0;
+            // (3) horizontal to W: I1 (Hc, Wc) -> P2 (Hc, W)
+            RJob &c = j3.j[m];
+            c.src = i1_ptr[i]; c.dst = p2_ptr[i];
+            c.src_cs = (long long)Hc * Wc; c.src_rs = Wc; c.src_xs = 1;
+            c.dst_cs = (long long)Hc * f.width; c.dst_rs = f.width;
+            c.n_rows = Hc; c.n_cols = f.width; c.src_len = Wc; c.dst_full = f.width; c.inv_fx = 0.0;
+            // (4) vertical to H, accumulate v / n_scales into the f64 average
+            RJob &d = j4.j[m];
+            d.src = p2_ptr[i]; d.dst = nullptr; d.acc = u_ptr[i];
+            d.src_cs = (long long)Hc * f.width; d.src_rs = f.width; d.src_xs = 1;
+            d.dst_cs = (long long)f.height * f.width; d.dst_rs = f.width;
+            d.n_rows = f.height; d.n_cols = f.width; d.src_len = Hc; d.dst_full = f.height; d.inv_fx = 0.0;
+            d.tail_w = f.width; d.tail_c = kHeatC; d.ndiv = f.n_scales; d.first = (s == 0) ? 1 : 0;
+            c1 = max(c1, Wc); r1 = max(r1, hs); r2 = max(r2, Hc); c3 = max(c3, f.width); r4 = max(r4, f.height);
+            m++;
+        }
+        if (!m) continue;
+        k_resize_h<<<dim3((c1 + 127) / 128, r1, m), 128, 0, st>>>(j1);
+        k_resize_v<<<dim3((c1 + 127) / 128, r2, m), 128, 0, st>>>(j2);
+        k_resize_h<<<dim3((c3 + 127) / 128, r2, m), 128, 0, st>>>(j3);
+        k_resize_v<<<dim3((c3 + 127) / 128, r4, m), 128, 0, st>>>(j4);
+        count_launch(4);
+    }
+    RMPE_CUDA_TRY(cudaGetLastError());
+    return RMPE_OK;
+}
+
+static size_t smooth_smem_bytes(bool f64) { return (size_t)(kSU * kSU + kSA * kSU + kSA * kSA) * (f64 ? 8 : 4); }
+
+static int ensure_smooth_attr() {
+    static bool done = false;
+    if (done) return RMPE_OK;
+    RMPE_CUDA_TRY(cudaFuncSetAttribute(k_smooth_peaks<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smooth_smem_bytes(true)));
+    RMPE_CUDA_TRY(cudaFuncSetAttribute(k_smooth_peaks<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smooth_smem_bytes(false)));
+    RMPE_CUDA_TRY(cudaFuncSetAttribute(k_limbs, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kMaxCandCap * 12 + 2 * kMaxPeaksCap));
+    done = true;
+    return RMPE_OK;
+}
+
+}  // namespace rmpe
+
+using namespace rmpe;
+
+extern "C" size_t rmpe_decode_workspace_bytes(int batch, const RmpeFrameDesc *frames_host, int max_peaks, int max_cand) {
+    if (batch <= 0 || !frames_host) return 0;
+    // enough for chunks of up to kChunkFrames of the largest frame
+    size_t biggest = 0;
+    for (int i = 0; i < batch; i++) {
+        size_t b = plan_frame(frames_host[i], 8).bytes;
+        if (b > biggest) biggest = b;
+    }
+    int chunk = batch < kChunkFrames ? batch : kChunkFrames;
+    return fixed_ws_bytes(batch, max_peaks, max_cand) + biggest * chunk + 4096;
+}
+
+extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
+    if (!is_initialised()) { set_error("rmpe_init not called"); return RMPE_E_NOTINIT; }
+    RMPE_REQUIRE(b != nullptr, "descriptor is null");
+    RMPE_REQUIRE(b->batch >= 0, "negative batch");
+    if (b->batch == 0) return RMPE_OK;
+    RMPE_REQUIRE(b->max_peaks > 0 && b->max_peaks <= kMaxPeaksCap, "max_peaks must be in [1,1024]");
+    RMPE_REQUIRE(b->max_cand > 0 && b->max_cand <= kMaxCandCap && (b->max_cand & (b->max_cand - 1)) == 0,
+                 "max_cand must be a power of two in [1,4096]");
+    RMPE_REQUIRE(b->max_persons > 0 && b->max_persons <= kMaxSubsetCap, "max_persons must be in [1,128]");
+    RMPE_REQUIRE(b->stride > 0, "stride");
+    RMPE_REQUIRE(b->heat && b->paf && b->frames && b->frames_host, "blobs / frame descriptors");
+    RMPE_REQUIRE(b->candidate && b->n_peaks && b->connections && b->n_conn && b->subset && b->n_subset && b->status,
+                 "output pointers");
+    RMPE_REQUIRE(b->workspace != nullptr, "workspace");
+    for (int i = 0; i < b->batch; i++) RMPE_REQUIRE(frame_ok(b->frames_host[i], b->stride), "frame descriptor");
+    cudaStream_t st = (cudaStream_t)stream_;
+    int rc = ensure_smooth_attr();
+    if (rc != RMPE_OK) return rc;
+
+    const int B = b->batch, MP = b->max_peaks, MC = b->max_cand;
+    uint8_t *ws = (uint8_t *)b->workspace;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void *p = ws + off; off += al256(bytes); return p; };
+    const size_t per_list = (size_t)B * kParts * MP;
+    int32_t *raw_key = (int32_t *)take(per_list * 4);
+    double *raw_score = (double *)take(per_list * 8);
+    int32_t *raw_count = (int32_t *)take((size_t)B * kParts * 4);
+    int32_t *pk_x = (int32_t *)take(per_list * 4);
+    int32_t *pk_y = (int32_t *)take(per_list * 4);
+    double *pk_s = (double *)take(per_list * 8);
+    double *ws_cand = (double *)take((size_t)B * kLimbs * MC * 4 * 8);
+    RMPE_REQUIRE(off <= b->workspace_bytes, "workspace too small (see rmpe_decode_workspace_bytes)");
+    const size_t frame_ws0 = off;
+
+    RMPE_CUDA_TRY(cudaMemsetAsync(raw_count, 0, (size_t)B * kParts * 4, st));
+    RMPE_CUDA_TRY(cudaMemsetAsync(b->status, 0, (size_t)B * 4, st));
+
+    int f0 = 0;
+    while (f0 < B) {
+        // take frames while they fit
+        int n = 0;
+        size_t o = frame_ws0;
+        uint8_t *u_ptr[kChunkFrames];
+        float *p1_ptr[kChunkFrames], *i1_ptr[kChunkFrames], *p2_ptr[kChunkFrames];
+        bool any_single = false, any_multi = false;
+        while (f0 + n < B && n < kChunkFrames) {
+            FramePlan p = plan_frame(b->frames_host[f0 + n], b->stride);
+            if (o + p.bytes > b->workspace_bytes) break;
+            u_ptr[n] = ws + o; o += al256(p.u_elems * (p.multi ? 8 : 4));
+            p1_ptr[n] = (float *)(ws + o); o += al256(p.p1_elems * 4);
+            i1_ptr[n] = (float *)(ws + o); o += al256(p.i1_elems * 4);
+            p2_ptr[n] = (float *)(ws + o); o += al256(p.p2_elems * 4);
+            (p.multi ? any_multi : any_single) = true;
+            n++;
+        }
+        RMPE_REQUIRE(n > 0, "workspace too small for one frame (see rmpe_decode_workspace_bytes)");
+        const RmpeFrameDesc *fr = b->frames_host + f0;
+        rc = launch_heat_up(fr, n, b->heat, b->stride, u_ptr, p1_ptr, i1_ptr, p2_ptr, st);
+        if (rc != RMPE_OK) return rc;
+
+        // smooth + peaks: one launch per map dtype present in the chunk
+        for (int pass = 0; pass < 2; pass++) {
+            bool multi = (pass == 1);
+            if (!(multi ? any_multi : any_single)) continue;
+            SmoothJobs sj{};
+            int m = 0, max_tiles = 0;
+            for (int i = 0; i < n; i++) {
+                if ((fr[i].n_scales > 1) != multi) continue;
+                sj.j[m].U = u_ptr[i]; sj.j[m].H = fr[i].height; sj.j[m].W = fr[i].width;
+                sj.j[m].frame = f0 + i; sj.j[m].S_out = nullptr;
+                int t = ((fr[i].height + kST - 1) / kST) * ((fr[i].width + kST - 1) / kST);
+                max_tiles = max(max_tiles, t);
+                m++;
+            }
+            dim3 grid(max_tiles, kParts, m);
+            if (multi)
+                k_smooth_peaks<double><<<grid, kSmoothThreads, smooth_smem_bytes(true), st>>>(
+                    sj, b->thre1, MP, raw_key, raw_score, raw_count, b->status);
+            else
+                k_smooth_peaks<float><<<grid, kSmoothThreads, smooth_smem_bytes(false), st>>>(
+                    sj, (float)b->thre1, MP, raw_key, raw_score, raw_count, b->status);
+            count_launch();
+        }
+        {
+            FinalizeJobs fj{};
+            for (int i = 0; i < n; i++) fj.W[i] = fr[i].width;
+            k_peaks_finalize<<<dim3(kParts, n), 256, 0, st>>>(fj, f0, MP, raw_key, raw_score, raw_count, b->candidate,
+                                                             b->n_peaks, pk_x, pk_y, pk_s);
+            count_launch();
+        }
+        f0 += n;
+    }
+    // limbs + assembly for the whole batch
+    {
+        size_t smem = (size_t)MC * 12 + 2 * kMaxPeaksCap;
+        k_limbs<<<dim3(kLimbs, B), kLimbThreads, smem, st>>>(b->frames, 0, b->paf, b->stride, b->thre2, MP, MC, b->n_peaks,
+                                                            pk_x, pk_y, pk_s, b->limb_cand, b->n_limb_cand,
+                                                            b->connections, b->n_conn, ws_cand, b->status);
+        k_assemble<<<B, 32, 0, st>>>(0, MP, b->max_persons, b->candidate, b->connections, b->n_conn, b->subset,
+                                     b->n_subset, b->status);
+        count_launch(2);
+    }
+    RMPE_CUDA_TRY(cudaGetLastError());
+    return RMPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// debugging / stage-parity hooks
+// ------------------------------------------------------------------------------------------
+extern "C" int rmpe_debug_heat_maps(const RmpeFrameDesc *f, const float *heat_dev, void *up_out_dev,
+                                    void *smooth_out_dev, void *stream_) {
+    if (!is_initialised()) { set_error("rmpe_init not called"); return RMPE_E_NOTINIT; }
+    RMPE_REQUIRE(f && heat_dev && up_out_dev, "null argument");
+    RMPE_REQUIRE(frame_ok(*f, 8), "frame descriptor");
+    cudaStream_t st = (cudaStream_t)stream_;
+    int rc = ensure_smooth_attr();
+    if (rc != RMPE_OK) return rc;
+    FramePlan p = plan_frame(*f, 8);
+    uint8_t *tmp = nullptr;
+    size_t scratch = al256(p.p1_elems * 4) + al256(p.i1_elems * 4) + al256(p.p2_elems * 4) + al256(kParts * 8 * 4) * 3;
+    RMPE_CUDA_TRY(cudaMalloc((void **)&tmp, scratch + 4096));
+    uint8_t *u_ptr[1] = {(uint8_t *)up_out_dev};
+    float *p1[1] = {(float *)tmp};
+    float *i1[1] = {(float *)(tmp + al256(p.p1_elems * 4))};
+    float *p2[1] = {(float *)(tmp + al256(p.p1_elems * 4) + al256(p.i1_elems * 4))};
+    rc = launch_heat_up(f, 1, heat_dev, 8, u_ptr, p1, i1, p2, st);
+    if (rc == RMPE_OK && smooth_out_dev) {
+        uint8_t *q = tmp + al256(p.p1_elems * 4) + al256(p.i1_elems * 4) + al256(p.p2_elems * 4);
+        int32_t *cnt = (int32_t *)q;
+        int32_t *keys = (int32_t *)(q + al256(kParts * 8 * 4));
+        double *scores = (double *)(q + 2 * al256(kParts * 8 * 4));
+        cudaMemsetAsync(cnt, 0, al256(kParts * 8 * 4), st);
+        SmoothJobs sj{};
+        sj.j[0].U = up_out_dev; sj.j[0].H = f->height; sj.j[0].W = f->width; sj.j[0].frame = 0;
+        sj.j[0].S_out = smooth_out_dev;
+        int tiles = ((f->height + kST - 1) / kST) * ((f->width + kST - 1) / kST);
+        dim3 grid(tiles, kParts, 1);
+        // thre1 = +inf: no peaks are emitted, only the smoothed map is written; status -> cnt[kParts..]
+        if (p.multi)
+            k_smooth_peaks<double><<<grid, kSmoothThreads, smooth_smem_bytes(true), st>>>(
+                sj, 1.0e300, 1, keys, scores, cnt, cnt + kParts);
+        else
+            k_smooth_peaks<float><<<grid, kSmoothThreads, smooth_smem_bytes(false), st>>>(
+                sj, 3.0e38f, 1, keys, scores, cnt, cnt + kParts);
+        count_launch();
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    if (rc != RMPE_OK) return rc;
+    RMPE_CUDA_TRY(e);
+    RMPE_CUDA_TRY(cudaGetLastError());
+    return RMPE_OK;
+}
+
+extern "C" int rmpe_debug_paf_points(const RmpeFrameDesc *f, const float *paf_dev, int n, const int32_t *cyx_dev,
+                                     double *out_dev, void *stream_) {
+    if (!is_initialised()) { set_error("rmpe_init not called"); return RMPE_E_NOTINIT; }
+    RMPE_REQUIRE(f && paf_dev && cyx_dev && out_dev && n >= 0, "null argument");
+    RMPE_REQUIRE(frame_ok(*f, 8), "frame descriptor");
+    if (n == 0) return RMPE_OK;
+    k_paf_points<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(*f, paf_dev, 8, n, cyx_dev, out_dev);
+    count_launch();
+    RMPE_CUDA_TRY(cudaGetLastError());
+    return RMPE_OK;
+}

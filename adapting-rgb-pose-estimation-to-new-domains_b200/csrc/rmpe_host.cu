@@ -1,0 +1,465 @@
+// Host side of the C ABI: lifetime, error strings, interpolation tables, the augmentation
+// matrix / RNG (T1), the host-buffer wrappers and padRightDownCorner.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "rmpe_common.cuh"
+
+namespace rmpe {
+
+static thread_local char t_error[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_error, sizeof(t_error), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+
+struct Arena {
+    uint8_t *dev = nullptr;
+    size_t bytes = 0;
+    size_t used = 0;
+    int reserve(size_t want) {
+        if (want <= bytes) return RMPE_OK;
+        if (dev) cudaFree(dev);
+        dev = nullptr;
+        bytes = 0;
+        size_t sz = want + (want >> 2) + (1 << 20);
+        cudaError_t e = cudaMalloc((void **)&dev, sz);
+        if (e != cudaSuccess) {
+            set_error("arena cudaMalloc(%zu) failed: %s", sz, cudaGetErrorString(e));
+            return RMPE_E_NOMEM;
+        }
+        bytes = sz;
+        return RMPE_OK;
+    }
+    void reset() { used = 0; }
+    void *take(size_t n) {
+        size_t off = (used + 255) & ~(size_t)255;
+        used = off + n + 16;  // 16 bytes of slack behind every block (bulk-copy over-read)
+        return dev + off;
+    }
+    static size_t need(size_t n) { return ((n + 16 + 255) & ~(size_t)255) + 256; }
+};
+
+struct State {
+    bool init = false;
+    int device = -1;
+    DeviceTables tab{};
+    void *tab_mem = nullptr;
+    Arena arena;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+};
+static State g;
+
+bool is_initialised() { return g.init; }
+const DeviceTables &tables() { return g.tab; }
+
+// OpenCV initInterTab2D(INTER_CUBIC, fixpt=true): [ay][ax][ky][kx] int16, every 4x4 sums to 32768
+static void build_bicubic_tables(std::vector<int16_t> &t16, std::vector<uint32_t> &tdp) {
+    float tab1[32][4];
+    for (int i = 0; i < 32; i++) cubic_coeffs((float)i * (1.0f / 32.0f), tab1[i]);
+    t16.assign(32 * 32 * 16, 0);
+    tdp.assign(32 * 32 * 8, 0);
+    for (int i = 0; i < 32; i++)
+        for (int j = 0; j < 32; j++) {
+            int it[4][4];
+            int isum = 0;
+            for (int k1 = 0; k1 < 4; k1++) {
+                float vy = tab1[i][k1];
+                for (int k2 = 0; k2 < 4; k2++) {
+                    float v = vy * tab1[j][k2];
+                    long iv = lrintf(v * 32768.0f);
+                    if (iv > 32767) iv = 32767;
+                    if (iv < -32768) iv = -32768;
+                    it[k1][k2] = (int)iv;
+                    isum += (int)iv;
+                }
+            }
+            if (isum != 32768) {
+                int diff = isum - 32768;
+                int Mk1 = 2, Mk2 = 2, mk1 = 2, mk2 = 2;
+                for (int k1 = 2; k1 < 4; k1++)
+                    for (int k2 = 2; k2 < 4; k2++) {
+                        if (it[k1][k2] < it[mk1][mk2]) { mk1 = k1; mk2 = k2; }
+                        else if (it[k1][k2] > it[Mk1][Mk2]) { Mk1 = k1; Mk2 = k2; }
+                    }
+                if (diff < 0) it[Mk1][Mk2] = (int16_t)(it[Mk1][Mk2] - diff);
+                else it[mk1][mk2] = (int16_t)(it[mk1][mk2] - diff);
+            }
+            int16_t *o = &t16[(i * 32 + j) * 16];
+            uint32_t *d = &tdp[(i * 32 + j) * 8];
+            for (int k1 = 0; k1 < 4; k1++) {
+                uint32_t hi = 0, lo = 0;
+                for (int k2 = 0; k2 < 4; k2++) {
+                    int w = it[k1][k2];
+                    o[k1 * 4 + k2] = (int16_t)w;
+                    int wh = w >> 8;          // arithmetic: w = 256*wh + wl, wl in [0,255]
+                    int wl = w & 255;
+                    hi |= (uint32_t)(wh & 255) << (8 * k2);
+                    lo |= (uint32_t)wl << (8 * k2);
+                }
+                d[k1 * 2 + 0] = hi;
+                d[k1 * 2 + 1] = lo;
+            }
+        }
+}
+
+}  // namespace rmpe
+
+using namespace rmpe;
+
+extern "C" int rmpe_init(int device) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (g.init) {
+        if (device != g.device) { set_error("already initialised on device %d", g.device); return RMPE_E_BADARG; }
+        return RMPE_OK;
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("no CUDA device available (%s): this library has no CPU path", cudaGetErrorString(e));
+        return RMPE_E_CUDA;
+    }
+    RMPE_REQUIRE(device >= 0 && device < n, "device index out of range");
+    RMPE_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RMPE_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return RMPE_E_CUDA;
+    }
+    std::vector<int16_t> t16;
+    std::vector<uint32_t> tdp;
+    build_bicubic_tables(t16, tdp);
+    size_t b16 = t16.size() * sizeof(int16_t), bdp = tdp.size() * sizeof(uint32_t);
+    RMPE_CUDA_TRY(cudaMalloc(&g.tab_mem, b16 + bdp));
+    RMPE_CUDA_TRY(cudaMemcpy(g.tab_mem, t16.data(), b16, cudaMemcpyHostToDevice));
+    RMPE_CUDA_TRY(cudaMemcpy((uint8_t *)g.tab_mem + b16, tdp.data(), bdp, cudaMemcpyHostToDevice));
+    g.tab.bicubic_i16 = (const int16_t *)g.tab_mem;
+    g.tab.bicubic_dp4a = (const uint32_t *)((uint8_t *)g.tab_mem + b16);
+    g.tab.sm_count = prop.multiProcessorCount;
+    RMPE_CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    g.device = device;
+    g.init = true;
+    return RMPE_OK;
+}
+
+extern "C" void rmpe_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!g.init) return;
+    cudaSetDevice(g.device);
+    cudaDeviceSynchronize();
+    if (g.tab_mem) cudaFree(g.tab_mem);
+    if (g.arena.dev) cudaFree(g.arena.dev);
+    if (g.stream) cudaStreamDestroy(g.stream);
+    g.init = false; g.device = -1; g.tab = DeviceTables{}; g.tab_mem = nullptr;
+    g.arena = Arena{}; g.stream = nullptr;
+}
+
+extern "C" const char *rmpe_last_error(void) { return t_error; }
+extern "C" int rmpe_abi_version(void) { return RMPE_ABI_VERSION; }
+extern "C" int rmpe_device(void) { return g.init ? g.device : -1; }
+extern "C" int64_t rmpe_launch_count(void) { return g_launches.load(); }
+
+// test hook: copies the host-built int16 table out (32*32*16 entries); no GPU needed
+extern "C" int rmpe_debug_bicubic_table(int16_t *out) {
+    std::vector<int16_t> t16;
+    std::vector<uint32_t> tdp;
+    build_bicubic_tables(t16, tdp);
+    memcpy(out, t16.data(), t16.size() * sizeof(int16_t));
+    return RMPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// T1: AugmentSelection.affine (py_rmpe_transformer.py:39-78), closed form of the five-matrix
+// product with the rounding sequence of the numpy chain (pinned in
+// tests/test_host_logic.py against the reference's own chain)
+// ------------------------------------------------------------------------------------------
+extern "C" int rmpe_aug_affine(int n, const uint8_t *flip, const double *degree, const int32_t *crop_xy,
+                               const double *scale, const double *center_xy, const double *scale_self,
+                               double *M_out) {
+    RMPE_REQUIRE(n >= 0 && flip && degree && crop_xy && scale && center_xy && scale_self && M_out, "null argument");
+    for (int i = 0; i < n; i++) {
+        volatile double rad = degree[i] / 180. * M_PI;
+        double A = scale[i] * cos(rad);
+        double B = scale[i] * sin(rad);
+        double s = 0.6 / scale_self[i] * scale[i];
+        double cx = center_xy[2 * i] + (double)crop_xy[2 * i];
+        double cy = center_xy[2 * i + 1] + (double)crop_xy[2 * i + 1];
+        double f = flip[i] ? -1.0 : 1.0;
+        volatile double fs = f * s;
+        volatile double m00 = fs * A, m01 = fs * B, m10 = s * (-B), m11 = s * A;
+        volatile double p0 = m00 * (-cx), p1 = m10 * (-cx);
+        double m02 = fma(m01, -cy, p0) + 184.0;
+        double m12 = fma(m11, -cy, p1) + 184.0;
+        double *M = M_out + 6 * i;
+        M[0] = m00; M[1] = m01; M[2] = m02; M[3] = m10; M[4] = m11; M[5] = m12;
+    }
+    return RMPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// AugmentSelection.random (py_rmpe_transformer.py:19-27) with CPython's Mersenne Twister
+// ------------------------------------------------------------------------------------------
+namespace {
+struct MT {
+    uint32_t mt[624];
+    int idx;
+    void init_genrand(uint32_t s) {
+        mt[0] = s;
+        for (int i = 1; i < 624; i++) mt[i] = 1812433253U * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        idx = 624;
+    }
+    void init_by_array(const uint32_t *key, int len) {
+        init_genrand(19650218U);
+        int i = 1, j = 0;
+        int k = 624 > len ? 624 : len;
+        for (; k; k--) {
+            mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525U)) + key[j] + (uint32_t)j;
+            i++; j++;
+            if (i >= 624) { mt[0] = mt[623]; i = 1; }
+            if (j >= len) j = 0;
+        }
+        for (k = 623; k; k--) {
+            mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941U)) - (uint32_t)i;
+            i++;
+            if (i >= 624) { mt[0] = mt[623]; i = 1; }
+        }
+        mt[0] = 0x80000000U;
+    }
+    uint32_t next() {
+        if (idx >= 624) {
+            for (int kk = 0; kk < 624; kk++) {
+                uint32_t y = (mt[kk] & 0x80000000U) | (mt[(kk + 1) % 624] & 0x7fffffffU);
+                mt[kk] = mt[(kk + 397) % 624] ^ (y >> 1) ^ ((y & 1U) ? 0x9908b0dfU : 0U);
+            }
+            idx = 0;
+        }
+        uint32_t y = mt[idx++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680U;
+        y ^= (y << 15) & 0xefc60000U;
+        y ^= (y >> 18);
+        return y;
+    }
+    double random() {
+        uint32_t a = next() >> 5, b = next() >> 6;
+        return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+    }
+    double uniform(double lo, double hi) { return lo + (hi - lo) * random(); }
+};
+}  // namespace
+
+extern "C" int rmpe_aug_random(int n, const uint64_t *seeds, uint8_t *flip, double *degree, int32_t *crop_xy,
+                               double *scale) {
+    RMPE_REQUIRE(n >= 0 && seeds && flip && degree && crop_xy && scale, "null argument");
+    for (int i = 0; i < n; i++) {
+        MT r;
+        uint32_t key[2] = {(uint32_t)(seeds[i] & 0xffffffffU), (uint32_t)(seeds[i] >> 32)};
+        r.init_by_array(key, key[1] ? 2 : 1);
+        flip[i] = r.uniform(0., 1.) > 0.5 ? 1 : 0;
+        degree[i] = r.uniform(-1., 1.) * 40.;
+        // scale_prob = 1: "scale improbability"; the condition is drawn first, the value only if it fires
+        if (r.uniform(0., 1.) > 1.0) scale[i] = (1.1 - 0.5) * r.uniform(0., 1.) + 0.5;
+        else scale[i] = 1.;
+        crop_xy[2 * i] = (int32_t)(r.uniform(-1., 1.) * 40.);
+        crop_xy[2 * i + 1] = (int32_t)(r.uniform(-1., 1.) * 40.);
+    }
+    return RMPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer GT wrapper
+// ------------------------------------------------------------------------------------------
+extern "C" int rmpe_gt_batch_host(const RmpeGtBatchHost *h) {
+    if (!g.init) { set_error("rmpe_init not called"); return RMPE_E_NOTINIT; }
+    RMPE_REQUIRE(h != nullptr, "descriptor is null");
+    RMPE_REQUIRE(h->batch >= 0, "negative batch");
+    if (h->batch == 0) return RMPE_OK;
+    std::lock_guard<std::mutex> lk(g.mu);
+    RMPE_CUDA_TRY(cudaSetDevice(g.device));
+    const int B = h->batch;
+    const bool no_transform = (h->flags & RMPE_GT_NO_TRANSFORM) != 0;
+    const bool no_warp = (h->flags & RMPE_GT_NO_WARP) != 0 || no_transform;
+    const bool f64 = (h->flags & RMPE_GT_LABELS_F64) != 0;
+    const size_t esz = f64 ? 8 : 4;
+    const size_t img_b = no_warp ? 0 : (size_t)B * h->src_height * h->src_width * 3;
+    const size_t msk_b = no_transform ? 0 : (size_t)B * h->src_height * h->src_width;
+    const size_t jnt_b = (size_t)B * h->max_persons * kParts * 3 * sizeof(double);
+    const size_t oimg_b = no_warp ? 0 : (size_t)B * 3 * kOutW * kOutH;
+    const size_t omsk_b = (size_t)B * kCells * esz;
+    const size_t olab_b = (size_t)B * kLayers * kCells * esz;  // always produced: the rasteriser also writes the joints
+    const size_t ocnt_b = h->out_count ? (size_t)B * kLimbs * kCells * sizeof(int32_t) : 0;
+    if (!no_transform) RMPE_REQUIRE(h->src_mask && h->M && h->flip && h->src_height > 0 && h->src_width > 0, "missing source");
+    if (!no_warp) RMPE_REQUIRE(h->src_img != nullptr, "src_img is null");
+    RMPE_REQUIRE(h->n_persons != nullptr && (h->max_persons == 0 || h->joints != nullptr), "joints / n_persons");
+    RMPE_REQUIRE(!no_transform || h->out_mask != nullptr, "with RMPE_GT_NO_TRANSFORM out_mask is the input mask");
+
+    size_t need = Arena::need(img_b) + Arena::need(msk_b) + Arena::need(B * sizeof(RmpeSrcDesc)) + Arena::need(jnt_b) * 2 +
+                  Arena::need(B * 4) * 2 + Arena::need(B * 48) + Arena::need(B) + Arena::need(oimg_b) +
+                  Arena::need(omsk_b) + Arena::need(olab_b) + Arena::need(ocnt_b);
+    int rc = g.arena.reserve(need);
+    if (rc != RMPE_OK) return rc;
+    g.arena.reset();
+    cudaStream_t st = g.stream;
+
+    RmpeGtBatch d;
+    memset(&d, 0, sizeof(d));
+    d.batch = B; d.max_persons = h->max_persons; d.flags = h->flags;
+    uint8_t *d_img = (uint8_t *)g.arena.take(img_b);
+    uint8_t *d_msk = (uint8_t *)g.arena.take(msk_b);
+    RmpeSrcDesc *d_desc = (RmpeSrcDesc *)g.arena.take(B * sizeof(RmpeSrcDesc));
+    double *d_j = (double *)g.arena.take(jnt_b);
+    double *d_jo = (double *)g.arena.take(jnt_b);
+    int32_t *d_np = (int32_t *)g.arena.take(B * 4);
+    int32_t *d_st = (int32_t *)g.arena.take(B * 4);
+    double *d_M = (double *)g.arena.take(B * 48);
+    uint8_t *d_flip = (uint8_t *)g.arena.take(B);
+    uint8_t *d_oimg = (uint8_t *)g.arena.take(oimg_b);
+    void *d_omsk = g.arena.take(omsk_b);
+    void *d_olab = g.arena.take(olab_b);
+    int32_t *d_ocnt = (int32_t *)g.arena.take(ocnt_b);
+
+    std::vector<RmpeSrcDesc> desc(B);
+    for (int i = 0; i < B; i++) {
+        desc[i].img_offset = (int64_t)i * h->src_height * h->src_width * 3;
+        desc[i].mask_offset = (int64_t)i * h->src_height * h->src_width;
+        desc[i].height = h->src_height; desc[i].width = h->src_width;
+        desc[i].img_pitch = 3 * h->src_width; desc[i].mask_pitch = h->src_width;
+    }
+    if (img_b) RMPE_CUDA_TRY(cudaMemcpyAsync(d_img, h->src_img, img_b, cudaMemcpyHostToDevice, st));
+    if (msk_b) RMPE_CUDA_TRY(cudaMemcpyAsync(d_msk, h->src_mask, msk_b, cudaMemcpyHostToDevice, st));
+    RMPE_CUDA_TRY(cudaMemcpyAsync(d_desc, desc.data(), B * sizeof(RmpeSrcDesc), cudaMemcpyHostToDevice, st));
+    if (jnt_b) RMPE_CUDA_TRY(cudaMemcpyAsync(d_j, h->joints, jnt_b, cudaMemcpyHostToDevice, st));
+    RMPE_CUDA_TRY(cudaMemcpyAsync(d_np, h->n_persons, B * 4, cudaMemcpyHostToDevice, st));
+    if (!no_transform) {
+        RMPE_CUDA_TRY(cudaMemcpyAsync(d_M, h->M, B * 48, cudaMemcpyHostToDevice, st));
+        RMPE_CUDA_TRY(cudaMemcpyAsync(d_flip, h->flip, B, cudaMemcpyHostToDevice, st));
+    } else {
+        RMPE_CUDA_TRY(cudaMemcpyAsync(d_omsk, h->out_mask, omsk_b, cudaMemcpyHostToDevice, st));
+    }
+    d.src_img = d_img; d.src_mask = d_msk; d.src_desc = d_desc; d.joints = d_j; d.n_persons = d_np;
+    d.M = d_M; d.flip = d_flip;
+    d.out_img = no_warp ? nullptr : d_oimg; d.out_mask = d_omsk; d.out_labels = d_olab;
+    d.out_joints = d_jo; d.out_count = h->out_count ? d_ocnt : nullptr; d.status = d_st;
+    rc = rmpe_gt_batch(&d, st);
+    if (rc != RMPE_OK) return rc;
+    if (h->out_img && oimg_b) RMPE_CUDA_TRY(cudaMemcpyAsync(h->out_img, d_oimg, oimg_b, cudaMemcpyDeviceToHost, st));
+    if (h->out_mask && !no_transform) RMPE_CUDA_TRY(cudaMemcpyAsync(h->out_mask, d_omsk, omsk_b, cudaMemcpyDeviceToHost, st));
+    if (h->out_labels) RMPE_CUDA_TRY(cudaMemcpyAsync(h->out_labels, d_olab, olab_b, cudaMemcpyDeviceToHost, st));
+    if (h->out_joints && jnt_b) RMPE_CUDA_TRY(cudaMemcpyAsync(h->out_joints, d_jo, jnt_b, cudaMemcpyDeviceToHost, st));
+    if (h->out_count) RMPE_CUDA_TRY(cudaMemcpyAsync(h->out_count, d_ocnt, ocnt_b, cudaMemcpyDeviceToHost, st));
+    if (h->status) RMPE_CUDA_TRY(cudaMemcpyAsync(h->status, d_st, B * 4, cudaMemcpyDeviceToHost, st));
+    RMPE_CUDA_TRY(cudaStreamSynchronize(st));
+    return RMPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// U1: util.padRightDownCorner (util.py:57-77)
+// ------------------------------------------------------------------------------------------
+namespace rmpe {
+__global__ void k_pad_rd(const uint8_t *__restrict__ src, int H, int W, int C, int Hp, int Wp, int pad_value,
+                         uint8_t *__restrict__ dst) {
+    size_t n = (size_t)Hp * Wp * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        size_t row = i / ((size_t)Wp * C);
+        size_t rem = i - row * (size_t)Wp * C;
+        int x = (int)(rem / C);
+        dst[i] = (row < (size_t)H && x < W) ? src[(row * W + x) * C + (rem - (size_t)x * C)] : (uint8_t)pad_value;
+    }
+}
+}  // namespace rmpe
+
+extern "C" int rmpe_pad_right_down_corner(const uint8_t *src_dev, int height, int width, int channels, int stride,
+                                          int pad_value, uint8_t *dst_dev, int *pad4_out, void *stream) {
+    if (!g.init) { set_error("rmpe_init not called"); return RMPE_E_NOTINIT; }
+    RMPE_REQUIRE(src_dev && dst_dev && pad4_out && height > 0 && width > 0 && channels > 0 && stride > 0, "bad argument");
+    int pd = (height % stride == 0) ? 0 : stride - height % stride;
+    int pr = (width % stride == 0) ? 0 : stride - width % stride;
+    pad4_out[0] = 0; pad4_out[1] = 0; pad4_out[2] = pd; pad4_out[3] = pr;
+    size_t n = (size_t)(height + pd) * (width + pr) * channels;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_pad_rd<<<blocks, 256, 0, (cudaStream_t)stream>>>(src_dev, height, width, channels, height + pd, width + pr,
+                                                        pad_value, dst_dev);
+    count_launch();
+    RMPE_CUDA_TRY(cudaGetLastError());
+    return RMPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer decode wrapper
+// ------------------------------------------------------------------------------------------
+extern "C" int rmpe_decode_batch_host(const RmpeDecodeBatchHost *h) {
+    if (!g.init) { set_error("rmpe_init not called"); return RMPE_E_NOTINIT; }
+    RMPE_REQUIRE(h != nullptr, "descriptor is null");
+    RMPE_REQUIRE(h->batch >= 0, "negative batch");
+    if (h->batch == 0) return RMPE_OK;
+    RMPE_REQUIRE(h->heat && h->paf && h->frames, "blobs / frames");
+    RMPE_REQUIRE(h->candidate && h->n_peaks && h->subset && h->n_subset, "candidate / subset outputs");
+    RMPE_REQUIRE(h->max_peaks > 0 && h->max_peaks <= 1024 && h->max_cand > 0 && h->max_cand <= 4096 &&
+                     h->max_persons > 0 && h->max_persons <= 128, "capacities");
+    std::lock_guard<std::mutex> lk(g.mu);
+    RMPE_CUDA_TRY(cudaSetDevice(g.device));
+    const int B = h->batch, MP = h->max_peaks, MC = h->max_cand, MS = h->max_persons;
+    size_t ws_bytes = rmpe_decode_workspace_bytes(B, h->frames, MP, MC);
+    const size_t cand_b = (size_t)B * kParts * MP * 4 * 8, npk_b = (size_t)B * kParts * 4;
+    const size_t conn_b = (size_t)B * kLimbs * MP * 5 * 8, nconn_b = (size_t)B * kLimbs * 4;
+    const size_t lc_b = h->limb_cand ? (size_t)B * kLimbs * MC * 4 * 8 : 0;
+    const size_t sub_b = (size_t)B * MS * 20 * 8;
+    size_t need = Arena::need(h->heat_elems * 4) + Arena::need(h->paf_elems * 4) + Arena::need(B * sizeof(RmpeFrameDesc)) +
+                  Arena::need(cand_b) + Arena::need(npk_b) + Arena::need(conn_b) + Arena::need(nconn_b) * 2 +
+                  Arena::need(lc_b) + Arena::need(sub_b) + Arena::need(B * 4) * 2 + Arena::need(ws_bytes);
+    int rc = g.arena.reserve(need);
+    if (rc != RMPE_OK) return rc;
+    g.arena.reset();
+    cudaStream_t st = g.stream;
+    float *d_heat = (float *)g.arena.take(h->heat_elems * 4);
+    float *d_paf = (float *)g.arena.take(h->paf_elems * 4);
+    RmpeFrameDesc *d_fr = (RmpeFrameDesc *)g.arena.take(B * sizeof(RmpeFrameDesc));
+    double *d_cand = (double *)g.arena.take(cand_b);
+    int32_t *d_npk = (int32_t *)g.arena.take(npk_b);
+    double *d_conn = (double *)g.arena.take(conn_b);
+    int32_t *d_nconn = (int32_t *)g.arena.take(nconn_b);
+    int32_t *d_nlc = (int32_t *)g.arena.take(nconn_b);
+    double *d_lc = lc_b ? (double *)g.arena.take(lc_b) : nullptr;
+    double *d_sub = (double *)g.arena.take(sub_b);
+    int32_t *d_nsub = (int32_t *)g.arena.take(B * 4);
+    int32_t *d_st = (int32_t *)g.arena.take(B * 4);
+    void *d_ws = g.arena.take(ws_bytes);
+    RMPE_CUDA_TRY(cudaMemcpyAsync(d_heat, h->heat, h->heat_elems * 4, cudaMemcpyHostToDevice, st));
+    RMPE_CUDA_TRY(cudaMemcpyAsync(d_paf, h->paf, h->paf_elems * 4, cudaMemcpyHostToDevice, st));
+    RMPE_CUDA_TRY(cudaMemcpyAsync(d_fr, h->frames, B * sizeof(RmpeFrameDesc), cudaMemcpyHostToDevice, st));
+    RMPE_CUDA_TRY(cudaMemsetAsync(d_npk, 0, npk_b, st));
+    RmpeDecodeBatch d;
+    memset(&d, 0, sizeof(d));
+    d.batch = B; d.max_peaks = MP; d.max_cand = MC; d.max_persons = MS; d.stride = h->stride; d.flags = h->flags;
+    d.thre1 = h->thre1; d.thre2 = h->thre2;
+    d.heat = d_heat; d.paf = d_paf; d.frames = d_fr; d.frames_host = h->frames;
+    d.candidate = d_cand; d.n_peaks = d_npk; d.connections = d_conn; d.n_conn = d_nconn;
+    d.limb_cand = d_lc; d.n_limb_cand = d_nlc; d.subset = d_sub; d.n_subset = d_nsub; d.status = d_st;
+    d.workspace = d_ws; d.workspace_bytes = ws_bytes;
+    rc = rmpe_decode_batch(&d, st);
+    if (rc != RMPE_OK) return rc;
+    RMPE_CUDA_TRY(cudaMemcpyAsync(h->candidate, d_cand, cand_b, cudaMemcpyDeviceToHost, st));
+    RMPE_CUDA_TRY(cudaMemcpyAsync(h->n_peaks, d_npk, npk_b, cudaMemcpyDeviceToHost, st));
+    if (h->connections) RMPE_CUDA_TRY(cudaMemcpyAsync(h->connections, d_conn, conn_b, cudaMemcpyDeviceToHost, st));
+    if (h->n_conn) RMPE_CUDA_TRY(cudaMemcpyAsync(h->n_conn, d_nconn, nconn_b, cudaMemcpyDeviceToHost, st));
+    if (h->limb_cand) RMPE_CUDA_TRY(cudaMemcpyAsync(h->limb_cand, d_lc, lc_b, cudaMemcpyDeviceToHost, st));
+    if (h->n_limb_cand) RMPE_CUDA_TRY(cudaMemcpyAsync(h->n_limb_cand, d_nlc, nconn_b, cudaMemcpyDeviceToHost, st));
+    RMPE_CUDA_TRY(cudaMemcpyAsync(h->subset, d_sub, sub_b, cudaMemcpyDeviceToHost, st));
+    RMPE_CUDA_TRY(cudaMemcpyAsync(h->n_subset, d_nsub, B * 4, cudaMemcpyDeviceToHost, st));
+    if (h->status) RMPE_CUDA_TRY(cudaMemcpyAsync(h->status, d_st, B * 4, cudaMemcpyDeviceToHost, st));
+    RMPE_CUDA_TRY(cudaStreamSynchronize(st));
+    return RMPE_OK;
+}

@@ -1,0 +1,110 @@
+"""Drop-in for the decode functions of the reference's eval/eval_coco2014_multi_modes.py:
+process_single_scale (:263-443) and process_multi_scale (:58-261), same signatures and return
+value (canvas, candidate (N,4) f64, subset (M,20) f64).
+
+Everything after `model.predict` -- blob up-sampling, 4-scale average, sigma=3 smoothing, peak
+test, PAF line-integral scoring, greedy matching, person assembly and pruning -- runs in the
+sm_100a kernels behind include/rmpe_b200.h (rmpe_decode_batch_host).  Only the canvas drawing
+(cv2.circle / fillConvexPoly, reference :417-441) stays on OpenCV; pass draw=False to skip it.
+`decode_frames` decodes many frames per call.
+"""
+import math
+
+import cv2
+import numpy as np
+
+from .. import batch as _batch
+from .. import _lib as L
+from ..util import padRightDownCorner
+
+orderCOCO = [0, 1, 15, 14, 17, 16, 5, 2, 6, 3, 7, 4, 11, 8, 12, 9, 13, 10]
+
+# 1-based part pairs per limb and the (x, y) channel pair of each limb in the 57-channel stack
+limbSeq = [[2, 3], [2, 6], [3, 4], [4, 5], [6, 7], [7, 8], [2, 9], [9, 10],
+           [10, 11], [2, 12], [12, 13], [13, 14], [2, 1], [1, 15], [15, 17],
+           [1, 16], [16, 18], [3, 17], [6, 18]]
+mapIdx = [[31, 32], [39, 40], [33, 34], [35, 36], [41, 42], [43, 44], [19, 20], [21, 22],
+          [23, 24], [25, 26], [27, 28], [29, 30], [47, 48], [49, 50], [53, 54], [51, 52],
+          [55, 56], [37, 38], [45, 46]]
+
+colors = [[255, 0, 0], [255, 85, 0], [255, 170, 0], [255, 255, 0], [170, 255, 0], [85, 255, 0],
+          [0, 255, 0], [0, 255, 85], [0, 255, 170], [0, 255, 255], [0, 170, 255], [0, 85, 255],
+          [0, 0, 255], [85, 0, 255], [170, 0, 255], [255, 0, 255], [255, 0, 170], [255, 0, 85]]
+
+
+def _raise_status(status):
+    if status & L.ST_FOUND_GT2:
+        # the reference indexes subset_idx[found] with found == 2 here (:192-195)
+        raise IndexError("list assignment index out of range")
+    if status & (L.ST_PEAK_OVERFLOW | L.ST_CAND_OVERFLOW | L.ST_PERSON_OVERFLOW):
+        raise OverflowError("decode capacity exceeded (status 0x%x): raise max_peaks/max_cand/max_persons" % status)
+
+
+def decode_frames(frames, params, model_params=None, **caps):
+    """frames: list of dict(H, W, scales=[(paf, heat, pad_down, pad_right), ...]) (see
+    batch.make_frames).  Returns the list of result dicts of batch.decode_batch_host."""
+    stride = 8 if model_params is None else int(model_params['stride'])
+    return _batch.decode_batch_host(frames, thre1=params['thre1'], thre2=params['thre2'], stride=stride, **caps)
+
+
+def draw_canvas(canvas, candidate, subset, n_peaks):
+    """Reference drawing tail (:417-441): circles on every peak, blended limb ellipses."""
+    off = 0
+    for i in range(18):
+        for j in range(int(n_peaks[i])):
+            x, y = int(candidate[off + j, 0]), int(candidate[off + j, 1])
+            cv2.circle(canvas, (x, y), 4, colors[i], thickness=-1)
+        off += int(n_peaks[i])
+    stickwidth = 4
+    for i in range(17):
+        for n in range(len(subset)):
+            index = subset[n][np.array(limbSeq[i]) - 1]
+            if -1 in index:
+                continue
+            cur_canvas = canvas.copy()
+            Y = candidate[index.astype(int), 0]
+            X = candidate[index.astype(int), 1]
+            mX, mY = np.mean(X), np.mean(Y)
+            length = ((X[0] - X[1]) ** 2 + (Y[0] - Y[1]) ** 2) ** 0.5
+            angle = math.degrees(math.atan2(X[0] - X[1], Y[0] - Y[1]))
+            polygon = cv2.ellipse2Poly((int(mY), int(mX)), (int(length / 2), stickwidth), int(angle), 0, 360, 1)
+            cv2.fillConvexPoly(cur_canvas, polygon, colors[i])
+            canvas = cv2.addWeighted(canvas, 0.4, cur_canvas, 0.6, 0)
+    return canvas
+
+
+def _finish(input_image, oriImg, r, draw):
+    _raise_status(r["status"])
+    candidate, subset = r["candidate"], r["subset"]
+    canvas = None
+    if draw:
+        canvas = cv2.imread(input_image) if isinstance(input_image, str) else oriImg.copy()
+        canvas = draw_canvas(canvas, candidate, subset, r["n_peaks"])
+    return canvas, candidate, subset
+
+
+def process_single_scale(input_image, model, params, model_params, draw=True, **caps):
+    oriImg = cv2.imread(input_image) if isinstance(input_image, str) else np.asarray(input_image)  # B,G,R order
+    input_img = np.transpose(np.float32(oriImg[:, :, :, np.newaxis]), (3, 0, 1, 2))  # (1, H, W, 3)
+    output_blobs = model.predict(input_img)
+    heatmap = np.squeeze(output_blobs[1], axis=0)   # output 1 is heatmaps
+    paf = np.squeeze(output_blobs[0], axis=0)       # output 0 is PAFs
+    frame = dict(H=oriImg.shape[0], W=oriImg.shape[1], scales=[(paf, heatmap, 0, 0)])
+    r = decode_frames([frame], params, model_params, **caps)[0]
+    return _finish(input_image, oriImg, r, draw)
+
+
+def process_multi_scale(input_image, model, params, model_params, draw=True, **caps):
+    oriImg = cv2.imread(input_image) if isinstance(input_image, str) else np.asarray(input_image)
+    scale_search = list(params['scale_search'])
+    multiplier = [x * model_params['boxsize'] / oriImg.shape[0] for x in scale_search]
+    scales = []
+    for scale in multiplier:
+        imageToTest = cv2.resize(oriImg, (0, 0), fx=scale, fy=scale, interpolation=cv2.INTER_CUBIC)
+        imageToTest_padded, pad = padRightDownCorner(imageToTest, model_params['stride'], model_params['padValue'])
+        input_img = np.transpose(np.float32(imageToTest_padded[:, :, :, np.newaxis]), (3, 0, 1, 2))
+        output_blobs = model.predict(input_img)
+        scales.append((np.squeeze(output_blobs[0], axis=0), np.squeeze(output_blobs[1], axis=0), pad[2], pad[3]))
+    frame = dict(H=oriImg.shape[0], W=oriImg.shape[1], scales=scales)
+    r = decode_frames([frame], params, model_params, **caps)[0]
+    return _finish(input_image, oriImg, r, draw)
