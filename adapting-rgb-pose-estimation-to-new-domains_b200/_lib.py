@@ -15,6 +15,7 @@ GT_LABELS_F64 = 0x2
 GT_NO_TRANSFORM = 0x4
 GT_NO_WARP = 0x8
 GT_SIMPLE_KERNELS = 0x10
+GT_WARP_ONLY = 0x20
 
 ST_ZERO_LIMB = 0x1
 ST_PEAK_OVERFLOW = 0x2

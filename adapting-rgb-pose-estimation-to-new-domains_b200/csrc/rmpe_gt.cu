@@ -674,7 +674,8 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
         }
         count_launch();
     }
-    if (!no_transform) {
+    const bool warp_only = (b->flags & RMPE_GT_WARP_ONLY) != 0;
+    if (!no_transform && !warp_only) {
         MaskArgs ma;
         ma.src_mask = b->src_mask; ma.desc = b->src_desc; ma.M = b->M; ma.out_mask = b->out_mask;
         ma.tab = T.bicubic_i16; ma.f64 = (b->flags & RMPE_GT_LABELS_F64) ? 1 : 0;
@@ -682,7 +683,7 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
         k_mask46<<<grid, 128, 0, st>>>(ma);
         count_launch();
     }
-    if (b->out_labels) {
+    if (b->out_labels && !warp_only) {
         RasterArgs ra;
         ra.joints = b->joints; ra.n_persons = b->n_persons; ra.M = b->M; ra.flip = b->flip;
         ra.mask = b->out_mask; ra.labels = b->out_labels; ra.out_joints = b->out_joints;

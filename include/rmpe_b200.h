@@ -98,6 +98,7 @@ typedef struct RmpeSrcDesc {
                                       Heatmapper.create_heatmaps(joints, mask) on its own */
 #define RMPE_GT_NO_WARP 0x8        /* skip image warp (labels + mask + joints only) */
 #define RMPE_GT_SIMPLE_KERNELS 0x10 /* debugging: straight-line kernels without smem staging */
+#define RMPE_GT_WARP_ONLY 0x20      /* image warp only (per-kernel timing in bench.py) */
 
 typedef struct RmpeGtBatch {
     int32_t batch;

@@ -1,0 +1,202 @@
+"""GPU parity of the target-generation path, through the C ABI, against the oracle and the
+reference's golden vectors.  Bars (BASELINE.json north_star): warped pixels, mask, joints and PAF
+counts bit-exact; confidence maps / PAF vectors max-abs <= 1e-5."""
+import numpy as np
+import pytest
+
+from cases import GT_CASES, FULL_LABEL_CASES, gt_case_inputs, sha
+from oracle import gt_oracle as go
+
+pytestmark = pytest.mark.gpu
+LABEL_TOL = 1e-5
+
+
+def _run_case(rmpe, s, **kw):
+    flip, deg, crop, scale = s["aug"]
+    M = rmpe.batch.aug_affine([flip], [deg], [crop], [scale], [s["objpos"][0]], [s["scale_provided"][0]])
+    P = s["joints"].shape[0]
+    r = rmpe.batch.gt_batch_host(s["img"][None], s["mask"][None], s["joints"][None], [P], M, [flip],
+                                 want_count=True, **kw)
+    return M[0], r
+
+
+@pytest.mark.parametrize("simple", [False, True], ids=["tile", "simple"])
+@pytest.mark.parametrize("case", GT_CASES, ids=[c[0] for c in GT_CASES])
+def test_gt_matches_reference_golden(rmpe, gt_golden, case, simple):
+    name = case[0]
+    s = gt_case_inputs(case)
+    M, r = _run_case(rmpe, s, f64=True, simple=simple)
+    assert np.array_equal(M, gt_golden[name + "_M"])
+    assert sha(r["img"][0]) == str(gt_golden[name + "_img_sha"]), \
+        "warped image: %d pixels differ in the 16 stored rows" % int((r["img"][0][::23] != gt_golden[name + "_img_rows"]).sum())
+    assert np.array_equal(np.rint(r["mask"][0] * 255).astype(np.uint8), gt_golden[name + "_mask46"])
+    assert sha(r["mask"][0]) == str(gt_golden[name + "_mask_sha"])
+    if s["joints"].shape[0]:
+        assert np.array_equal(r["joints"][0], gt_golden[name + "_joints"])
+    assert np.abs(r["labels"][0].sum(axis=(1, 2)) - gt_golden[name + "_labels_sum"]).max() < 1e-2
+    if name in FULL_LABEL_CASES:
+        assert np.abs(r["labels"][0] - gt_golden[name + "_labels_f32"].astype(np.float64)).max() <= LABEL_TOL + 1e-7
+
+
+@pytest.mark.parametrize("case", GT_CASES, ids=[c[0] for c in GT_CASES])
+def test_gt_matches_oracle(rmpe, case):
+    s = gt_case_inputs(case)
+    M, r = _run_case(rmpe, s, f64=True)
+    flip = s["aug"][0]
+    oimg, omask, oj = go.transform(s["img"], s["mask"], s["joints"], M, flip)
+    olab, ocnt = go.create_heatmaps(oj, omask, return_count=True)
+    assert np.array_equal(r["img"][0], oimg)
+    assert np.array_equal(r["mask"][0], omask)
+    assert np.array_equal(r["joints"][0], oj)
+    assert np.array_equal(r["count"][0], ocnt)                      # PAF counts bit-exact
+    assert np.array_equal(r["labels"][0] != 0, olab != 0) or np.abs(r["labels"][0] - olab).max() <= LABEL_TOL
+    assert np.abs(r["labels"][0] - olab).max() <= LABEL_TOL
+    assert r["status"][0] == 0
+
+
+def test_gt_f32_chw_outputs(rmpe):
+    s = gt_case_inputs(GT_CASES[1])
+    M, r64 = _run_case(rmpe, s, f64=True)
+    _, r32 = _run_case(rmpe, s, f64=False, chw=True)
+    assert r32["labels"].dtype == np.float32 and r32["mask"].dtype == np.float32
+    assert np.array_equal(r32["img"][0], np.transpose(r64["img"][0], (2, 0, 1)))
+    assert np.array_equal(r32["mask"][0], r64["mask"][0].astype(np.float32))
+    assert np.abs(r32["labels"][0] - r64["labels"][0]).max() <= 2e-7
+    assert np.array_equal(r32["count"], r64["count"])
+
+
+def test_background_is_one_minus_max_where_unmasked(rmpe):
+    """The reference's own notebook assertion (check_dataset_iterator.ipynb cell 7)."""
+    s = gt_case_inputs(GT_CASES[2])
+    _, r = _run_case(rmpe, s, f64=False)
+    lab, mask = r["labels"][0], r["mask"][0]
+    on = mask == 1
+    assert on.any()
+    assert np.abs(lab[56][on] - (1 - lab[38:56].max(axis=0))[on]).max() <= 1e-6
+
+
+def test_drop_in_classes_match_golden(rmpe, gt_golden):
+    case = GT_CASES[3]
+    name = case[0]
+    s = gt_case_inputs(case)
+    flip, deg, crop, scale = s["aug"]
+    aug = rmpe.transformer.AugmentSelection(flip, deg, crop, scale)
+    meta = dict(objpos=s["objpos"], scale_provided=s["scale_provided"], joints=s["joints"].copy())
+    img, mask, meta2 = rmpe.transformer.Transformer.transform(s["img"], s["mask"], meta, aug)
+    assert meta2 is meta and img.shape == (368, 368, 3) and mask.shape == (46, 46) and mask.dtype == np.float64
+    assert sha(img) == str(gt_golden[name + "_img_sha"])
+    assert sha(mask) == str(gt_golden[name + "_mask_sha"])
+    assert np.array_equal(meta["joints"], gt_golden[name + "_joints"])          # mutated in place
+    labels = rmpe.heatmapper.Heatmapper().create_heatmaps(meta["joints"], mask)
+    assert labels.shape == (57, 46, 46) and labels.dtype == np.float64
+    assert np.abs(labels.sum(axis=(1, 2)) - gt_golden[name + "_labels_sum"]).max() < 1e-2
+    olab = go.create_heatmaps(meta["joints"], mask)
+    assert np.abs(labels - olab).max() <= LABEL_TOL
+    # iterator glue: one fused call gives the same sample
+    it = rmpe.data_iterator.RawDataIterator(None, shuffle=False, augment=False)
+    meta3 = dict(objpos=s["objpos"], scale_provided=s["scale_provided"], joints=s["joints"].copy())
+    i2, m2, _, l2 = it.transform_data(s["img"], s["mask"], meta3)
+    assert i2.shape == (368, 368, 3) and l2.shape == (57, 46, 46)
+
+
+def test_edge_cases(rmpe):
+    rng = np.random.RandomState(11)
+    # (a) source far larger than the staged footprint (inverse scale 4): falls back to global taps
+    img = rng.randint(0, 256, size=(900, 1200, 3)).astype(np.uint8)
+    mask = rng.randint(0, 2, size=(900, 1200)).astype(np.uint8) * 255
+    joints = rng.uniform(0, 900, size=(1, 2, 18, 3))
+    joints[..., 2] = 1
+    M = rmpe.batch.aug_affine([0], [25.0], [(10, -5)], [1.0], [(600., 450.)], [2.4])
+    r = rmpe.batch.gt_batch_host(img[None], mask[None], joints, [2], M, [0], f64=True)
+    oimg, omask, oj = go.transform(img, mask, joints[0], M[0], False)
+    assert np.array_equal(r["img"][0], oimg) and np.array_equal(r["mask"][0], omask)
+    # (b) tiny source, heavy zoom, odd pitch
+    img = rng.randint(0, 256, size=(37, 53, 3)).astype(np.uint8)
+    mask = rng.randint(0, 256, size=(37, 53)).astype(np.uint8)
+    M = rmpe.batch.aug_affine([1], [-38.0], [(3, 2)], [1.0], [(26., 18.)], [0.08])
+    r = rmpe.batch.gt_batch_host(img[None], mask[None], np.zeros((1, 0, 18, 3)), [0], M, [1], f64=True)
+    oimg, omask, _ = go.transform(img, mask, np.zeros((0, 18, 3)), M[0], True)
+    assert np.array_equal(r["img"][0], oimg) and np.array_equal(r["mask"][0], omask)
+    assert (r["labels"][0][:56] == 0).all()
+    # (c) zero-length limb is skipped and flagged; absent joints (vis 2) are not drawn
+    j = np.zeros((1, 1, 18, 3))
+    j[0, 0, :, 0] = 100
+    j[0, 0, :, 1] = 120
+    j[0, 0, 5:, 2] = 2
+    m1 = np.ones((1, 46, 46))
+    h = rmpe.batch.heatmaps_host(j, [1], m1, f64=True, want_count=True)
+    olab, ocnt = go.create_heatmaps(j[0], m1[0], return_count=True)
+    assert h["status"][0] & 1
+    assert np.array_equal(h["count"][0], ocnt) and np.abs(h["labels"][0] - olab).max() <= LABEL_TOL
+    # (d) singular matrix is flagged, output is all border like cv2
+    M0 = np.zeros((1, 2, 3))
+    r = rmpe.batch.gt_batch_host(img[None], mask[None], np.zeros((1, 0, 18, 3)), [0], M0, [0], f64=True)
+    assert r["status"][0] & 0x20
+    oimg, omask, _ = go.transform(img, mask, np.zeros((0, 18, 3)), M0[0], False)
+    assert np.array_equal(r["img"][0], oimg) and np.array_equal(r["mask"][0], omask)
+
+
+def test_tie_prone_integer_joints_counts_exact(rmpe):
+    """Axis-aligned limbs with integer joints put pixels exactly on dist == 8.0 (fp64 decision)."""
+    rng = np.random.RandomState(3)
+    j = np.zeros((1, 6, 18, 3))
+    j[..., 0] = rng.randint(0, 46, size=(1, 6, 18)) * 8
+    j[..., 1] = rng.randint(0, 46, size=(1, 6, 18)) * 8
+    j[..., 2] = (rng.uniform(size=(1, 6, 18)) < 0.1) * 2.0
+    m = np.ones((1, 46, 46))
+    h = rmpe.batch.heatmaps_host(j, [6], m, f64=True, want_count=True)
+    olab, ocnt = go.create_heatmaps(j[0], m[0], return_count=True)
+    assert np.array_equal(h["count"][0], ocnt)
+    assert np.array_equal(h["labels"][0][:38] != 0, olab[:38] != 0)
+    assert np.abs(h["labels"][0] - olab).max() <= LABEL_TOL
+
+
+def test_full_size_batch_properties(rmpe):
+    """BASELINE config 2 size (batch 256, 3 persons) on device-resident buffers: the staged
+    (TMA bulk copy + dp4a) warp equals the straight-line kernel bit for bit, a handful of samples
+    equal the oracle, and size-independent properties hold for all 256."""
+    import torch
+    B, P = 256, 3
+    b = rmpe.synth.gt_batch(B, n_persons=P, seed0=1000)
+    flip = np.array([a[0] for a in b["augs"]], np.uint8)
+    M = rmpe.batch.aug_affine(flip, [a[1] for a in b["augs"]], [a[2] for a in b["augs"]],
+                              [a[3] for a in b["augs"]], b["centers"], b["scale_self"])
+    plan = rmpe.batch.GtDevicePlan(B, P, want_count=True)
+    plan.upload(b["imgs"], b["masks"], b["joints"], b["n_persons"], M, flip)
+    plan.run(simple=True)
+    torch.cuda.synchronize()
+    img_simple = plan.out_img.cpu().numpy().copy()
+    lab_simple = plan.out_labels.cpu().numpy().copy()
+    plan.out_img.zero_()
+    plan.run(simple=False)
+    torch.cuda.synchronize()
+    img_tile = plan.out_img.cpu().numpy()
+    assert np.array_equal(img_tile, img_simple)
+    assert np.array_equal(plan.out_labels.cpu().numpy(), lab_simple)
+    assert (plan.status.cpu().numpy() == 0).all()
+    lab = plan.out_labels.cpu().numpy()
+    mask = plan.out_mask.cpu().numpy()
+    cnt = plan.out_count.cpu().numpy()
+    # properties: bkg = (1-max heat)*mask; PAF vectors are unit (or zero) where mask==1; count>0 <=> PAF set
+    assert np.abs(lab[:, 56] - (1 - lab[:, 38:56].max(axis=1) / np.where(mask > 0, mask, 1)) * mask).max() <= 2e-6
+    full = mask == 1
+    n2 = lab[:, 0:38:2] ** 2 + lab[:, 1:38:2] ** 2
+    sel = np.broadcast_to(full[:, None], n2.shape)
+    assert np.all((np.abs(n2[sel] - 1) < 1e-5) | (n2[sel] == 0))
+    assert np.array_equal((cnt > 0)[sel], (n2 > 0)[sel])
+    for i in (0, 17, 101, 255):
+        oimg, omask, oj = go.transform(b["imgs"][i], b["masks"][i], b["joints"][i], M[i], bool(flip[i]))
+        assert np.array_equal(img_tile[i], oimg)
+        assert np.array_equal(mask[i], omask.astype(np.float32))
+        olab, ocnt = go.create_heatmaps(oj, omask, return_count=True)
+        assert np.array_equal(cnt[i], ocnt)
+        assert np.abs(lab[i] - olab).max() <= LABEL_TOL
+
+
+def test_crowded_20_persons(rmpe):
+    s = rmpe.synth.gt_sample(77, 20)
+    M, r = _run_case(rmpe, s, f64=True)
+    oimg, omask, oj = go.transform(s["img"], s["mask"], s["joints"], M, s["aug"][0])
+    olab, ocnt = go.create_heatmaps(oj, omask, return_count=True)
+    assert np.array_equal(r["img"][0], oimg) and np.array_equal(r["count"][0], ocnt)
+    assert np.abs(r["labels"][0] - olab).max() <= LABEL_TOL

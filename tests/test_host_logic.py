@@ -1,0 +1,166 @@
+"""CPU: host-side logic and the C-ABI surface (no kernel is launched here)."""
+import ctypes
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+from cases import ROOT
+from oracle import gt_oracle as go
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "rmpe_b200.h")).read()
+    declared = set(re.findall(r"\b(rmpe_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = built_lib.lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), "missing export: " + name
+    assert set(built_lib.lib.EXPORTS) <= declared
+    assert lib.rmpe_abi_version() == 1
+    assert lib.rmpe_device() == -1 or lib.rmpe_device() >= 0
+
+
+def test_struct_layouts_match_header(built_lib):
+    L = built_lib.lib
+    assert ctypes.sizeof(L.SrcDesc) == 32
+    assert ctypes.sizeof(L.FrameDesc) == 144
+    assert L.FRAME_DESC_DTYPE.itemsize == 144 and L.SRC_DESC_DTYPE.itemsize == 32
+    # 6 int32 + 12 pointers
+    assert ctypes.sizeof(L.GtBatchHost) == 6 * 4 + 12 * 8
+    assert ctypes.sizeof(L.GtBatch) == 4 * 4 + 13 * 8
+
+
+def test_no_gpu_fails_loudly(built_lib):
+    """Without a CUDA device rmpe_init reports an error; nothing falls back to the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = built_lib.lib.load()
+    assert lib.rmpe_init(0) != 0
+    assert b"no CPU path" in lib.rmpe_last_error()
+    with pytest.raises(RuntimeError):
+        built_lib.batch.gt_batch_host(np.zeros((1, 8, 8, 3), np.uint8), np.zeros((1, 8, 8), np.uint8),
+                                      np.zeros((1, 1, 18, 3)), [1], np.zeros((1, 2, 3)), [0])
+
+
+def test_aug_affine_matches_reference_chain(built_lib):
+    rnd = random.Random(7)
+    n = 500
+    flip = [rnd.random() > 0.5 for _ in range(n)]
+    deg = [rnd.uniform(-40, 40) for _ in range(n)]
+    crop = [(int(rnd.uniform(-40, 40)), int(rnd.uniform(-40, 40))) for _ in range(n)]
+    scale = [rnd.choice([1.0, rnd.uniform(0.5, 1.1)]) for _ in range(n)]
+    center = [(rnd.uniform(0, 500), rnd.uniform(0, 500)) for _ in range(n)]
+    ss = [rnd.uniform(0.15, 1.6) for _ in range(n)]
+    M = built_lib.batch.aug_affine(flip, deg, crop, scale, center, ss)
+    for i in range(n):
+        ref = go.affine_chain(flip[i], deg[i], crop[i], scale[i], center[i], ss[i])
+        assert np.array_equal(M[i], ref), i
+    # the drop-in class goes through the same call
+    a = built_lib.transformer.AugmentSelection(flip[0], deg[0], crop[0], scale[0]).affine(center[0], ss[0])
+    assert a.shape == (2, 3) and np.array_equal(a, M[0])
+
+
+def test_aug_random_matches_python_random(built_lib):
+    seeds = [0, 1, 2, 17, 123456, 2 ** 31, 2 ** 32 + 5, 2 ** 40 + 3]
+    flip, deg, crop, scale = built_lib.batch.aug_random(seeds)
+    for i, s in enumerate(seeds):
+        random.seed(s)
+        a = built_lib.transformer.AugmentSelection.random()
+        assert (bool(flip[i]), float(deg[i]), (int(crop[i, 0]), int(crop[i, 1])), float(scale[i])) == \
+            (a.flip, a.degree, tuple(a.crop), a.scale), s
+        assert built_lib.synth.random_aug(s) == (a.flip, a.degree, tuple(a.crop), a.scale)
+
+
+def test_bicubic_table_built_by_the_library_is_opencvs(built_lib):
+    lib = built_lib.lib.load()
+    out = np.zeros((32, 32, 4, 4), np.int16)
+    assert lib.rmpe_debug_bicubic_table(out.ctypes.data) == 0
+    assert np.array_equal(out, go.bicubic_tab_i16())
+
+
+def test_config_tables(built_lib):
+    G = built_lib.config.RmpeGlobalConfig
+    assert G.limbs_conn == go.LIMBS_CONN
+    assert [(f - 1, t - 1) for f, t in zip(G.limb_from, G.limb_to)] == G.limbs_conn
+    assert (G.paf_start, G.heat_start, G.bkg_start, G.num_layers) == (0, 38, 56, 57)
+    assert G.leftParts == go.LEFT_PARTS and G.rightParts == go.RIGHT_PARTS
+    names = built_lib.config.check_layer_dictionary()
+    assert len(set(names)) == 57
+    # CUDA-side tables (csrc/rmpe_common.cuh) agree with the Python constants
+    src = open(os.path.join(ROOT, "adapting-rgb-pose-estimation-to-new-domains_b200", "csrc", "rmpe_common.cuh")).read()
+
+    def table(name):
+        m = re.search(name + r"\[[A-Za-z]+\]\s*=\s*\{([^}]*)\}", src)
+        return [int(v) for v in m.group(1).split(",")]
+    assert table("c_limb_from") == [f for f, _ in G.limbs_conn]
+    assert table("c_limb_to") == [t for _, t in G.limbs_conn]
+    partner = list(range(18))
+    for l, r in zip(G.leftParts, G.rightParts):
+        partner[l], partner[r] = r, l
+    assert table("c_flip_partner") == partner
+    dec = built_lib.decode
+    assert table("c_dec_a") == [a - 1 for a, _ in dec.limbSeq]
+    assert table("c_dec_b") == [b - 1 for _, b in dec.limbSeq]
+    assert table("c_dec_paf") == [m[0] - 19 for m in dec.mapIdx]
+    assert all(m[1] == m[0] + 1 for m in dec.mapIdx)
+    # decode limb k reads the PAF channels of the training limb with the same endpoints
+    for k in range(19):
+        tl = (dec.mapIdx[k][0] - 19) // 2
+        assert G.limbs_conn[tl] == (dec.limbSeq[k][0] - 1, dec.limbSeq[k][1] - 1)
+
+
+def test_coco_convert_matches_reference(built_lib):
+    from oracle import ref_shim
+    rng = np.random.RandomState(0)
+    j = rng.uniform(0, 300, size=(5, 17, 3))
+    j[:, :, 2] = rng.randint(0, 3, size=(5, 17))
+    out = built_lib.config.RmpeCocoConfig.convert(j)
+    assert out.shape == (5, 18, 3)
+    if ref_shim.available():
+        assert np.array_equal(out, ref_shim.load().RmpeCocoConfig.convert(j))
+
+
+def test_make_frames_layout(built_lib):
+    f = [dict(H=40, W=48, scales=[(np.zeros((5, 6, 38), np.float32), np.ones((5, 6, 19), np.float32), 0, 0)]),
+         dict(H=30, W=20, scales=[(np.zeros((2, 3, 38), np.float32), np.ones((2, 3, 19), np.float32), 1, 2),
+                                  (np.zeros((4, 5, 38), np.float32), np.ones((4, 5, 19), np.float32), 3, 4)])]
+    desc, heat, paf = built_lib.batch.make_frames(f)
+    assert desc["n_scales"].tolist() == [1, 2]
+    assert desc["heat_offset"][1, 0] == 5 * 6 * 19 and desc["paf_offset"][1, 1] == (5 * 6 + 2 * 3) * 38
+    assert heat.size == (30 + 6 + 20) * 19 and paf.size == (30 + 6 + 20) * 38
+    assert desc["pad_down"][1].tolist() == [1, 3, 0, 0] and desc["pad_right"][1].tolist() == [2, 4, 0, 0]
+
+
+def _shard_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import rmpe_b200
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    shard = rmpe_b200.sub("shard")
+    idx = shard.shard_indices(11, rank, world)
+    local = [dict(index=int(i), payload=np.full((2,), i)) for i in idx]
+    merged = shard.gather_results(local, 11)
+    t = shard.max_over_ranks(float(rank + 1))
+    dist.destroy_process_group()
+    q.put((rank, idx.tolist(), [m["index"] for m in merged], t))
+
+
+def test_sharding_world_size_2_gloo():
+    """N>1 path on CPU: images partition i % world; results gather back in input order; the
+    timing reduction is a max over ranks."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert got[0][1] == [0, 2, 4, 6, 8, 10] and got[1][1] == [1, 3, 5, 7, 9]
+    assert got[0][2] == list(range(11)) and got[1][2] == list(range(11))
+    assert got[0][3] == 2.0 and got[1][3] == 2.0
