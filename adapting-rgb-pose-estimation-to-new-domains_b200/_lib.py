@@ -31,7 +31,8 @@ EXPORTS = [
     "rmpe_aug_affine", "rmpe_aug_random", "rmpe_gt_batch", "rmpe_gt_batch_host",
     "rmpe_decode_workspace_bytes", "rmpe_decode_batch", "rmpe_decode_batch_host",
     "rmpe_debug_heat_maps", "rmpe_debug_paf_points", "rmpe_pad_right_down_corner",
-    "rmpe_launch_count",
+    "rmpe_launch_count", "rmpe_profile_enable", "rmpe_profile_reset", "rmpe_profile_count",
+    "rmpe_profile_get",
 ]
 
 _vp = C.c_void_p
@@ -143,6 +144,12 @@ def load():
     lib.rmpe_debug_paf_points.restype = C.c_int
     lib.rmpe_pad_right_down_corner.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]
     lib.rmpe_pad_right_down_corner.restype = C.c_int
+    lib.rmpe_profile_enable.argtypes = [C.c_int]
+    lib.rmpe_profile_enable.restype = C.c_int
+    lib.rmpe_profile_reset.restype = C.c_int
+    lib.rmpe_profile_count.restype = C.c_int
+    lib.rmpe_profile_get.argtypes = [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.rmpe_profile_get.restype = C.c_int
     lib.rmpe_debug_bicubic_table.argtypes = [_vp]
     lib.rmpe_debug_bicubic_table.restype = C.c_int
     _lib = lib
@@ -170,6 +177,26 @@ def ensure_init(device=None):
     check(lib.rmpe_init(int(device)))
     _inited_device = int(device)
     return lib
+
+
+def profile_enable(on=True, reset=True):
+    lib = load()
+    if reset:
+        check(lib.rmpe_profile_reset())
+    check(lib.rmpe_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """{kernel name: (total device ms, launches)} accumulated since the last reset."""
+    lib = load()
+    out = {}
+    for i in range(lib.rmpe_profile_count()):
+        name = C.create_string_buffer(64)
+        ms = C.c_double()
+        n = C.c_int64()
+        check(lib.rmpe_profile_get(i, name, 64, C.byref(ms), C.byref(n)))
+        out[name.value.decode()] = (ms.value, n.value)
+    return out
 
 
 def ptr(a):

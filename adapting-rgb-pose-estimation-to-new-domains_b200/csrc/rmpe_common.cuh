@@ -18,6 +18,23 @@ namespace rmpe {
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 
+// Per-kernel device timing (rmpe_profile_* in the C ABI): when enabled, a ProfScope brackets one
+// kernel launch with two CUDA events on the launching stream; rmpe_profile_get() resolves them.
+// Disabled (the default) it costs one predictable branch.
+bool prof_enabled();
+void prof_mark(const char *name, cudaStream_t st, bool begin);
+struct ProfScope {
+    const char *name;
+    cudaStream_t st;
+    bool on;
+    ProfScope(const char *n, cudaStream_t s) : name(n), st(s), on(prof_enabled()) {
+        if (on) prof_mark(name, st, true);
+    }
+    ~ProfScope() {
+        if (on) prof_mark(name, st, false);
+    }
+};
+
 #define RMPE_CUDA_TRY(expr)                                                               \
     do {                                                                                  \
         cudaError_t _e = (expr);                                                          \

@@ -693,8 +693,8 @@ static int launch_heat_up(const RmpeFrameDesc *fr, int n, const float *heat, int
             m++;
         }
         if (m) {
-            k_resize_h<<<dim3((maxc + 127) / 128, maxr_h, m), 128, 0, st>>>(jh);
-            k_resize_v<<<dim3((maxc + 127) / 128, maxr_v, m), 128, 0, st>>>(jv);
+            { ProfScope ps("k_resize_h", st); k_resize_h<<<dim3((maxc + 127) / 128, maxr_h, m), 128, 0, st>>>(jh); }
+            { ProfScope ps("k_resize_v", st); k_resize_v<<<dim3((maxc + 127) / 128, maxr_v, m), 128, 0, st>>>(jv); }
             count_launch(2);
         }
     }
@@ -737,10 +737,10 @@ static int launch_heat_up(const RmpeFrameDesc *fr, int n, const float *heat, int
             m++;
         }
         if (!m) continue;
-        k_resize_h<<<dim3((c1 + 127) / 128, r1, m), 128, 0, st>>>(j1);
-        k_resize_v<<<dim3((c1 + 127) / 128, r2, m), 128, 0, st>>>(j2);
-        k_resize_h<<<dim3((c3 + 127) / 128, r2, m), 128, 0, st>>>(j3);
-        k_resize_v<<<dim3((c3 + 127) / 128, r4, m), 128, 0, st>>>(j4);
+        { ProfScope ps("k_resize_h", st); k_resize_h<<<dim3((c1 + 127) / 128, r1, m), 128, 0, st>>>(j1); }
+        { ProfScope ps("k_resize_v", st); k_resize_v<<<dim3((c1 + 127) / 128, r2, m), 128, 0, st>>>(j2); }
+        { ProfScope ps("k_resize_h", st); k_resize_h<<<dim3((c3 + 127) / 128, r2, m), 128, 0, st>>>(j3); }
+        { ProfScope ps("k_resize_v", st); k_resize_v<<<dim3((c3 + 127) / 128, r4, m), 128, 0, st>>>(j4); }
         count_launch(4);
     }
     RMPE_CUDA_TRY(cudaGetLastError());
@@ -853,6 +853,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                 m++;
             }
             dim3 grid(max_tiles, kParts, m);
+            ProfScope ps("k_smooth_peaks", st);
             if (multi)
                 k_smooth_peaks<double><<<grid, kSmoothThreads, smooth_smem_bytes(true), st>>>(
                     sj, b->thre1, MP, raw_key, raw_score, raw_count, b->status);
@@ -864,6 +865,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
         {
             FinalizeJobs fj{};
             for (int i = 0; i < n; i++) fj.W[i] = fr[i].width;
+            ProfScope ps("k_peaks_finalize", st);
             k_peaks_finalize<<<dim3(kParts, n), 256, 0, st>>>(fj, f0, MP, raw_key, raw_score, raw_count, b->candidate,
                                                              b->n_peaks, pk_x, pk_y, pk_s);
             count_launch();
@@ -873,11 +875,18 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
     // limbs + assembly for the whole batch
     {
         size_t smem = (size_t)MC * 12 + 2 * kMaxPeaksCap;
-        k_limbs<<<dim3(kLimbs, B), kLimbThreads, smem, st>>>(b->frames, 0, b->paf, b->stride, b->thre2, MP, MC, b->n_peaks,
-                                                            pk_x, pk_y, pk_s, b->limb_cand, b->n_limb_cand,
-                                                            b->connections, b->n_conn, ws_cand, b->status);
-        k_assemble<<<B, 32, 0, st>>>(0, MP, b->max_persons, b->candidate, b->connections, b->n_conn, b->subset,
-                                     b->n_subset, b->status);
+        {
+            ProfScope ps("k_limbs", st);
+            k_limbs<<<dim3(kLimbs, B), kLimbThreads, smem, st>>>(b->frames, 0, b->paf, b->stride, b->thre2, MP, MC,
+                                                                b->n_peaks, pk_x, pk_y, pk_s, b->limb_cand,
+                                                                b->n_limb_cand, b->connections, b->n_conn, ws_cand,
+                                                                b->status);
+        }
+        {
+            ProfScope ps("k_assemble", st);
+            k_assemble<<<B, 32, 0, st>>>(0, MP, b->max_persons, b->candidate, b->connections, b->n_conn, b->subset,
+                                         b->n_subset, b->status);
+        }
         count_launch(2);
     }
     RMPE_CUDA_TRY(cudaGetLastError());

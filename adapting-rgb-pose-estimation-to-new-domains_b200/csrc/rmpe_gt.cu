@@ -660,6 +660,7 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
         wa.batch = b->batch; wa.chw = (b->flags & RMPE_GT_IMG_CHW) ? 1 : 0;
         if (b->flags & RMPE_GT_SIMPLE_KERNELS) {
             dim3 grid((kOutW * kOutH + 255) / 256, b->batch);
+            ProfScope ps("k_warp_simple", st);
             k_warp_simple<<<grid, 256, 0, st>>>(wa);
         } else {
             static bool attr_set = false;
@@ -670,6 +671,7 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
             }
             int n_items = b->batch * kTilesPerSample;
             int grid = min(n_items, 2 * T.sm_count);
+            ProfScope ps("k_warp_tile", st);
             k_warp_tile<<<grid, kWarpThreads, smem, st>>>(wa, n_items);
         }
         count_launch();
@@ -680,6 +682,7 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
         ma.src_mask = b->src_mask; ma.desc = b->src_desc; ma.M = b->M; ma.out_mask = b->out_mask;
         ma.tab = T.bicubic_i16; ma.f64 = (b->flags & RMPE_GT_LABELS_F64) ? 1 : 0;
         dim3 grid((kCells + 127) / 128, b->batch);
+        ProfScope ps("k_mask46", st);
         k_mask46<<<grid, 128, 0, st>>>(ma);
         count_launch();
     }
@@ -691,6 +694,7 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
         ra.f64 = (b->flags & RMPE_GT_LABELS_F64) ? 1 : 0; ra.no_transform = no_transform ? 1 : 0;
         ra.sigma = 7.0; ra.thre = 8.0;
         dim3 grid(3, b->batch);
+        ProfScope ps("k_raster", st);
         if (ra.f64) k_raster<double><<<grid, kRasterThreads, 0, st>>>(ra);
         else k_raster<float><<<grid, kRasterThreads, 0, st>>>(ra);
         count_launch();

@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "rmpe_common.cuh"
@@ -22,6 +23,69 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+
+// ---- per-kernel event timing ----
+namespace {
+struct ProfEntry {
+    std::string name;
+    double ms = 0.0;
+    int64_t launches = 0;
+};
+struct ProfPending {
+    int entry;
+    cudaEvent_t e0, e1;
+};
+std::atomic<bool> g_prof_on{false};
+std::mutex g_prof_mu;
+std::vector<ProfEntry> g_prof;
+std::vector<ProfPending> g_prof_pending;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t g_prof_open = nullptr;
+int g_prof_open_entry = -1;
+
+cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) {
+        cudaEvent_t e = g_prof_pool.back();
+        g_prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_resolve() {  // g_prof_mu held
+    for (auto &p : g_prof_pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.e1) == cudaSuccess && cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+            g_prof[p.entry].ms += ms;
+            g_prof[p.entry].launches += 1;
+        }
+        g_prof_pool.push_back(p.e0);
+        g_prof_pool.push_back(p.e1);
+    }
+    g_prof_pending.clear();
+}
+}  // namespace
+
+bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+void prof_mark(const char *name, cudaStream_t st, bool begin) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (begin) {
+        int idx = -1;
+        for (size_t i = 0; i < g_prof.size(); i++)
+            if (g_prof[i].name == name) { idx = (int)i; break; }
+        if (idx < 0) { g_prof.push_back(ProfEntry{name, 0.0, 0}); idx = (int)g_prof.size() - 1; }
+        g_prof_open = prof_event();
+        g_prof_open_entry = idx;
+        cudaEventRecord(g_prof_open, st);
+    } else if (g_prof_open) {
+        cudaEvent_t e1 = prof_event();
+        cudaEventRecord(e1, st);
+        g_prof_pending.push_back(ProfPending{g_prof_open_entry, g_prof_open, e1});
+        g_prof_open = nullptr;
+        if (g_prof_pending.size() >= 4096) prof_resolve();
+    }
+}
 
 struct Arena {
     uint8_t *dev = nullptr;
@@ -170,6 +234,33 @@ extern "C" const char *rmpe_last_error(void) { return t_error; }
 extern "C" int rmpe_abi_version(void) { return RMPE_ABI_VERSION; }
 extern "C" int rmpe_device(void) { return g.init ? g.device : -1; }
 extern "C" int64_t rmpe_launch_count(void) { return g_launches.load(); }
+
+extern "C" int rmpe_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on.store(on != 0);
+    return RMPE_OK;
+}
+extern "C" int rmpe_profile_reset(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    prof_resolve();
+    g_prof.clear();
+    return RMPE_OK;
+}
+extern "C" int rmpe_profile_count(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    prof_resolve();
+    return (int)g_prof.size();
+}
+extern "C" int rmpe_profile_get(int index, char *name_out, int name_cap, double *total_ms, int64_t *launches) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    prof_resolve();
+    RMPE_REQUIRE(index >= 0 && index < (int)g_prof.size(), "profile index out of range");
+    RMPE_REQUIRE(name_out && name_cap > 0 && total_ms && launches, "null argument");
+    snprintf(name_out, (size_t)name_cap, "%s", g_prof[index].name.c_str());
+    *total_ms = g_prof[index].ms;
+    *launches = g_prof[index].launches;
+    return RMPE_OK;
+}
 
 // test hook: copies the host-built int16 table out (32*32*16 entries); no GPU needed
 extern "C" int rmpe_debug_bicubic_table(int16_t *out) {

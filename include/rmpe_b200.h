@@ -248,6 +248,16 @@ int rmpe_pad_right_down_corner(const uint8_t *src_dev, int height, int width, in
 /* kernels launched by this library since rmpe_init (bench.py's gpu_launches) */
 int64_t rmpe_launch_count(void);
 
+/* Per-kernel device time (bench.py's roofline leg).  While enabled every kernel launch of this
+ * library is bracketed by two CUDA events on its own stream; rmpe_profile_get() waits for the
+ * recorded events and returns the accumulated milliseconds and launch count of kernel `index`
+ * (0 <= index < rmpe_profile_count()).  Off by default; the reference's counterpart is the
+ * time() prints of py_rmpe_server/rmpe_server.py:64-78. */
+int rmpe_profile_enable(int on);
+int rmpe_profile_reset(void);
+int rmpe_profile_count(void);
+int rmpe_profile_get(int index, char *name_out, int name_cap, double *total_ms, int64_t *launches);
+
 #ifdef __cplusplus
 }
 #endif
