@@ -2,9 +2,11 @@
 // bicubic), fused 368->46 mask resize, keypoint transform and the 57-plane heat/PAF rasteriser.
 //
 // Reference path replaced (paths relative to the reference root):
-//   py_rmpe_server/py_rmpe_transformer.py:83-114  Transformer.transform      -> k_warp_tile / k_warp_simple,
+//   py_rmpe_server/py_rmpe_transformer.py:83-114  Transformer.transform      -> k_warp_fused / k_warp_simple,
 //                                                                               k_mask46, joints in k_raster
 //   py_rmpe_server/py_rmpe_heatmapper.py:32-138    Heatmapper.create_heatmaps -> k_raster
+#include <stdlib.h>
+
 #include "rmpe_common.cuh"
 
 namespace rmpe {
@@ -54,7 +56,7 @@ __device__ inline void warp_pixel_generic(const uint8_t *__restrict__ src, int H
 
 // ==========================================================================================
 // k_warp_simple: one thread per destination pixel, taps straight from global memory.
-// Debug / fallback-for-huge-footprints variant; also the A/B check of k_warp_tile on the GPU.
+// Debug / fallback-for-huge-footprints variant; also the A/B check of k_warp_fused on the GPU.
 // ==========================================================================================
 struct WarpArgs {
     const uint8_t *src_img;
@@ -98,234 +100,350 @@ __global__ void __launch_bounds__(256) k_warp_simple(WarpArgs a) {
 }
 
 // ==========================================================================================
-// k_warp_tile: persistent CTAs; per 32x32 destination tile the clipped source footprint is
-// staged row by row into shared memory with cp.async.bulk (TMA bulk copies, double buffered on
-// mbarriers), the 16-tap sum runs as dp4a over hi/lo byte-split int16 weights (exact), and the
-// finished tile leaves through a shared-memory staging buffer as 16-byte row segments.
+// k_warp_fused: warpAffine(image, border 127) + warpAffine(mask, border 255) + the 368->46 mask
+// resize in ONE pass over the destination.
+//
+// A persistent CTA (one per SM) holds the 32 KB dp4a weight table once and runs NG independent
+// groups of 128 threads; each group walks 32x32 destination tiles, warp w owning the cell row
+// (destination rows 8w..8w+7) so every warp does identical work.  Per tile the group
+//   1. (one tile ahead, overlapped with the taps) builds the fixed-point row/column terms of
+//      cv::WarpAffineInvoker in f64,
+//   2. stages the UNCLIPPED source footprint of the tile into shared memory as one 32-bit word
+//      per source pixel (B,G,R,mask), out-of-image pixels already replaced by the border
+//      constants (127,127,127,255) -- the 16-tap loop needs no bounds test at all; sources whose
+//      rows are 16-byte aligned are read with 128-bit loads, 16 pixels per thread,
+//   3. evaluates the 16 taps of the channels with dp4a over hi/lo byte-split int16 weights
+//      (exact: identical to OpenCV's int32 accumulation): 4 LDS.32 + 8 PRMT + 8 IDP per tap row
+//      on the four rows that feed the mask, 4 + 7 + 6 on the others,
+//   4. reduces the warped mask to the 46x46 grid in registers/shuffles (cells are 8x8 destination
+//      pixels of which rows/cols 2..5 feed cv2.resize),
+//   5. packs B,G,R of 32 neighbouring pixels into 24 words with two shuffles and stores the row
+//      as one coalesced 96-byte segment (planar rows for CHW).
+// The shared-memory row pitch is kept = 16 (mod 32) words so that a warp walking a rotated line
+// through the footprint spreads over the banks.
 // ==========================================================================================
 constexpr int kTile = 32;
 constexpr int kTilesX = (kOutW + kTile - 1) / kTile;  // 12
 constexpr int kTilesPerSample = kTilesX * kTilesX;    // 144
-constexpr int kFootRows = 96;                         // staged source rows per tile (max)
-constexpr int kFootPitch = 336;                       // bytes per staged row (multiple of 16)
-constexpr int kWarpConsumers = 512;              // 16 compute warps
-constexpr int kWarpThreads = kWarpConsumers + 32;  // + 1 producer warp (bulk-copy issue)
 constexpr int kTabBytes = 32 * 32 * 8 * 4;            // dp4a table
+constexpr int kGroupThreads = 128;
+constexpr int kGeoInts = 4 * kTile;                   // X0, Y0, ad, bd
+constexpr int kGroupFixedBytes = 2 * kGeoInts * 4;    // double-buffered geometry
+constexpr unsigned kBorderWord = 0xFF7F7F7Fu;         // (B,G,R,mask) = (127,127,127,255)
 
-struct TileGeom {      // per staged tile, written by warp 0
-    int X0[kTile];     // row terms  (+16 rounding already in)
-    int Y0[kTile];
-    int ad[kTile];     // column terms
-    int bd[kTile];
-    int fx0, fy0, fx1, fy1;  // clipped footprint in source pixels (inclusive); fx1 < fx0 = empty
-    int staged;              // 1 = footprint is in shared memory, 0 = take taps from global
-    int g0;                  // (address of footprint row 0, col fx0) & 15
-    int sample, x0, y0, tw, th;
-    int ok;                  // matrix invertible
+struct FusedArgs {
+    const uint8_t *src_img;
+    const uint8_t *src_mask;
+    const RmpeSrcDesc *desc;
+    const double *M;
+    uint8_t *out_img;
+    void *out_mask;
+    int32_t *status;
+    const int16_t *tab;
+    const uint32_t *tab_dp4a;
+    int batch;
+    int chw;
+    int mask_f64;
+    int foot_cap;   // footprint capacity of one group, in pixels (32-bit words)
 };
 
-struct WarpSmem {
-    uint32_t tab[kTabBytes / 4];
-    uint8_t foot[2][kFootRows * kFootPitch];
-    uint8_t outbuf[kTile * kTile * 3];
-    TileGeom geom[2];
-    uint64_t full[2];   // producer lanes + bulk-copy bytes -> consumers
-    uint64_t empty[2];  // consumer warps -> producer
-};
-
-__device__ inline void stage_tile(const WarpArgs &a, WarpSmem &s, int buf, int item) {
-    // executed by warp 0 (all 32 lanes)
-    int lane = threadIdx.x & 31;
-    TileGeom &g = s.geom[buf];
-    int sample = item / kTilesPerSample;
-    int t = item - sample * kTilesPerSample;
-    int ty = t / kTilesX, tx = t - ty * kTilesX;
-    int x0 = tx * kTile, y0 = ty * kTile;
-    int tw = min(kTile, kOutW - x0), th = min(kTile, kOutH - y0);
-    double iM[6];
-    bool ok = invert_affine(a.M + 6 * sample, iM);
-    g.X0[lane] = warp_row_term(iM[1], iM[2], y0 + lane);
-    g.Y0[lane] = warp_row_term(iM[4], iM[5], y0 + lane);
-    g.ad[lane] = warp_col_term(iM[0], x0 + lane);
-    g.bd[lane] = warp_col_term(iM[3], x0 + lane);
-    __syncwarp();
-    RmpeSrcDesc d = a.desc[sample];
-    // footprint from the 4 corners: X(x,y) = (X0[y]+ad[x])>>5 is monotone in x and in y
-    int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        int cx = (c & 1) ? tw - 1 : 0, cy = (c & 2) ? th - 1 : 0;
-        int X = (g.X0[cy] + g.ad[cx]) >> 5, Y = (g.Y0[cy] + g.bd[cx]) >> 5;
-        int sx = sat_short(X >> 5) - 1, sy = sat_short(Y >> 5) - 1;
-        mnx = min(mnx, sx); mxx = max(mxx, sx + 3);
-        mny = min(mny, sy); mxy = max(mxy, sy + 3);
-    }
-    int fx0 = max(mnx, 0), fx1 = min(mxx, d.width - 1);
-    int fy0 = max(mny, 0), fy1 = min(mxy, d.height - 1);
-    bool empty = (fx1 < fx0) || (fy1 < fy0);
-    const uint8_t *base = a.src_img + d.img_offset;
-    size_t addr0 = (size_t)(base + (size_t)(empty ? 0 : fy0) * d.img_pitch + 3 * (empty ? 0 : fx0));
-    int rows = empty ? 0 : fy1 - fy0 + 1;
-    int row_bytes = empty ? 0 : 3 * (fx1 - fx0 + 1);
-    // every staged row must fit: misalignment (<16) + payload + funnel slack (4 words) + round-up
-    bool fits = rows <= kFootRows && (row_bytes + 15 + 16 + 15) <= kFootPitch &&
-                ((size_t)a.src_img & 15) == 0;
-    unsigned my_bytes = 0;
-    if (!empty && fits) {
-        for (int r = lane; r < rows; r += 32) {
-            size_t ga = addr0 + (size_t)r * d.img_pitch;
-            size_t ga0 = ga & ~(size_t)15;
-            unsigned nbytes = (unsigned)(((ga + row_bytes + 15) & ~(size_t)15) - ga0);
-            bulk_g2s(&s.foot[buf][r * kFootPitch], (const void *)ga0, nbytes, &s.full[buf]);
-            my_bytes += nbytes;
-        }
-    }
-    if (lane == 0) {
-        g.fx0 = fx0; g.fy0 = fy0; g.fx1 = empty ? fx0 - 1 : fx1; g.fy1 = empty ? fy0 - 1 : fy1;
-        g.staged = (!empty && fits) ? 1 : 0;
-        g.g0 = (int)(addr0 & 15);
-        g.sample = sample; g.x0 = x0; g.y0 = y0; g.tw = tw; g.th = th;
-        g.ok = ok ? 1 : 0;
-    }
-    __syncwarp();
-    if (my_bytes) mbar_arrive_expect_tx(&s.full[buf], my_bytes);  // release: geom + copies
-    else mbar_arrive(&s.full[buf]);
+__device__ __forceinline__ void group_bar(int group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kGroupThreads) : "memory");
 }
 
-__global__ void __launch_bounds__(kWarpThreads, 2) k_warp_tile(WarpArgs a, int n_items) {
+// 16 taps x {B,G,R[,mask]} from a staged (B,G,R,mask) footprint.  p -> tap (0,0).
+template <bool kMask>
+__device__ __forceinline__ void bicubic_bgrm(const uint32_t *__restrict__ p, int fpitch,
+                                             const uint32_t *__restrict__ wt, int &oB, int &oG, int &oR, int &oM) {
+    const uint4 wa = *reinterpret_cast<const uint4 *>(wt);      // rows 0,1: {hi,lo,hi,lo}
+    const uint4 wb = *reinterpret_cast<const uint4 *>(wt + 4);  // rows 2,3
+    const unsigned whi[4] = {wa.x, wa.z, wb.x, wb.z};
+    const unsigned wlo[4] = {wa.y, wa.w, wb.y, wb.w};
+    int hB = 0, hG = 0, hR = 0, hM = 0;
+    int lB = 16384, lG = 16384, lR = 16384, lM = 16384;   // rounding term of the >>15
+#pragma unroll
+    for (int ky = 0; ky < 4; ky++) {
+        const unsigned p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3];
+        p += fpitch;
+        const unsigned t0 = __byte_perm(p0, p1, 0x5140);   // B0 B1 G0 G1
+        const unsigned t1 = __byte_perm(p2, p3, 0x5140);   // B2 B3 G2 G3
+        const unsigned pb = __byte_perm(t0, t1, 0x5410);
+        const unsigned pg = __byte_perm(t0, t1, 0x7632);
+        const unsigned t2 = __byte_perm(p0, p1, 0x7362);   // R0 R1 M0 M1
+        const unsigned t3 = __byte_perm(p2, p3, 0x7362);   // R2 R3 M2 M3
+        const unsigned pr = __byte_perm(t2, t3, 0x5410);
+        hB = dp4a_us(pb, whi[ky], hB); lB = dp4a_uu(pb, wlo[ky], lB);
+        hG = dp4a_us(pg, whi[ky], hG); lG = dp4a_uu(pg, wlo[ky], lG);
+        hR = dp4a_us(pr, whi[ky], hR); lR = dp4a_uu(pr, wlo[ky], lR);
+        if (kMask) {
+            const unsigned pm = __byte_perm(t2, t3, 0x7632);
+            hM = dp4a_us(pm, whi[ky], hM); lM = dp4a_uu(pm, wlo[ky], lM);
+        }
+    }
+    oB = min(255, max(0, (hB * 256 + lB) >> 15));
+    oG = min(255, max(0, (hG * 256 + lG) >> 15));
+    oR = min(255, max(0, (hR * 256 + lR) >> 15));
+    oM = kMask ? min(255, max(0, (hM * 256 + lM) >> 15)) : 0;
+}
+
+// (B,G,R,mask) word of one source pixel with cv2's per-tap constant border
+__device__ __forceinline__ unsigned bgrm_pixel(const uint8_t *__restrict__ img, const uint8_t *__restrict__ msk,
+                                               int H, int W, int ipitch, int mpitch, int yy, int xx) {
+    if ((unsigned)yy >= (unsigned)H || (unsigned)xx >= (unsigned)W) return kBorderWord;
+    const uint8_t *ip = img + (size_t)yy * ipitch + 3 * xx;
+    return (unsigned)__ldg(ip) | ((unsigned)__ldg(ip + 1) << 8) | ((unsigned)__ldg(ip + 2) << 16) |
+           ((unsigned)__ldg(msk + (size_t)yy * mpitch + xx) << 24);
+}
+
+// 4 pixels (12 image bytes in q0..q2, 4 mask bytes in mq) -> 4 (B,G,R,mask) words
+__device__ __forceinline__ uint4 bgrm_pack4(unsigned q0, unsigned q1, unsigned q2, unsigned mq) {
+    uint4 w;
+    w.x = __byte_perm(q0, mq, 0x4210);
+    w.y = __byte_perm(__byte_perm(q0, q1, 0x0543), mq, 0x5210);
+    w.z = __byte_perm(__byte_perm(q1, q2, 0x0432), mq, 0x6210);
+    w.w = __byte_perm(q2, mq, 0x7321);
+    return w;
+}
+
+// 4 pixels starting at (yy, xx) of an arbitrary-pitch source
+__device__ __forceinline__ uint4 bgrm_load4(const uint8_t *__restrict__ img, const uint8_t *__restrict__ msk,
+                                            int H, int W, int ipitch, int mpitch, int yy, int xx) {
+    if ((unsigned)yy >= (unsigned)H) return make_uint4(kBorderWord, kBorderWord, kBorderWord, kBorderWord);
+    if (xx >= 0 && xx + 3 < W) {
+        // 12 image bytes + 4 mask bytes through aligned 32-bit loads
+        const size_t ia = (size_t)(img + (size_t)yy * ipitch + 3 * xx);
+        const uint32_t *iw = reinterpret_cast<const uint32_t *>(ia & ~(size_t)3);
+        const unsigned ish = (unsigned)(ia & 3) * 8;
+        const unsigned u0 = __ldg(iw), u1 = __ldg(iw + 1), u2 = __ldg(iw + 2);
+        const unsigned u3 = ish ? __ldg(iw + 3) : 0u;
+        const size_t ma = (size_t)(msk + (size_t)yy * mpitch + xx);
+        const uint32_t *mwp = reinterpret_cast<const uint32_t *>(ma & ~(size_t)3);
+        const unsigned msh = (unsigned)(ma & 3) * 8;
+        const unsigned v0 = __ldg(mwp);
+        const unsigned v1 = msh ? __ldg(mwp + 1) : 0u;
+        return bgrm_pack4(__funnelshift_r(u0, u1, ish), __funnelshift_r(u1, u2, ish), __funnelshift_r(u2, u3, ish),
+                          __funnelshift_r(v0, v1, msh));
+    }
+    uint4 w;
+    w.x = bgrm_pixel(img, msk, H, W, ipitch, mpitch, yy, xx);
+    w.y = bgrm_pixel(img, msk, H, W, ipitch, mpitch, yy, xx + 1);
+    w.z = bgrm_pixel(img, msk, H, W, ipitch, mpitch, yy, xx + 2);
+    w.w = bgrm_pixel(img, msk, H, W, ipitch, mpitch, yy, xx + 3);
+    return w;
+}
+
+// tiles whose footprint does not fit the staging buffer (heavy down-scaling) take their taps
+// straight from global memory
+__device__ __noinline__ unsigned generic_bgrm(const uint8_t *__restrict__ img, const uint8_t *__restrict__ msk,
+                                              int H, int W, int ipitch, int mpitch, int X, int Y,
+                                              const int16_t *__restrict__ tab, bool want_mask) {
+    int o[3], m1[1] = {255};
+    warp_pixel_generic<3>(img, H, W, ipitch, X, Y, tab, 127, o);
+    if (want_mask) warp_pixel_generic<1>(msk, H, W, mpitch, X, Y, tab, 255, m1);
+    return (unsigned)o[0] | ((unsigned)o[1] << 8) | ((unsigned)o[2] << 16) | ((unsigned)m1[0] << 24);
+}
+
+struct TileCtx {
+    const uint32_t *foot;
+    const uint32_t *tab;
+    const int *gX0, *gY0;
+    int adx, bdx, fpitch, bx0, by0;
+    int mode;   // 0 = staged, 1 = all border, 2 = generic
+    const uint8_t *img, *msk;
+    int H, W, ipitch, mpitch;
+    const int16_t *tab16;
+};
+
+// one destination row of the warp: returns packed B | G<<8 | R<<16 | mask<<24
+template <bool kMask>
+__device__ __forceinline__ unsigned fused_row(const TileCtx &c, int ly, bool lane_on) {
+    if (c.mode == 1 || !lane_on) return kBorderWord;
+    const int X = (c.gX0[ly] + c.adx) >> 5;
+    const int Y = (c.gY0[ly] + c.bdx) >> 5;
+    if (c.mode == 0) {
+        int oB, oG, oR, oM;
+        const uint32_t *p = c.foot + ((Y >> 5) - 1 - c.by0) * c.fpitch + ((X >> 5) - 1 - c.bx0);
+        const uint32_t *wt = c.tab + (((Y & 31) * 32 + (X & 31)) << 3);
+        bicubic_bgrm<kMask>(p, c.fpitch, wt, oB, oG, oR, oM);
+        return (unsigned)oB | ((unsigned)oG << 8) | ((unsigned)oR << 16) | ((unsigned)oM << 24);
+    }
+    return generic_bgrm(c.img, c.msk, c.H, c.W, c.ipitch, c.mpitch, X, Y, c.tab16, kMask);
+}
+
+// store one 32-pixel destination row held one pixel per lane
+__device__ __forceinline__ void store_row(uint8_t *__restrict__ out_sample, int chw, int y, int x0, int tw, int lane,
+                                          unsigned bgr, int pk_lane, unsigned pk_sel) {
+    if (!chw) {
+        // 24 words of the 96-byte row: word w = bytes 4w..4w+3 = pixels floor(4w/3), +1
+        const unsigned a = __shfl_sync(0xffffffffu, bgr, pk_lane);
+        const unsigned b = __shfl_sync(0xffffffffu, bgr, pk_lane + 1);
+        if (4 * lane < 3 * tw)
+            reinterpret_cast<uint32_t *>(out_sample + ((size_t)y * kOutW + x0) * 3)[lane] = __byte_perm(a, b, pk_sel);
+    } else if (lane < tw) {
+        uint8_t *o = out_sample + (size_t)y * kOutW + x0 + lane;
+        o[0] = (uint8_t)bgr;
+        o[kOutW * kOutH] = (uint8_t)(bgr >> 8);
+        o[2 * kOutW * kOutH] = (uint8_t)(bgr >> 16);
+    }
+}
+
+template <int NG, bool kWantMask>
+__global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a, int n_items) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    WarpSmem &s = *reinterpret_cast<WarpSmem *>(smem_raw);
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const int lane = tid & 31;
+    uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem_raw);
+    const int group = threadIdx.x / kGroupThreads;
+    const int t = threadIdx.x - group * kGroupThreads;
+    const int warp = t >> 5, lane = t & 31;
+    uint8_t *gbase = smem_raw + kTabBytes + (size_t)group * ((size_t)a.foot_cap * 4 + kGroupFixedBytes);
+    uint32_t *foot = reinterpret_cast<uint32_t *>(gbase);
+    int *geo = reinterpret_cast<int *>(gbase + (size_t)a.foot_cap * 4);
 
-    if (tid == 0) {
-        mbar_init(&s.full[0], 32);
-        mbar_init(&s.full[1], 32);
-        mbar_init(&s.empty[0], kWarpConsumers / 32);
-        mbar_init(&s.empty[1], kWarpConsumers / 32);
-        mbar_fence_init();
-    }
-    // dp4a weight table -> shared memory (32 KB, once per persistent CTA)
-    {
+    {   // dp4a weight table -> shared memory, once per persistent CTA
         const uint4 *src = reinterpret_cast<const uint4 *>(a.tab_dp4a);
-        uint4 *dst = reinterpret_cast<uint4 *>(s.tab);
-        for (int i = tid; i < kTabBytes / 16; i += kWarpThreads) dst[i] = __ldg(src + i);
-    }
-    __syncthreads();
-
-    if (warp == kWarpConsumers / 32) {
-        // ---------------- producer warp: geometry + bulk copies, two tiles ahead ----------------
-        int k = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, k++) {
-            int buf = k & 1;
-            if (k >= 2) {
-                mbar_wait(&s.empty[buf], ((k >> 1) - 1) & 1);
-                fence_proxy_async();
-            }
-            stage_tile(a, s, buf, item);
-        }
-        return;
+        uint4 *dst = reinterpret_cast<uint4 *>(s_tab);
+        for (int i = threadIdx.x; i < kTabBytes / 16; i += NG * kGroupThreads) dst[i] = __ldg(src + i);
     }
 
-    // ---------------- consumer warps ----------------
-    int k = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, k++) {
-        const int buf = k & 1;
-        mbar_wait(&s.full[buf], (k >> 1) & 1);
+    const int l7 = lane & 7;
+    const int mw = (l7 == 3 || l7 == 4) ? 1216 : ((l7 == 2 || l7 == 5) ? -192 : 0);
+    const int pk_lane = (4 * lane) / 3;                       // HWC row packing (store_row)
+    const unsigned pk_sel = (4 * lane) % 3 == 0 ? 0x4210u : ((4 * lane) % 3 == 1 ? 0x5421u : 0x6542u);
+    const float sc = 1.0f / 4194304.0f;                       // 2^-22
+    const float b0 = -192.0f * sc, b1 = 1216.0f * sc;
 
-        const TileGeom &g = s.geom[buf];
-        const RmpeSrcDesc d = a.desc[g.sample];
-        const uint8_t *gsrc = a.src_img + d.img_offset;
-        const uint8_t *foot = s.foot[buf];
-        const int staged = g.staged;
-        const int fx0 = g.fx0, fy0 = g.fy0, fx1 = g.fx1, fy1 = g.fy1, g0 = g.g0;
-        const int pitch = d.img_pitch;
-        const int tw = g.tw, th = g.th, x0 = g.x0, y0 = g.y0, sample = g.sample;
-
-        // warp w owns tile rows w and w+16; lane = tile column
-        const int adx = g.ad[lane], bdx = g.bd[lane];
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-            const int ly = warp + half * 16;
-            if (lane < tw && ly < th) {
-                int X = (g.X0[ly] + adx) >> 5;
-                int Y = (g.Y0[ly] + bdx) >> 5;
-                int sx = sat_short(X >> 5) - 1;
-                int sy = sat_short(Y >> 5) - 1;
-                int o0, o1, o2;
-                if (staged && sx >= fx0 && sx + 3 <= fx1 && sy >= fy0 && sy + 3 <= fy1) {
-                    const uint4 *wp = reinterpret_cast<const uint4 *>(s.tab + (((Y & 31) * 32 + (X & 31)) << 3));
-                    uint4 wa = wp[0], wb = wp[1];  // rows 0,1 and rows 2,3: {hi,lo,hi,lo}
-                    const unsigned whi[4] = {wa.x, wa.z, wb.x, wb.z};
-                    const unsigned wlo[4] = {wa.y, wa.w, wb.y, wb.w};
-                    int hB = 0, hG = 0, hR = 0, lB = 0, lG = 0, lR = 0;
-                    int r0i = sy - fy0;
-                    int colb = 3 * (sx - fx0);
-#pragma unroll
-                    for (int ky = 0; ky < 4; ky++) {
-                        int r = r0i + ky;
-                        int aoff = r * kFootPitch + ((g0 + r * pitch) & 15) + colb;
-                        const uint32_t *wptr = reinterpret_cast<const uint32_t *>(foot + (aoff & ~3));
-                        unsigned w0 = wptr[0], w1 = wptr[1], w2 = wptr[2], w3 = wptr[3];
-                        unsigned sh = (aoff & 3) * 8;
-                        unsigned q0 = __funnelshift_r(w0, w1, sh);  // B0 G0 R0 B1
-                        unsigned q1 = __funnelshift_r(w1, w2, sh);  // G1 R1 B2 G2
-                        unsigned q2 = __funnelshift_r(w2, w3, sh);  // R2 B3 G3 R3
-                        unsigned pb = __byte_perm(__byte_perm(q0, q1, 0x0630), q2, 0x5210);
-                        unsigned pg = __byte_perm(__byte_perm(q0, q1, 0x0741), q2, 0x6210);
-                        unsigned pr = __byte_perm(__byte_perm(q0, q1, 0x0052), q2, 0x7410);
-                        hB = dp4a_us(pb, whi[ky], hB); lB = dp4a_uu(pb, wlo[ky], lB);
-                        hG = dp4a_us(pg, whi[ky], hG); lG = dp4a_uu(pg, wlo[ky], lG);
-                        hR = dp4a_us(pr, whi[ky], hR); lR = dp4a_uu(pr, wlo[ky], lR);
-                    }
-                    o0 = min(255, max(0, (hB * 256 + lB + 16384) >> 15));
-                    o1 = min(255, max(0, (hG * 256 + lG + 16384) >> 15));
-                    o2 = min(255, max(0, (hR * 256 + lR + 16384) >> 15));
-                } else {
-                    int o[3];
-                    warp_pixel_generic<3>(gsrc, d.height, d.width, pitch, X, Y, a.tab, 127, o);
-                    o0 = o[0]; o1 = o[1]; o2 = o[2];
-                }
-                if (a.chw) {
-                    s.outbuf[(0 * kTile + ly) * kTile + lane] = (uint8_t)o0;
-                    s.outbuf[(1 * kTile + ly) * kTile + lane] = (uint8_t)o1;
-                    s.outbuf[(2 * kTile + ly) * kTile + lane] = (uint8_t)o2;
-                } else {
-                    uint8_t *ob = s.outbuf + (ly * kTile + lane) * 3;
-                    ob[0] = (uint8_t)o0; ob[1] = (uint8_t)o1; ob[2] = (uint8_t)o2;
-                }
-            }
-        }
-        if (tid == 0 && !g.ok && x0 == 0 && y0 == 0) atomicOr(a.status + sample, RMPE_ST_SINGULAR);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s.empty[buf]);  // this warp is done with foot[buf] / geom[buf]
-        // this warp's two rows leave as 16-byte segments: HWC row = 96 B (48 B for the 16-px edge
-        // tile), CHW plane row = 32 B (16 B at the edge)
-        uint8_t *out = a.out_img + (size_t)sample * (3 * kOutW * kOutH);
-        if (!a.chw) {
-            int segs = tw * 3 / 16;
-            if (lane < 2 * segs) {
-                int half = lane / segs, sg = lane - half * segs;
-                int r = warp + half * 16;
-                if (r < th) {
-                    uint4 v = *reinterpret_cast<const uint4 *>(s.outbuf + r * (kTile * 3) + sg * 16);
-                    *reinterpret_cast<uint4 *>(out + ((size_t)(y0 + r) * kOutW + x0) * 3 + sg * 16) = v;
-                }
-            }
+    // geometry of one tile -> geo[buf]  (threads 0..63 of the group)
+    auto geometry = [&](int item, int buf) {
+        const int sample = item / kTilesPerSample;
+        const int tt = item - sample * kTilesPerSample;
+        const int ty = tt / kTilesX, tx = tt - ty * kTilesX;
+        int *g = geo + buf * kGeoInts;
+        double iM[6];
+        const bool ok = invert_affine(a.M + 6 * sample, iM);
+        if (t < kTile) {
+            g[t] = warp_row_term(iM[1], iM[2], ty * kTile + t);
+            g[kTile + t] = warp_row_term(iM[4], iM[5], ty * kTile + t);
         } else {
-            int segs = tw / 16;
-            if (lane < 6 * segs) {
-                int q = lane / segs, sg = lane - q * segs;  // q = plane*2 + half
-                int pl = q >> 1, r = warp + (q & 1) * 16;
-                if (r < th) {
-                    uint4 v = *reinterpret_cast<const uint4 *>(s.outbuf + (pl * kTile + r) * kTile + sg * 16);
-                    *reinterpret_cast<uint4 *>(out + (size_t)pl * (kOutW * kOutH) + (size_t)(y0 + r) * kOutW + x0 +
-                                               sg * 16) = v;
+            g[2 * kTile + t - kTile] = warp_col_term(iM[0], tx * kTile + t - kTile);
+            g[3 * kTile + t - kTile] = warp_col_term(iM[3], tx * kTile + t - kTile);
+        }
+        if (t == 0 && !ok && tt == 0) atomicOr(a.status + sample, RMPE_ST_SINGULAR);
+    };
+
+    const int stride = gridDim.x * NG;
+    int item = blockIdx.x * NG + group;
+    if (item < n_items && t < 2 * kTile) geometry(item, 0);
+    __syncthreads();   // weight table + first geometry
+
+    for (int k = 0; item < n_items; item += stride, k++) {
+        const int sample = item / kTilesPerSample;
+        const int tt = item - sample * kTilesPerSample;
+        const int ty = tt / kTilesX, tx = tt - ty * kTilesX;
+        const int x0 = tx * kTile, y0 = ty * kTile;
+        const int tw = min(kTile, kOutW - x0), th = min(kTile, kOutH - y0);
+        const RmpeSrcDesc d = a.desc[sample];
+        const uint8_t *img = a.src_img + d.img_offset;
+        const uint8_t *msk = a.src_mask + d.mask_offset;
+        const int *gX0 = geo + (k & 1) * kGeoInts, *gY0 = gX0 + kTile, *gad = gY0 + kTile, *gbd = gad + kTile;
+
+        // footprint from the 4 corners: X(x,y) = (X0[y]+ad[x])>>5 is monotone in x and in y
+        int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
+        bool sane = true;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int cx = (c & 1) ? tw - 1 : 0, cy = (c & 2) ? th - 1 : 0;
+            const int qx = (gX0[cy] + gad[cx]) >> 10, qy = (gY0[cy] + gbd[cx]) >> 10;
+            sane = sane && qx > -30000 && qx < 30000 && qy > -30000 && qy < 30000;  // no short saturation
+            mnx = min(mnx, qx - 1); mxx = max(mxx, qx + 2);
+            mny = min(mny, qy - 1); mxy = max(mxy, qy + 2);
+        }
+        // rows 16-byte aligned -> 128-bit loads of 16 pixels; the footprint then starts on a multiple of 16
+        const bool wide = ((((size_t)img | (size_t)msk) & 15) == 0) && (((d.img_pitch | d.mask_pitch) & 15) == 0);
+        const int bx0 = wide ? (mnx & ~15) : mnx, by0 = mny;
+        const int fw = mxx - bx0 + 1, fh = mxy - mny + 1;
+        const int fwa = wide ? ((fw + 15) & ~15) : ((fw + 3) & ~3);
+        int fpitch = ((fwa + 15) & ~31) + 16;                       // = 16 (mod 32), >= fwa
+        if ((long long)fpitch * fh > a.foot_cap) fpitch = fwa;
+        const bool outside = sane && (mxx < 0 || mnx >= d.width || mxy < 0 || mny >= d.height);
+        const bool staged = sane && !outside && (long long)fpitch * fh <= a.foot_cap;
+
+        // ---- stage the footprint as (B,G,R,mask) words ----
+        if (staged) {
+            if (wide) {
+                const int n16 = fwa >> 4;
+                for (int it = t; it < fh * n16; it += kGroupThreads) {
+                    const int r = it / n16, c = (it - r * n16) << 4;
+                    const int yy = by0 + r, xx = bx0 + c;
+                    uint4 *dst = reinterpret_cast<uint4 *>(foot + r * fpitch + c);
+                    if ((unsigned)yy < (unsigned)d.height && xx >= 0 && xx + 15 < d.width) {
+                        const uint4 *ip = reinterpret_cast<const uint4 *>(img + (size_t)yy * d.img_pitch + 3 * xx);
+                        const uint4 i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
+                        const uint4 mq = __ldg(reinterpret_cast<const uint4 *>(msk + (size_t)yy * d.mask_pitch + xx));
+                        dst[0] = bgrm_pack4(i0.x, i0.y, i0.z, mq.x);
+                        dst[1] = bgrm_pack4(i0.w, i1.x, i1.y, mq.y);
+                        dst[2] = bgrm_pack4(i1.z, i1.w, i2.x, mq.z);
+                        dst[3] = bgrm_pack4(i2.y, i2.z, i2.w, mq.w);
+                    } else {
+#pragma unroll 1
+                        for (int q = 0; q < 4; q++)
+                            dst[q] = bgrm_load4(img, msk, d.height, d.width, d.img_pitch, d.mask_pitch, yy, xx + 4 * q);
+                    }
+                }
+            } else {
+                const int n4 = fwa >> 2;
+                for (int it = t; it < fh * n4; it += kGroupThreads) {
+                    const int r = it / n4, c = (it - r * n4) << 2;
+                    *reinterpret_cast<uint4 *>(foot + r * fpitch + c) =
+                        bgrm_load4(img, msk, d.height, d.width, d.img_pitch, d.mask_pitch, by0 + r, bx0 + c);
                 }
             }
         }
-        __syncwarp();  // outbuf rows of this warp are free again
+        group_bar(group);     // footprint visible
+
+        // geometry of the next tile, overlapped with this tile's taps
+        if (item + stride < n_items && t < 2 * kTile) geometry(item + stride, (k + 1) & 1);
+
+        // ---- taps, mask reduction, stores: warp = cell row ----
+        if (8 * warp < th) {
+            TileCtx c;
+            c.foot = foot; c.tab = s_tab; c.gX0 = gX0; c.gY0 = gY0;
+            c.adx = gad[lane]; c.bdx = gbd[lane]; c.fpitch = fpitch; c.bx0 = bx0; c.by0 = by0;
+            c.mode = staged ? 0 : (outside ? 1 : 2);
+            c.img = img; c.msk = msk; c.H = d.height; c.W = d.width; c.ipitch = d.img_pitch; c.mpitch = d.mask_pitch;
+            c.tab16 = a.tab;
+            const bool lane_on = lane < tw;
+            uint8_t *out_sample = a.out_img + (size_t)sample * (3 * kOutW * kOutH);
+            const int r0 = 8 * warp;
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+                store_row(out_sample, a.chw, y0 + r0 + j, x0, tw, lane, fused_row<false>(c, r0 + j, lane_on), pk_lane, pk_sel);
+            float macc = 0.f;   // cv2.resize vertical pass, float32 FMA chain S3*b0 -> S2*b1 -> S1*b1 -> S0*b0
+#pragma unroll
+            for (int j = 5; j >= 2; j--) {
+                const unsigned v4 = kWantMask ? fused_row<true>(c, r0 + j, lane_on) : fused_row<false>(c, r0 + j, lane_on);
+                store_row(out_sample, a.chw, y0 + r0 + j, x0, tw, lane, v4, pk_lane, pk_sel);
+                if (kWantMask) {
+                    // cv2.resize horizontal pass: exact int32 sum of (-192,1216,1216,-192) x cols 8c+2..8c+5
+                    int v = (int)(v4 >> 24) * mw;
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    const float Sj = (float)v;
+                    macc = (j == 5) ? Sj * b0 : fmaf(Sj, (j == 2) ? b0 : b1, macc);
+                }
+            }
+#pragma unroll
+            for (int j = 6; j < 8; j++)
+                store_row(out_sample, a.chw, y0 + r0 + j, x0, tw, lane, fused_row<false>(c, r0 + j, lane_on), pk_lane, pk_sel);
+            if (kWantMask && l7 == 0 && lane_on) {
+                // rint, saturate; then /255.  (py_rmpe_transformer.py:92,95)
+                const int iv = min(255, max(0, __float2int_rn(macc)));
+                const double m = __ddiv_rn((double)iv, 255.0);
+                const size_t o = (size_t)sample * kCells + (size_t)((y0 >> 3) + warp) * kGrid + (x0 >> 3) + (lane >> 3);
+                if (a.mask_f64) reinterpret_cast<double *>(a.out_mask)[o] = m;
+                else reinterpret_cast<float *>(a.out_mask)[o] = (float)m;
+            }
+        }
+        group_bar(group);     // footprint free, next geometry visible
     }
 }
 
@@ -627,7 +745,31 @@ __global__ void __launch_bounds__(kRasterThreads) k_raster(RasterArgs a) {
 // ==========================================================================================
 // host entry
 // ==========================================================================================
-static size_t warp_smem_bytes() { return sizeof(WarpSmem) + 128; }
+constexpr int kMaxSmemOptin = 227 * 1024;
+
+// footprint capacity (pixels) of one tile group when NG groups share a CTA
+static int fused_foot_cap(int ng) {
+    int bytes = (kMaxSmemOptin - kTabBytes) / ng - kGroupFixedBytes;
+    return (bytes / 4) & ~31;   // keeps every group's base 128-byte aligned
+}
+static size_t fused_smem_bytes(int ng) { return (size_t)kTabBytes + (size_t)ng * ((size_t)fused_foot_cap(ng) * 4 + kGroupFixedBytes); }
+
+template <int NG>
+static int launch_fused(const FusedArgs &fa_, bool want_mask, int n_items, int sm_count, cudaStream_t st) {
+    FusedArgs fa = fa_;
+    fa.foot_cap = fused_foot_cap(NG);
+    const size_t smem = fused_smem_bytes(NG);
+    static bool attr_set = false;
+    if (!attr_set) {
+        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int grid = min((n_items + NG - 1) / NG, sm_count);
+    if (want_mask) k_warp_fused<NG, true><<<grid, NG * kGroupThreads, smem, st>>>(fa, n_items);
+    else k_warp_fused<NG, false><<<grid, NG * kGroupThreads, smem, st>>>(fa, n_items);
+    return RMPE_OK;
+}
 
 }  // namespace rmpe
 
@@ -653,31 +795,44 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
     const DeviceTables &T = tables();
     RMPE_CUDA_TRY(cudaMemsetAsync(b->status, 0, sizeof(int32_t) * b->batch, st));
 
+    const bool warp_only = (b->flags & RMPE_GT_WARP_ONLY) != 0;
+    const bool simple = (b->flags & RMPE_GT_SIMPLE_KERNELS) != 0;
+    const bool want_mask = !no_transform && !warp_only;
+    bool mask_done = false;
     if (!no_warp) {
-        WarpArgs wa;
-        wa.src_img = b->src_img; wa.desc = b->src_desc; wa.M = b->M; wa.out_img = b->out_img;
-        wa.status = b->status; wa.tab = T.bicubic_i16; wa.tab_dp4a = T.bicubic_dp4a;
-        wa.batch = b->batch; wa.chw = (b->flags & RMPE_GT_IMG_CHW) ? 1 : 0;
-        if (b->flags & RMPE_GT_SIMPLE_KERNELS) {
+        RMPE_REQUIRE(((size_t)b->out_img & 15) == 0, "out_img must be 16-byte aligned");
+        if (simple) {
+            WarpArgs wa;
+            wa.src_img = b->src_img; wa.desc = b->src_desc; wa.M = b->M; wa.out_img = b->out_img;
+            wa.status = b->status; wa.tab = T.bicubic_i16; wa.tab_dp4a = T.bicubic_dp4a;
+            wa.batch = b->batch; wa.chw = (b->flags & RMPE_GT_IMG_CHW) ? 1 : 0;
             dim3 grid((kOutW * kOutH + 255) / 256, b->batch);
             ProfScope ps("k_warp_simple", st);
             k_warp_simple<<<grid, 256, 0, st>>>(wa);
         } else {
-            static bool attr_set = false;
-            size_t smem = warp_smem_bytes();
-            if (!attr_set) {
-                RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_set = true;
-            }
-            int n_items = b->batch * kTilesPerSample;
-            int grid = min(n_items, 2 * T.sm_count);
-            ProfScope ps("k_warp_tile", st);
-            k_warp_tile<<<grid, kWarpThreads, smem, st>>>(wa, n_items);
+            FusedArgs fa;
+            fa.src_img = b->src_img; fa.src_mask = b->src_mask; fa.desc = b->src_desc; fa.M = b->M;
+            fa.out_img = b->out_img; fa.out_mask = b->out_mask; fa.status = b->status;
+            fa.tab = T.bicubic_i16; fa.tab_dp4a = T.bicubic_dp4a; fa.batch = b->batch;
+            fa.chw = (b->flags & RMPE_GT_IMG_CHW) ? 1 : 0;
+            fa.mask_f64 = (b->flags & RMPE_GT_LABELS_F64) ? 1 : 0;
+            fa.foot_cap = 0;
+            const int n_items = b->batch * kTilesPerSample;
+            static const int ng = [] {
+                const char *e = getenv("RMPE_WARP_GROUPS");
+                int v = e ? atoi(e) : 6;
+                return (v == 4 || v == 8) ? v : 6;
+            }();
+            ProfScope ps("k_warp_fused", st);
+            int rc = ng == 4 ? launch_fused<4>(fa, want_mask, n_items, T.sm_count, st)
+                   : ng == 8 ? launch_fused<8>(fa, want_mask, n_items, T.sm_count, st)
+                             : launch_fused<6>(fa, want_mask, n_items, T.sm_count, st);
+            if (rc != RMPE_OK) return rc;
+            mask_done = want_mask;
         }
         count_launch();
     }
-    const bool warp_only = (b->flags & RMPE_GT_WARP_ONLY) != 0;
-    if (!no_transform && !warp_only) {
+    if (want_mask && !mask_done) {
         MaskArgs ma;
         ma.src_mask = b->src_mask; ma.desc = b->src_desc; ma.M = b->M; ma.out_mask = b->out_mask;
         ma.tab = T.bicubic_i16; ma.f64 = (b->flags & RMPE_GT_LABELS_F64) ? 1 : 0;

@@ -45,7 +45,7 @@ def gt_bytes_per_sample(P, src_hw=SRC_HW):
     img_out, mask_out, labels = 368 * 368 * 3, 46 * 46 * 4, 57 * 46 * 46 * 4
     joints = 432 * P
     return {
-        "k_warp_tile": img_in + img_out + 48,
+        "k_warp_fused": img_in + mask_in + img_out + mask_out + 48,
         "k_warp_simple": img_in + img_out + 48,
         "k_mask46": mask_in + mask_out + 48,
         "k_raster": mask_out + labels + 2 * joints + 48 + 1 + 4,

@@ -200,3 +200,28 @@ def test_crowded_20_persons(rmpe):
     olab, ocnt = go.create_heatmaps(oj, omask, return_count=True)
     assert np.array_equal(r["img"][0], oimg) and np.array_equal(r["count"][0], ocnt)
     assert np.abs(r["labels"][0] - olab).max() <= LABEL_TOL
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_geometry_sweep(rmpe, seed):
+    """Fused warp+mask kernel against the oracle over odd source sizes (unaligned row pitches),
+    zoom factors on both sides of the staging capacity, rotations beyond the augmentation range
+    and centres near / outside the frame (all-border tiles)."""
+    rng = np.random.RandomState(4000 + seed)
+    H, W = int(rng.randint(40, 700)), int(rng.randint(40, 700))
+    img = rng.randint(0, 256, size=(H, W, 3)).astype(np.uint8)
+    mask = (rng.randint(0, 4, size=(H, W)) > 0).astype(np.uint8) * 255
+    if seed % 2:
+        mask = rng.randint(0, 256, size=(H, W)).astype(np.uint8)
+    flip = int(rng.randint(0, 2))
+    deg = float(rng.uniform(-180, 180)) if seed % 3 == 0 else float(rng.uniform(-40, 40))
+    scale_self = float(np.exp(rng.uniform(np.log(0.12), np.log(2.5))))
+    center = (float(rng.uniform(-0.2, 1.2) * W), float(rng.uniform(-0.2, 1.2) * H))
+    crop = (int(rng.randint(-40, 41)), int(rng.randint(-40, 41)))
+    M = rmpe.batch.aug_affine([flip], [deg], [crop], [1.0], [center], [scale_self])
+    for chw in (False, True):
+        r = rmpe.batch.gt_batch_host(img[None], mask[None], np.zeros((1, 0, 18, 3)), [0], M, [flip], f64=True, chw=chw)
+        oimg, omask, _ = go.transform(img, mask, np.zeros((0, 18, 3)), M[0], bool(flip))
+        got = r["img"][0] if not chw else np.transpose(r["img"][0], (1, 2, 0))
+        assert np.array_equal(got, oimg), "%d warped pixels differ" % int((got != oimg).sum())
+        assert np.array_equal(r["mask"][0], omask)
