@@ -128,7 +128,7 @@ constexpr int kTilesPerSample = kTilesX * kTilesX;    // 144
 constexpr int kTabBytes = 32 * 32 * 8 * 4;            // dp4a table
 constexpr int kGroupThreads = 128;
 constexpr int kGeoInts = 4 * kTile;                   // X0, Y0, ad, bd
-constexpr int kGroupFixedBytes = 2 * kGeoInts * 4;    // double-buffered geometry
+constexpr int kGroupFixedBytes = 4 * kGeoInts * 4;    // geometry ring (3 used): tile k, k+1 (prefetch), k+2 (being built)
 constexpr unsigned kBorderWord = 0xFF7F7F7Fu;         // (B,G,R,mask) = (127,127,127,255)
 
 struct FusedArgs {
@@ -155,10 +155,12 @@ __device__ __forceinline__ void group_bar(int group) {
 template <bool kMask>
 __device__ __forceinline__ void bicubic_bgrm(const uint32_t *__restrict__ p, int fpitch,
                                              const uint32_t *__restrict__ wt, int &oB, int &oG, int &oR, int &oM) {
-    const uint4 wa = *reinterpret_cast<const uint4 *>(wt);      // rows 0,1: {hi,lo,hi,lo}
-    const uint4 wb = *reinterpret_cast<const uint4 *>(wt + 4);  // rows 2,3
-    const unsigned whi[4] = {wa.x, wa.z, wb.x, wb.z};
-    const unsigned wlo[4] = {wa.y, wa.w, wb.y, wb.w};
+    // hi bytes (s8 x4 per tap row) and lo bytes (u8 x4) of the 16 int16 weights of this phase live in
+    // two tables of 16-byte entries: a quarter-warp's LDS.128 then spreads over all 8 bank groups
+    const uint4 wa = *reinterpret_cast<const uint4 *>(wt);
+    const uint4 wb = *reinterpret_cast<const uint4 *>(wt + kTabBytes / 8);
+    const unsigned whi[4] = {wa.x, wa.y, wa.z, wa.w};
+    const unsigned wlo[4] = {wb.x, wb.y, wb.z, wb.w};
     int hB = 0, hG = 0, hR = 0, hM = 0;
     int lB = 16384, lG = 16384, lR = 16384, lM = 16384;   // rounding term of the >>15
 #pragma unroll
@@ -263,7 +265,7 @@ __device__ __forceinline__ unsigned fused_row(const TileCtx &c, int ly, bool lan
     if (c.mode == 0) {
         int oB, oG, oR, oM;
         const uint32_t *p = c.foot + ((Y >> 5) - 1 - c.by0) * c.fpitch + ((X >> 5) - 1 - c.bx0);
-        const uint32_t *wt = c.tab + (((Y & 31) * 32 + (X & 31)) << 3);
+        const uint32_t *wt = c.tab + (((Y & 31) * 32 + (X & 31)) << 2);
         bicubic_bgrm<kMask>(p, c.fpitch, wt, oB, oG, oR, oM);
         return (unsigned)oB | ((unsigned)oG << 8) | ((unsigned)oR << 16) | ((unsigned)oM << 24);
     }
@@ -298,10 +300,14 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
     uint32_t *foot = reinterpret_cast<uint32_t *>(gbase);
     int *geo = reinterpret_cast<int *>(gbase + (size_t)a.foot_cap * 4);
 
-    {   // dp4a weight table -> shared memory, once per persistent CTA
+    {   // dp4a weight table -> shared memory, once per persistent CTA: [phase][row]{hi,lo} -> hi[phase][row], lo[phase][row]
         const uint4 *src = reinterpret_cast<const uint4 *>(a.tab_dp4a);
         uint4 *dst = reinterpret_cast<uint4 *>(s_tab);
-        for (int i = threadIdx.x; i < kTabBytes / 16; i += NG * kGroupThreads) dst[i] = __ldg(src + i);
+        for (int e = threadIdx.x; e < 1024; e += NG * kGroupThreads) {
+            const uint4 r01 = __ldg(src + 2 * e), r23 = __ldg(src + 2 * e + 1);
+            dst[e] = make_uint4(r01.x, r01.z, r23.x, r23.z);
+            dst[1024 + e] = make_uint4(r01.y, r01.w, r23.y, r23.w);
+        }
     }
 
     const int l7 = lane & 7;
@@ -329,10 +335,28 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
         if (t == 0 && !ok && tt == 0) atomicOr(a.status + sample, RMPE_ST_SINGULAR);
     };
 
+    // footprint bounding box of a tile from its 4 corners: X(x,y) = (X0[y]+ad[x])>>5 is monotone in x and y
+    auto bbox = [&](const int *g, int tw, int th, int &mnx, int &mxx, int &mny, int &mxy) -> bool {
+        mnx = INT_MAX; mxx = INT_MIN; mny = INT_MAX; mxy = INT_MIN;
+        bool sane = true;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int cx = (c & 1) ? tw - 1 : 0, cy = (c & 2) ? th - 1 : 0;
+            const int qx = (g[cy] + g[2 * kTile + cx]) >> 10, qy = (g[kTile + cy] + g[3 * kTile + cx]) >> 10;
+            sane = sane && qx > -30000 && qx < 30000 && qy > -30000 && qy < 30000;  // no short saturation
+            mnx = min(mnx, qx - 1); mxx = max(mxx, qx + 2);
+            mny = min(mny, qy - 1); mxy = max(mxy, qy + 2);
+        }
+        return sane;
+    };
+
     const int stride = gridDim.x * NG;
     int item = blockIdx.x * NG + group;
-    if (item < n_items && t < 2 * kTile) geometry(item, 0);
-    __syncthreads();   // weight table + first geometry
+    if (t < 2 * kTile) {
+        if (item < n_items) geometry(item, 0);
+        if (item + stride < n_items) geometry(item + stride, 1);
+    }
+    __syncthreads();   // weight table + first two geometries
 
     for (int k = 0; item < n_items; item += stride, k++) {
         const int sample = item / kTilesPerSample;
@@ -343,64 +367,85 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
         const RmpeSrcDesc d = a.desc[sample];
         const uint8_t *img = a.src_img + d.img_offset;
         const uint8_t *msk = a.src_mask + d.mask_offset;
-        const int *gX0 = geo + (k & 1) * kGeoInts, *gY0 = gX0 + kTile, *gad = gY0 + kTile, *gbd = gad + kTile;
+        const int *gX0 = geo + (k % 3) * kGeoInts, *gY0 = gX0 + kTile, *gad = gY0 + kTile, *gbd = gad + kTile;
 
-        // footprint from the 4 corners: X(x,y) = (X0[y]+ad[x])>>5 is monotone in x and in y
-        int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
-        bool sane = true;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const int cx = (c & 1) ? tw - 1 : 0, cy = (c & 2) ? th - 1 : 0;
-            const int qx = (gX0[cy] + gad[cx]) >> 10, qy = (gY0[cy] + gbd[cx]) >> 10;
-            sane = sane && qx > -30000 && qx < 30000 && qy > -30000 && qy < 30000;  // no short saturation
-            mnx = min(mnx, qx - 1); mxx = max(mxx, qx + 2);
-            mny = min(mny, qy - 1); mxy = max(mxy, qy + 2);
-        }
-        // rows 16-byte aligned -> 128-bit loads of 16 pixels; the footprint then starts on a multiple of 16
-        const bool wide = ((((size_t)img | (size_t)msk) & 15) == 0) && (((d.img_pitch | d.mask_pitch) & 15) == 0);
-        const int bx0 = wide ? (mnx & ~15) : mnx, by0 = mny;
+        int mnx, mxx, mny, mxy;
+        const bool sane = bbox(gX0, tw, th, mnx, mxx, mny, mxy);
+        // 4-byte aligned sources are read with plain 32-bit loads; the footprint then starts on a multiple of 4
+        const bool al4 = ((((size_t)img | (size_t)msk) & 3) == 0) && (((d.img_pitch | d.mask_pitch) & 3) == 0);
+        const int bx0 = al4 ? (mnx & ~3) : mnx, by0 = mny;
         const int fw = mxx - bx0 + 1, fh = mxy - mny + 1;
-        const int fwa = wide ? ((fw + 15) & ~15) : ((fw + 3) & ~3);
-        int fpitch = ((fwa + 15) & ~31) + 16;                       // = 16 (mod 32), >= fwa
+        const int fwa = (fw + 3) & ~3;
+        int fpitch = (fwa + 31) & ~31;     // = 0 (mod 32): the bank of a tap is its column, whatever its row
         if ((long long)fpitch * fh > a.foot_cap) fpitch = fwa;
         const bool outside = sane && (mxx < 0 || mnx >= d.width || mxy < 0 || mny >= d.height);
         const bool staged = sane && !outside && (long long)fpitch * fh <= a.foot_cap;
 
-        // ---- stage the footprint as (B,G,R,mask) words ----
+        // ---- stage the footprint as (B,G,R,mask) words: one thread = 4 pixels = one 16-byte store ----
         if (staged) {
-            if (wide) {
-                const int n16 = fwa >> 4;
-                for (int it = t; it < fh * n16; it += kGroupThreads) {
-                    const int r = it / n16, c = (it - r * n16) << 4;
-                    const int yy = by0 + r, xx = bx0 + c;
-                    uint4 *dst = reinterpret_cast<uint4 *>(foot + r * fpitch + c);
-                    if ((unsigned)yy < (unsigned)d.height && xx >= 0 && xx + 15 < d.width) {
-                        const uint4 *ip = reinterpret_cast<const uint4 *>(img + (size_t)yy * d.img_pitch + 3 * xx);
-                        const uint4 i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
-                        const uint4 mq = __ldg(reinterpret_cast<const uint4 *>(msk + (size_t)yy * d.mask_pitch + xx));
-                        dst[0] = bgrm_pack4(i0.x, i0.y, i0.z, mq.x);
-                        dst[1] = bgrm_pack4(i0.w, i1.x, i1.y, mq.y);
-                        dst[2] = bgrm_pack4(i1.z, i1.w, i2.x, mq.z);
-                        dst[3] = bgrm_pack4(i2.y, i2.z, i2.w, mq.w);
-                    } else {
-#pragma unroll 1
-                        for (int q = 0; q < 4; q++)
-                            dst[q] = bgrm_load4(img, msk, d.height, d.width, d.img_pitch, d.mask_pitch, yy, xx + 4 * q);
-                    }
+            // 16 threads x 4 pixels per footprint row; two rows (r, r+8) in flight per thread and pass
+            for (int r = t >> 4; r < fh; r += 2 * (kGroupThreads / 16))
+            for (int c = (t & 15) << 2; c < fwa; c += 64) {
+                const int xx = bx0 + c;
+                const int r1 = r + kGroupThreads / 16;
+                const int ya = by0 + r, yb = by0 + r1;
+                const bool xin = al4 && xx >= 0 && xx + 3 < d.width;
+                const bool fa = xin && (unsigned)ya < (unsigned)d.height;
+                const bool fb = xin && (unsigned)yb < (unsigned)d.height && r1 < fh;
+                unsigned qa0 = 0, qa1 = 0, qa2 = 0, qam = 0, qb0 = 0, qb1 = 0, qb2 = 0, qbm = 0;
+                if (fa) {
+                    const uint32_t *ip = reinterpret_cast<const uint32_t *>(img + (size_t)ya * d.img_pitch + 3 * xx);
+                    qa0 = __ldg(ip); qa1 = __ldg(ip + 1); qa2 = __ldg(ip + 2);
+                    qam = __ldg(reinterpret_cast<const uint32_t *>(msk + (size_t)ya * d.mask_pitch + xx));
                 }
-            } else {
-                const int n4 = fwa >> 2;
-                for (int it = t; it < fh * n4; it += kGroupThreads) {
-                    const int r = it / n4, c = (it - r * n4) << 2;
-                    *reinterpret_cast<uint4 *>(foot + r * fpitch + c) =
-                        bgrm_load4(img, msk, d.height, d.width, d.img_pitch, d.mask_pitch, by0 + r, bx0 + c);
+                if (fb) {
+                    const uint32_t *ip = reinterpret_cast<const uint32_t *>(img + (size_t)yb * d.img_pitch + 3 * xx);
+                    qb0 = __ldg(ip); qb1 = __ldg(ip + 1); qb2 = __ldg(ip + 2);
+                    qbm = __ldg(reinterpret_cast<const uint32_t *>(msk + (size_t)yb * d.mask_pitch + xx));
                 }
+                *reinterpret_cast<uint4 *>(foot + r * fpitch + c) =
+                    fa ? bgrm_pack4(qa0, qa1, qa2, qam)
+                       : bgrm_load4(img, msk, d.height, d.width, d.img_pitch, d.mask_pitch, ya, xx);
+                if (r1 < fh)
+                    *reinterpret_cast<uint4 *>(foot + r1 * fpitch + c) =
+                        fb ? bgrm_pack4(qb0, qb1, qb2, qbm)
+                           : bgrm_load4(img, msk, d.height, d.width, d.img_pitch, d.mask_pitch, yb, xx);
             }
         }
         group_bar(group);     // footprint visible
 
-        // geometry of the next tile, overlapped with this tile's taps
-        if (item + stride < n_items && t < 2 * kTile) geometry(item + stride, (k + 1) & 1);
+        // two tiles ahead: geometry; one tile ahead: pull the footprint's lines into L2 -- both overlap this tile's taps
+        if (item + 2 * stride < n_items && t < 2 * kTile) geometry(item + 2 * stride, (k + 2) % 3);
+        if (item + stride < n_items) {
+            const int ni = item + stride;
+            const int ns = ni / kTilesPerSample, ntt = ni - ns * kTilesPerSample;
+            const int nty = ntt / kTilesX, ntx = ntt - nty * kTilesX;
+            int pnx, pxx, pny, pxy;
+            if (bbox(geo + ((k + 1) % 3) * kGeoInts, min(kTile, kOutW - ntx * kTile), min(kTile, kOutH - nty * kTile), pnx,
+                     pxx, pny, pxy)) {
+                const RmpeSrcDesc nd = a.desc[ns];
+                pnx = max(pnx, 0); pxx = min(pxx, nd.width - 1);
+                pny = max(pny, 0); pxy = min(pxy, nd.height - 1);
+                const int rows = pxy - pny + 1;
+                if (pxx >= pnx && rows > 0 && rows <= 256) {
+                    // per row: up to 3 image lines + 1 mask line of 128 bytes (wider footprints: first 384 bytes)
+                    for (int i = t; i < rows * 4; i += kGroupThreads) {
+                        const int row = pny + (i >> 2), seg = i & 3;
+                        const uint8_t *pa;
+                        bool on = true;
+                        if (seg < 3) {
+                            const uint8_t *rb = a.src_img + nd.img_offset + (size_t)row * nd.img_pitch;
+                            pa = rb + 3 * pnx + seg * 128;
+                            on = pa <= rb + 3 * pxx + 2 + 127;
+                            if (pa > rb + 3 * pxx + 2) pa = rb + 3 * pxx + 2;
+                        } else {
+                            pa = a.src_mask + nd.mask_offset + (size_t)row * nd.mask_pitch + pnx;
+                        }
+                        if (on) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+                    }
+                }
+            }
+        }
 
         // ---- taps, mask reduction, stores: warp = cell row ----
         if (8 * warp < th) {
