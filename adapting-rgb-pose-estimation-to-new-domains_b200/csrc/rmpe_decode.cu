@@ -9,6 +9,10 @@
 //
 // All float arithmetic follows the order of operations of OpenCV 4.13 (resize.cpp, SSE baseline:
 // no FMA) and SciPy (ni_filters.c symmetric correlate, f64 accumulate), see oracle/decode_oracle.py.
+#include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
 #include <vector>
 
 #include "rmpe_common.cuh"
@@ -317,6 +321,311 @@ __global__ void __launch_bounds__(kSmoothThreads) k_smooth_peaks(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------
+// Fast peak path for single-scale frames: screen in float32, decide in the reference's arithmetic.
+//
+// Up-sampling (cv2.resize, replicate border) and smoothing (scipy gaussian, reflect border) are
+// both linear and separable, so the smoothed map is  S = Ky * blob * Kx^T  with composite
+// per-axis operators  K = G * R  that have ~(24 h/H + 5) non-zeros per row.
+//   k_axis_tables  builds K (f64 accumulation, stored f32) and the first source index per row.
+//   k_heat_screen  evaluates S~ = Ky * blob * Kx^T straight from the NHWC blob (the 57x larger
+//                  up-sampled map is never written), and emits every pixel that could be a peak
+//                  once a rigorous bound delta on |S~ - S| is allowed for: S~ > thre1 - delta and
+//                  S~ >= neighbour~ - 2 delta for the four neighbours.
+//   k_peak_verify  re-evaluates each such pixel and its four neighbours EXACTLY -- cv2's float32
+//                  tap order, scipy's f64 accumulation order and per-axis float32 store -- and
+//                  applies the reference's test; survivors go to the same raw lists that
+//                  k_smooth_peaks fills, so ordering/ids are restored by k_peaks_finalize.
+// delta: S and S~ are sums of <= ~60 rounded float32 operations on terms bounded by
+// (sum|Ky|)(sum|Kx|) max|blob| <= 1.9 max|blob| (bicubic a=-0.75: sum|c| <= 1.375; Gaussian: 1),
+// i.e. |S~ - S| <= 60 * 2^-24 * 1.9 * max|blob| = 6.8e-6 max|blob|; kScreenDelta = 2e-5 of the
+// tile's max|blob| leaves a 3x margin.
+// ------------------------------------------------------------------------------------------
+constexpr int kScrTW = 126;          // interior columns of a screening tile
+constexpr int kScrTH = 32;           // interior rows
+constexpr int kScrCols = kScrTW + 2; // with the 1-pixel ring the 4-neighbour test needs
+constexpr int kScrRows = kScrTH + 2;
+constexpr int kScrThreads = 256;
+constexpr int kScrMaxSrcRows = 16;   // staged blob rows per tile (dense vertical operator)
+constexpr int kScrMaxKW = 12;        // non-zeros per row of Kx
+constexpr float kScreenDelta = 2.0e-5f;
+
+struct AxisJob {
+    int dst, src, kw;
+    float *K;    // [dst][kw]
+    int *lo;     // [dst]
+};
+struct AxisJobs {
+    AxisJob j[2 * kChunkFrames];
+};
+
+__global__ void __launch_bounds__(128) k_axis_tables(const __grid_constant__ AxisJobs jobs, int32_t *__restrict__ err) {
+    const AxisJob &J = jobs.j[blockIdx.y];
+    const int d = blockIdx.x * 128 + threadIdx.x;
+    if (d >= J.dst) return;
+    const double scale = resize_scale(J.dst, J.src, 0.0);
+    int lo = INT_MAX, hi = INT_MIN;
+    for (int t = -kSR; t <= kSR; t++) {
+        float co[4];
+        const int s = resize_axis(reflect_idx(d + t, J.dst), scale, co);
+        lo = min(lo, clampi(s - 1, 0, J.src - 1));
+        hi = max(hi, clampi(s + 2, 0, J.src - 1));
+    }
+    double acc[24];
+#pragma unroll
+    for (int i = 0; i < 24; i++) acc[i] = 0.0;
+    if (hi - lo + 1 > J.kw || J.kw > 24) { atomicOr(err, 1); hi = lo + min(J.kw, 24) - 1; }
+    for (int t = -kSR; t <= kSR; t++) {
+        float co[4];
+        const int s = resize_axis(reflect_idx(d + t, J.dst), scale, co);
+        const double g = c_gauss[12 - abs(t)];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int idx = clampi(s - 1 + k, 0, J.src - 1) - lo;
+#pragma unroll
+            for (int i = 0; i < 24; i++)
+                if (i == idx) acc[i] = fma(g, (double)co[k], acc[i]);
+        }
+    }
+    J.lo[d] = lo;
+#pragma unroll
+    for (int i = 0; i < 24; i++)
+        if (i < J.kw) J.K[(size_t)d * J.kw + i] = (float)acc[i];
+}
+
+struct ScreenJob {
+    const float *heat;    // NHWC (h,w,19) blob of the frame
+    const float *Ky, *Kx;
+    const int *loy, *lox;
+    int H, W, h, w, kwy, kwx;
+    int frame, tiles_x, tiles;
+};
+struct ScreenJobs {
+    ScreenJob j[kChunkFrames];
+};
+
+template <int KWX>
+__global__ void __launch_bounds__(kScrThreads) k_heat_screen(const __grid_constant__ ScreenJobs jobs, float thre1,
+                                                              int cand_cap, int32_t *__restrict__ cand_key,
+                                                              int32_t *__restrict__ cand_fp,
+                                                              int32_t *__restrict__ cand_count,
+                                                              const int32_t *__restrict__ tab_err,
+                                                              int32_t *__restrict__ status) {
+    const ScreenJob &J = jobs.j[blockIdx.y];
+    if ((int)blockIdx.x >= J.tiles) return;
+    if (*tab_err) {   // an operator row did not fit its table (cannot happen with plan_frame's bound): never screen on it
+        if (threadIdx.x == 0) atomicOr(status + J.frame, RMPE_ST_PEAK_OVERFLOW);
+        return;
+    }
+    const int H = J.H, W = J.W, h = J.h, w = J.w;
+    const int ty = blockIdx.x / J.tiles_x, tx = blockIdx.x - ty * J.tiles_x;
+    const int y0 = ty * kScrTH, x0 = tx * kScrTW;          // first interior pixel
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int col = tid & (kScrCols - 1), half = tid >> 7;  // 128 columns x 2 row halves
+
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    __shared__ int s_rng[4];            // r0, r1, c0, c1 of the staged blob region
+    __shared__ int s_bmax[kHeatC];      // max |blob| per channel over the staged region (float bits)
+    __shared__ int s_loy[kScrRows];
+
+    // ---- staged source region ----
+    if (tid < 4) s_rng[tid] = (tid & 1) ? INT_MIN : INT_MAX;
+    if (tid < kHeatC) s_bmax[tid] = 0;
+    __syncthreads();
+    if (tid < kScrRows) {
+        const int y = clampi(y0 - 1 + tid, 0, H - 1);
+        const int lo = J.loy[y];
+        s_loy[tid] = lo;
+        atomicMin(&s_rng[0], lo);
+        atomicMax(&s_rng[1], min(lo + J.kwy - 1, h - 1));
+    }
+    const int xg = clampi(x0 - 1 + col, 0, W - 1);          // this thread's (clamped) column
+    const int mylox = J.lox[xg];
+    if (half == 0) {
+        atomicMin(&s_rng[2], mylox);
+        atomicMax(&s_rng[3], min(mylox + KWX - 1, w - 1));
+    }
+    __syncthreads();
+    const int r0 = s_rng[0], c0 = s_rng[2];
+    const int nrows = s_rng[1] - r0 + 1, ncols = s_rng[3] - c0 + 1;
+    float *sB = reinterpret_cast<float *>(sm_raw);                   // [nrows][ncols][19]
+    float *sT = sB + ((nrows * ncols * kHeatC + 3) & ~3);            // [nrows][128]
+    float *sS = sT + nrows * kScrCols;                               // [34][128]
+    float *sKy = sS + kScrRows * kScrCols;                           // [34][kScrMaxSrcRows] dense over staged rows
+    if (nrows > kScrMaxSrcRows) {   // host sized the launch for this never to happen
+        if (tid == 0) atomicOr(status + J.frame, RMPE_ST_PEAK_OVERFLOW);
+        return;
+    }
+    {
+        const int rowlen = ncols * kHeatC;
+        for (int i = tid; i < nrows * rowlen; i += kScrThreads) {
+            const int r = i / rowlen, e = i - r * rowlen;
+            sB[i] = J.heat[((size_t)(r0 + r) * w + c0) * kHeatC + e];
+        }
+        // dense vertical operator of the tile: sKy[row][i] = Ky[y][i - (loy[y]-r0)] or 0
+        for (int i = tid; i < kScrRows * kScrMaxSrcRows; i += kScrThreads) {
+            const int r = i / kScrMaxSrcRows, q = i - r * kScrMaxSrcRows;
+            const int y = clampi(y0 - 1 + r, 0, H - 1);
+            const int k = q - (s_loy[r] - r0);
+            sKy[i] = (k >= 0 && k < J.kwy) ? J.Ky[(size_t)y * J.kwy + k] : 0.f;
+        }
+    }
+    float kxw[KWX];
+#pragma unroll
+    for (int j = 0; j < KWX; j++) kxw[j] = (j < J.kwx) ? J.Kx[(size_t)xg * J.kwx + j] : 0.f;
+    const int off = mylox - c0;     // first staged column of this thread's taps
+    __syncthreads();
+
+    for (int part = 0; part < kParts; part++) {
+        {   // max |blob| of this part over the staged region (scales delta)
+            float m = 0.f;
+            for (int i = tid; i < nrows * ncols; i += kScrThreads) m = fmaxf(m, fabsf(sB[i * kHeatC + part]));
+            const int mi = __reduce_max_sync(0xffffffffu, __float_as_int(m));
+            if (lane == 0) atomicMax(&s_bmax[part], mi);
+        }
+        // ---- horizontal: T[i][col] = sum_j Kx[col][j] * B[i][lox+j][part] ----
+        for (int i = half; i < nrows; i += 2) {
+            const float *b = sB + ((size_t)i * ncols + off) * kHeatC + part;
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < KWX; j++)
+                if (off + j < ncols) acc = fmaf(kxw[j], b[j * kHeatC], acc);   // beyond: zero padding of Kx
+            sT[i * kScrCols + col] = acc;
+        }
+        __syncthreads();
+        // ---- vertical: S[r][col] = sum_i sKy[r][i] * T[i][col], 17 rows per thread ----
+        float tcol[kScrMaxSrcRows];
+#pragma unroll
+        for (int i = 0; i < kScrMaxSrcRows; i++) tcol[i] = (i < nrows) ? sT[i * kScrCols + col] : 0.f;
+#pragma unroll 1
+        for (int q = 0; q < kScrRows / 2; q++) {
+            const int r = half * (kScrRows / 2) + q;
+            const float4 *ky = reinterpret_cast<const float4 *>(sKy + r * kScrMaxSrcRows);
+            float acc = 0.f;
+#pragma unroll
+            for (int i4 = 0; i4 < kScrMaxSrcRows / 4; i4++) {
+                const float4 k4 = ky[i4];
+                acc = fmaf(k4.x, tcol[4 * i4 + 0], acc);
+                acc = fmaf(k4.y, tcol[4 * i4 + 1], acc);
+                acc = fmaf(k4.z, tcol[4 * i4 + 2], acc);
+                acc = fmaf(k4.w, tcol[4 * i4 + 3], acc);
+            }
+            sS[r * kScrCols + col] = acc;
+        }
+        __syncthreads();
+        // ---- conservative 4-neighbour test on the interior ----
+        const float delta = kScreenDelta * __int_as_float(s_bmax[part]);
+        const float lim = thre1 - delta, d2 = 2.f * delta;
+        for (int q = 0; q < kScrTH / 2; q++) {
+            const int r = 1 + half * (kScrTH / 2) + q;
+            const int y = y0 + r - 1, x = x0 + col - 1;
+            bool cand = false;
+            if (col >= 1 && col <= kScrTW && y < H && x < W) {
+                const float sv = sS[r * kScrCols + col];
+                if (sv > lim) {
+                    const float up = (y > 0) ? sS[(r - 1) * kScrCols + col] : 0.f;
+                    const float dn = (y < H - 1) ? sS[(r + 1) * kScrCols + col] : 0.f;
+                    const float lf = (x > 0) ? sS[r * kScrCols + col - 1] : 0.f;
+                    const float rt = (x < W - 1) ? sS[r * kScrCols + col + 1] : 0.f;
+                    cand = (sv >= up - d2) && (sv >= dn - d2) && (sv >= lf - d2) && (sv >= rt - d2);
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, cand);
+            if (bal) {
+                const int leader = __ffs(bal) - 1;
+                int slot0 = 0;
+                if (lane == leader) slot0 = atomicAdd(cand_count, __popc(bal));
+                slot0 = __shfl_sync(0xffffffffu, slot0, leader);
+                if (cand) {
+                    const int slot = slot0 + __popc(bal & ((1u << lane) - 1));
+                    if (slot < cand_cap) {
+                        cand_key[slot] = y * W + x;
+                        cand_fp[slot] = J.frame * kParts + part;
+                    } else {
+                        atomicOr(status + J.frame, RMPE_ST_PEAK_OVERFLOW);
+                    }
+                }
+            }
+        }
+        // sT / sS are rewritten only after the next part's barriers
+    }
+}
+
+// one CTA per screened pixel: exact S at the pixel and its four neighbours
+constexpr int kVerThreads = 128;
+constexpr int kVerN = 2 * kSR + 3;   // 27: the pixel +-1, +-12
+
+__global__ void __launch_bounds__(kVerThreads) k_peak_verify(const RmpeFrameDesc *__restrict__ frames,
+                                                            const float *__restrict__ heat, float thre1, int cand_cap,
+                                                            const int32_t *__restrict__ cand_key,
+                                                            const int32_t *__restrict__ cand_fp,
+                                                            const int32_t *__restrict__ cand_count, int max_peaks,
+                                                            int32_t *__restrict__ raw_key, double *__restrict__ raw_score,
+                                                            int32_t *__restrict__ raw_count, int32_t *__restrict__ status) {
+    __shared__ float sU[kVerN][kVerN + 1];
+    __shared__ float sA[3][kVerN + 1];
+    __shared__ float sS5[5];
+    const int total = min(*cand_count, cand_cap);
+    const int tid = threadIdx.x;
+    for (int ci = blockIdx.x; ci < total; ci += gridDim.x) {
+        const int fp = cand_fp[ci], key = cand_key[ci];
+        const int frame = fp / kParts, part = fp - frame * kParts;
+        const RmpeFrameDesc f = frames[frame];
+        const int H = f.height, W = f.width;
+        const int y = key / W, x = key - y * W;
+        const float *blob = heat + f.heat_offset[0];
+        // U on the 27x27 reflected neighbourhood, cv2.resize arithmetic
+        for (int i = tid; i < kVerN * kVerN; i += kVerThreads) {
+            const int a = i / kVerN, b = i - a * kVerN;
+            sU[a][b] = resize_point_blob(blob, f.grid_h[0], f.grid_w[0], kHeatC, part, reflect_idx(y - kSR - 1 + a, H),
+                                         reflect_idx(x - kSR - 1 + b, W), H, W, 0.0);
+        }
+        __syncthreads();
+        // axis 0 on rows y-1, y, y+1 (scipy order, f64 accumulate, float32 store)
+        for (int i = tid; i < 3 * kVerN; i += kVerThreads) {
+            const int rr = i / kVerN, b = i - rr * kVerN;
+            const int a = kSR + rr;   // local row of y-1+rr
+            double tmp = __dmul_rn((double)sU[a][b], c_gauss[12]);
+#pragma unroll
+            for (int j = -kSR; j < 0; j++) {
+                const double pair = __dadd_rn((double)sU[a + j][b], (double)sU[a - j][b]);
+                tmp = __dadd_rn(tmp, __dmul_rn(pair, c_gauss[12 + j]));
+            }
+            sA[rr][b] = (float)tmp;
+        }
+        __syncthreads();
+        // axis 1 at (y,x), (y-1,x), (y+1,x), (y,x-1), (y,x+1)
+        if (tid < 5) {
+            const int rr = (tid == 1) ? 0 : (tid == 2) ? 2 : 1;
+            const int b = kSR + 1 + ((tid == 3) ? -1 : (tid == 4) ? 1 : 0);
+            double tmp = __dmul_rn((double)sA[rr][b], c_gauss[12]);
+#pragma unroll
+            for (int j = -kSR; j < 0; j++) {
+                const double pair = __dadd_rn((double)sA[rr][b + j], (double)sA[rr][b - j]);
+                tmp = __dadd_rn(tmp, __dmul_rn(pair, c_gauss[12 + j]));
+            }
+            sS5[tid] = (float)tmp;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const float sv = sS5[0];
+            const float up = (y > 0) ? sS5[1] : 0.f, dn = (y < H - 1) ? sS5[2] : 0.f;
+            const float lf = (x > 0) ? sS5[3] : 0.f, rt = (x < W - 1) ? sS5[4] : 0.f;
+            if ((sv >= up) && (sv >= dn) && (sv >= lf) && (sv >= rt) && (sv > thre1)) {
+                const int slot = atomicAdd(raw_count + fp, 1);
+                if (slot < max_peaks) {
+                    const size_t o = (size_t)fp * max_peaks + slot;
+                    raw_key[o] = key;
+                    raw_score[o] = (double)sU[kSR + 1][kSR + 1];
+                } else {
+                    atomicOr(status + frame, RMPE_ST_PEAK_OVERFLOW);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // k_peaks_finalize: restore np.nonzero order (ascending y*W+x) per part, assign consecutive ids
 // across parts, write candidate rows [x, y, score, id] and the per-part peak tables.
 // ------------------------------------------------------------------------------------------
@@ -621,6 +930,9 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
 // host side
 // ==========================================================================================
 struct FramePlan {
+    bool screen;         // single-scale frame decoded through k_heat_screen / k_peak_verify
+    int kwy, kwx;        // non-zeros per row of the composite operators
+    int nrows_b, ncols_b;  // bounds on the staged blob region of a screening tile
     bool multi;
     size_t u_elems;      // 18*H*W (T)
     size_t p1_elems;     // floats
@@ -631,10 +943,27 @@ struct FramePlan {
 
 static size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-static FramePlan plan_frame(const RmpeFrameDesc &f, int stride) {
+static int ceil_div_d(double a) { return (int)ceil(a - 1e-9); }
+
+static FramePlan plan_frame(const RmpeFrameDesc &f, int stride, bool allow_screen = true) {
     FramePlan p{};
     p.multi = f.n_scales > 1;
     p.u_elems = (size_t)kParts * f.height * f.width;
+    if (!p.multi) {
+        // composite operator supports: a 25-tap window of destination pixels spans 24*src/dst source pixels
+        const int h = f.grid_h[0], w = f.grid_w[0];
+        p.kwy = ceil_div_d(24.0 * h / f.height) + 6;
+        p.kwx = ceil_div_d(24.0 * w / f.width) + 6;
+        p.nrows_b = std::min(h, ceil_div_d((double)kScrRows * h / f.height) + p.kwy + 1);
+        p.ncols_b = std::min(w, ceil_div_d((double)kScrCols * w / f.width) + p.kwx + 1);
+        static const bool off = getenv("RMPE_DECODE_EXACT_MAPS") != nullptr;   // debugging: force the full-map path
+        p.screen = allow_screen && !off && p.kwy <= 24 && p.kwx <= kScrMaxKW && p.nrows_b <= kScrMaxSrcRows && p.ncols_b <= 64;
+    }
+    if (p.screen) {
+        p.u_elems = 0;
+        p.bytes = al256(((size_t)f.height * (p.kwy + 1) + (size_t)f.width * (p.kwx + 1)) * 4);
+        return p;
+    }
     if (!p.multi) {
         p.p1_elems = (size_t)kParts * f.grid_h[0] * f.width;
     } else {
@@ -650,11 +979,17 @@ static FramePlan plan_frame(const RmpeFrameDesc &f, int stride) {
     return p;
 }
 
+static size_t screen_smem_bytes(int nrows_b, int ncols_b) {
+    return ((size_t)((nrows_b * ncols_b * kHeatC + 3) & ~3) + (size_t)nrows_b * kScrCols + (size_t)kScrRows * kScrCols +
+            (size_t)kScrRows * kScrMaxSrcRows) * 4;
+}
+
 static size_t fixed_ws_bytes(int batch, int max_peaks, int max_cand) {
     size_t per_list = (size_t)batch * kParts * max_peaks;
     return al256(per_list * 4) /*raw_key*/ + al256(per_list * 8) /*raw_score*/ + al256((size_t)batch * kParts * 4) /*raw_count*/ +
            al256(per_list * 4) * 2 /*pk_x, pk_y*/ + al256(per_list * 8) /*pk_s*/ +
-           al256((size_t)batch * kLimbs * max_cand * 4 * 8) /*ws_cand*/ + 4096;
+           al256((size_t)batch * kLimbs * max_cand * 4 * 8) /*ws_cand*/ +
+           al256(per_list * 2 * 4) * 2 /*cand_key, cand_fp*/ + 256 /*cand_count, tab_err*/ + 4096;
 }
 
 static bool frame_ok(const RmpeFrameDesc &f, int stride) {
@@ -669,14 +1004,15 @@ static bool frame_ok(const RmpeFrameDesc &f, int stride) {
 
 // heat maps of a chunk of frames -> U (planar [18][H][W], float single-scale / double multi-scale)
 static int launch_heat_up(const RmpeFrameDesc *fr, int n, const float *heat, int stride, uint8_t *const *u_ptr,
-                          float *const *p1_ptr, float *const *i1_ptr, float *const *p2_ptr, cudaStream_t st) {
+                          float *const *p1_ptr, float *const *i1_ptr, float *const *p2_ptr, const FramePlan *plans,
+                          cudaStream_t st) {
     // single-scale frames: blob -> (h x W) -> (H x W)
     {
         RJobs jh{}, jv{};
         int m = 0, maxc = 0, maxr_h = 0, maxr_v = 0;
         for (int i = 0; i < n; i++) {
             const RmpeFrameDesc &f = fr[i];
-            if (f.n_scales != 1) continue;
+            if (f.n_scales != 1 || (plans && plans[i].screen)) continue;
             int h = f.grid_h[0], w = f.grid_w[0];
             RJob &a = jh.j[m];
             a.src = heat + f.heat_offset[0]; a.dst = p1_ptr[i]; a.acc = nullptr;
@@ -758,6 +1094,10 @@ static int ensure_smooth_attr() {
                                        (int)smooth_smem_bytes(false)));
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_limbs, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kMaxCandCap * 12 + 2 * kMaxPeaksCap));
+    RMPE_CUDA_TRY(cudaFuncSetAttribute(k_heat_screen<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)screen_smem_bytes(kScrMaxSrcRows, 64)));
+    RMPE_CUDA_TRY(cudaFuncSetAttribute(k_heat_screen<kScrMaxKW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)screen_smem_bytes(kScrMaxSrcRows, 64)));
     done = true;
     return RMPE_OK;
 }
@@ -809,11 +1149,16 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
     int32_t *pk_y = (int32_t *)take(per_list * 4);
     double *pk_s = (double *)take(per_list * 8);
     double *ws_cand = (double *)take((size_t)B * kLimbs * MC * 4 * 8);
+    int32_t *cand_key = (int32_t *)take(per_list * 2 * 4);
+    int32_t *cand_fp = (int32_t *)take(per_list * 2 * 4);
+    int32_t *cand_count = (int32_t *)take(256);
+    int32_t *tab_err = cand_count + 1;
     RMPE_REQUIRE(off <= b->workspace_bytes, "workspace too small (see rmpe_decode_workspace_bytes)");
     const size_t frame_ws0 = off;
 
     RMPE_CUDA_TRY(cudaMemsetAsync(raw_count, 0, (size_t)B * kParts * 4, st));
     RMPE_CUDA_TRY(cudaMemsetAsync(b->status, 0, (size_t)B * 4, st));
+    RMPE_CUDA_TRY(cudaMemsetAsync(cand_count, 0, 256, st));
 
     int f0 = 0;
     while (f0 < B) {
@@ -822,30 +1167,89 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
         size_t o = frame_ws0;
         uint8_t *u_ptr[kChunkFrames];
         float *p1_ptr[kChunkFrames], *i1_ptr[kChunkFrames], *p2_ptr[kChunkFrames];
-        bool any_single = false, any_multi = false;
+        FramePlan plans[kChunkFrames];
+        bool any_single = false, any_multi = false, any_screen = false;
         while (f0 + n < B && n < kChunkFrames) {
             FramePlan p = plan_frame(b->frames_host[f0 + n], b->stride);
             if (o + p.bytes > b->workspace_bytes) break;
-            u_ptr[n] = ws + o; o += al256(p.u_elems * (p.multi ? 8 : 4));
-            p1_ptr[n] = (float *)(ws + o); o += al256(p.p1_elems * 4);
-            i1_ptr[n] = (float *)(ws + o); o += al256(p.i1_elems * 4);
-            p2_ptr[n] = (float *)(ws + o); o += al256(p.p2_elems * 4);
-            (p.multi ? any_multi : any_single) = true;
+            plans[n] = p;
+            if (p.screen) {
+                u_ptr[n] = ws + o; o += p.bytes;       // the frame's operator tables
+                p1_ptr[n] = i1_ptr[n] = p2_ptr[n] = nullptr;
+                any_screen = true;
+            } else {
+                u_ptr[n] = ws + o; o += al256(p.u_elems * (p.multi ? 8 : 4));
+                p1_ptr[n] = (float *)(ws + o); o += al256(p.p1_elems * 4);
+                i1_ptr[n] = (float *)(ws + o); o += al256(p.i1_elems * 4);
+                p2_ptr[n] = (float *)(ws + o); o += al256(p.p2_elems * 4);
+                (p.multi ? any_multi : any_single) = true;
+            }
             n++;
         }
         RMPE_REQUIRE(n > 0, "workspace too small for one frame (see rmpe_decode_workspace_bytes)");
         const RmpeFrameDesc *fr = b->frames_host + f0;
-        rc = launch_heat_up(fr, n, b->heat, b->stride, u_ptr, p1_ptr, i1_ptr, p2_ptr, st);
-        if (rc != RMPE_OK) return rc;
 
-        // smooth + peaks: one launch per map dtype present in the chunk
+        if (any_screen) {
+            // ---- screen in float32 straight from the blobs, decide exactly per surviving pixel ----
+            AxisJobs aj{};
+            ScreenJobs sj{};
+            int m = 0, max_tiles = 0, max_len = 0, nr = 0, nc = 0, kwx_max = 0;
+            for (int i = 0; i < n; i++) {
+                if (!plans[i].screen) continue;
+                const RmpeFrameDesc &f = fr[i];
+                const FramePlan &p = plans[i];
+                float *Ky = (float *)u_ptr[i];
+                int *loy = (int *)(Ky + (size_t)f.height * p.kwy);
+                float *Kx = (float *)(loy + f.height);
+                int *lox = (int *)(Kx + (size_t)f.width * p.kwx);
+                aj.j[2 * m] = AxisJob{f.height, f.grid_h[0], p.kwy, Ky, loy};
+                aj.j[2 * m + 1] = AxisJob{f.width, f.grid_w[0], p.kwx, Kx, lox};
+                ScreenJob &J = sj.j[m];
+                J.heat = b->heat + f.heat_offset[0];
+                J.Ky = Ky; J.Kx = Kx; J.loy = loy; J.lox = lox;
+                J.H = f.height; J.W = f.width; J.h = f.grid_h[0]; J.w = f.grid_w[0]; J.kwy = p.kwy; J.kwx = p.kwx;
+                J.frame = f0 + i;
+                J.tiles_x = (f.width + kScrTW - 1) / kScrTW;
+                J.tiles = J.tiles_x * ((f.height + kScrTH - 1) / kScrTH);
+                max_tiles = std::max(max_tiles, J.tiles);
+                max_len = std::max(max_len, std::max(f.height, f.width));
+                nr = std::max(nr, p.nrows_b); nc = std::max(nc, p.ncols_b); kwx_max = std::max(kwx_max, p.kwx);
+                m++;
+            }
+            const int cand_cap = (int)std::min<size_t>(per_list * 2, (size_t)n * kParts * MP * 2);
+            if (f0 > 0) RMPE_CUDA_TRY(cudaMemsetAsync(cand_count, 0, 4, st));
+            { ProfScope ps("k_axis_tables", st); k_axis_tables<<<dim3((max_len + 127) / 128, 2 * m), 128, 0, st>>>(aj, tab_err); }
+            {
+                ProfScope ps("k_heat_screen", st);
+                const size_t smem = screen_smem_bytes(nr, nc);
+                if (kwx_max <= 10)
+                    k_heat_screen<10><<<dim3(max_tiles, m), kScrThreads, smem, st>>>(sj, (float)b->thre1, cand_cap, cand_key,
+                                                                                  cand_fp, cand_count, tab_err, b->status);
+                else
+                    k_heat_screen<kScrMaxKW><<<dim3(max_tiles, m), kScrThreads, smem, st>>>(
+                        sj, (float)b->thre1, cand_cap, cand_key, cand_fp, cand_count, tab_err, b->status);
+            }
+            {
+                ProfScope ps("k_peak_verify", st);
+                const int grid = std::min(cand_cap, 8 * tables().sm_count);
+                k_peak_verify<<<grid, kVerThreads, 0, st>>>(b->frames, b->heat, (float)b->thre1, cand_cap, cand_key, cand_fp,
+                                                           cand_count, MP, raw_key, raw_score, raw_count, b->status);
+            }
+            count_launch(3);
+        }
+        if (any_single || any_multi) {
+            rc = launch_heat_up(fr, n, b->heat, b->stride, u_ptr, p1_ptr, i1_ptr, p2_ptr, plans, st);
+            if (rc != RMPE_OK) return rc;
+        }
+
+        // smooth + peaks on the materialised maps: one launch per map dtype present in the chunk
         for (int pass = 0; pass < 2; pass++) {
             bool multi = (pass == 1);
             if (!(multi ? any_multi : any_single)) continue;
             SmoothJobs sj{};
             int m = 0, max_tiles = 0;
             for (int i = 0; i < n; i++) {
-                if ((fr[i].n_scales > 1) != multi) continue;
+                if (plans[i].screen || (fr[i].n_scales > 1) != multi) continue;
                 sj.j[m].U = u_ptr[i]; sj.j[m].H = fr[i].height; sj.j[m].W = fr[i].width;
                 sj.j[m].frame = f0 + i; sj.j[m].S_out = nullptr;
                 int t = ((fr[i].height + kST - 1) / kST) * ((fr[i].width + kST - 1) / kST);
@@ -904,7 +1308,7 @@ extern "C" int rmpe_debug_heat_maps(const RmpeFrameDesc *f, const float *heat_de
     cudaStream_t st = (cudaStream_t)stream_;
     int rc = ensure_smooth_attr();
     if (rc != RMPE_OK) return rc;
-    FramePlan p = plan_frame(*f, 8);
+    FramePlan p = plan_frame(*f, 8, false);
     uint8_t *tmp = nullptr;
     size_t scratch = al256(p.p1_elems * 4) + al256(p.i1_elems * 4) + al256(p.p2_elems * 4) + al256(kParts * 8 * 4) * 3;
     RMPE_CUDA_TRY(cudaMalloc((void **)&tmp, scratch + 4096));
@@ -912,7 +1316,7 @@ extern "C" int rmpe_debug_heat_maps(const RmpeFrameDesc *f, const float *heat_de
     float *p1[1] = {(float *)tmp};
     float *i1[1] = {(float *)(tmp + al256(p.p1_elems * 4))};
     float *p2[1] = {(float *)(tmp + al256(p.p1_elems * 4) + al256(p.i1_elems * 4))};
-    rc = launch_heat_up(f, 1, heat_dev, 8, u_ptr, p1, i1, p2, st);
+    rc = launch_heat_up(f, 1, heat_dev, 8, u_ptr, p1, i1, p2, nullptr, st);
     if (rc == RMPE_OK && smooth_out_dev) {
         uint8_t *q = tmp + al256(p.p1_elems * 4) + al256(p.i1_elems * 4) + al256(p.p2_elems * 4);
         int32_t *cnt = (int32_t *)q;
