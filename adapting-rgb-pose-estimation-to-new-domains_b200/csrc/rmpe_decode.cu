@@ -361,7 +361,9 @@ struct AxisJobs {
 __global__ void __launch_bounds__(128) k_axis_tables(const __grid_constant__ AxisJobs jobs, int32_t *__restrict__ err) {
     const AxisJob &J = jobs.j[blockIdx.y];
     const int d = blockIdx.x * 128 + threadIdx.x;
+    __shared__ double s_acc[128][25];     // one accumulator row per thread (odd pitch: conflict-free)
     if (d >= J.dst) return;
+    double *acc = s_acc[threadIdx.x];
     const double scale = resize_scale(J.dst, J.src, 0.0);
     int lo = INT_MAX, hi = INT_MIN;
     for (int t = -kSR; t <= kSR; t++) {
@@ -370,10 +372,9 @@ __global__ void __launch_bounds__(128) k_axis_tables(const __grid_constant__ Axi
         lo = min(lo, clampi(s - 1, 0, J.src - 1));
         hi = max(hi, clampi(s + 2, 0, J.src - 1));
     }
-    double acc[24];
-#pragma unroll
-    for (int i = 0; i < 24; i++) acc[i] = 0.0;
-    if (hi - lo + 1 > J.kw || J.kw > 24) { atomicOr(err, 1); hi = lo + min(J.kw, 24) - 1; }
+    const int kw = min(J.kw, 24);
+    if (hi - lo + 1 > kw || J.kw > 24) { atomicOr(err, 1); hi = lo + kw - 1; }
+    for (int i = 0; i < kw; i++) acc[i] = 0.0;
     for (int t = -kSR; t <= kSR; t++) {
         float co[4];
         const int s = resize_axis(reflect_idx(d + t, J.dst), scale, co);
@@ -381,15 +382,11 @@ __global__ void __launch_bounds__(128) k_axis_tables(const __grid_constant__ Axi
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int idx = clampi(s - 1 + k, 0, J.src - 1) - lo;
-#pragma unroll
-            for (int i = 0; i < 24; i++)
-                if (i == idx) acc[i] = fma(g, (double)co[k], acc[i]);
+            if (idx < kw) acc[idx] = fma(g, (double)co[k], acc[idx]);
         }
     }
     J.lo[d] = lo;
-#pragma unroll
-    for (int i = 0; i < 24; i++)
-        if (i < J.kw) J.K[(size_t)d * J.kw + i] = (float)acc[i];
+    for (int i = 0; i < kw; i++) J.K[(size_t)d * J.kw + i] = (float)acc[i];
 }
 
 struct ScreenJob {
@@ -474,14 +471,20 @@ __global__ void __launch_bounds__(kScrThreads) k_heat_screen(const __grid_consta
     for (int j = 0; j < KWX; j++) kxw[j] = (j < J.kwx) ? J.Kx[(size_t)xg * J.kwx + j] : 0.f;
     const int off = mylox - c0;     // first staged column of this thread's taps
     __syncthreads();
+    // max |blob| per part over the staged region: scales delta and lets whole parts be skipped
+    for (int part = tid >> 5; part < kParts; part += kScrThreads / 32) {
+        float m = 0.f;
+        for (int i = lane; i < nrows * ncols; i += 32) m = fmaxf(m, fabsf(sB[i * kHeatC + part]));
+        const int mi = __reduce_max_sync(0xffffffffu, __float_as_int(m));
+        if (lane == 0) s_bmax[part] = mi;
+    }
+    __syncthreads();
 
     for (int part = 0; part < kParts; part++) {
-        {   // max |blob| of this part over the staged region (scales delta)
-            float m = 0.f;
-            for (int i = tid; i < nrows * ncols; i += kScrThreads) m = fmaxf(m, fabsf(sB[i * kHeatC + part]));
-            const int mi = __reduce_max_sync(0xffffffffu, __float_as_int(m));
-            if (lane == 0) atomicMax(&s_bmax[part], mi);
-        }
+        // A part whose staged blob values are all small cannot produce a peak in this tile:
+        // |S| <= (sum|Ky|)(sum|Kx|) max|blob| <= 1.375^2 max|blob| (+ rounding), a peak needs S > thre1.
+        const float bmax = __int_as_float(s_bmax[part]);
+        if (1.8907f * bmax + kScreenDelta * bmax <= thre1) continue;    // block-uniform
         // ---- horizontal: T[i][col] = sum_j Kx[col][j] * B[i][lox+j][part] ----
         for (int i = half; i < nrows; i += 2) {
             const float *b = sB + ((size_t)i * ncols + off) * kHeatC + part;
@@ -513,7 +516,7 @@ __global__ void __launch_bounds__(kScrThreads) k_heat_screen(const __grid_consta
         }
         __syncthreads();
         // ---- conservative 4-neighbour test on the interior ----
-        const float delta = kScreenDelta * __int_as_float(s_bmax[part]);
+        const float delta = kScreenDelta * bmax;
         const float lim = thre1 - delta, d2 = 2.f * delta;
         for (int q = 0; q < kScrTH / 2; q++) {
             const int r = 1 + half * (kScrTH / 2) + q;
@@ -833,14 +836,40 @@ __global__ void __launch_bounds__(kLimbThreads) k_limbs(const RmpeFrameDesc *__r
 // ------------------------------------------------------------------------------------------
 // k_assemble: one warp per frame; sequential person assembly, merge and prune.
 // ------------------------------------------------------------------------------------------
+constexpr int kAsmConnRows = 1024;   // connection rows of a frame held in shared memory (more: read from global)
+
 __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks, int max_persons,
                                                  const double *__restrict__ candidate,
                                                  const double *__restrict__ connections,
-                                                 const int32_t *__restrict__ n_conn, double *__restrict__ subset,
+                                                 const int32_t *__restrict__ n_conn, const int32_t *__restrict__ n_peaks,
+                                                 double *__restrict__ subset,
                                                  int32_t *__restrict__ n_subset, int32_t *__restrict__ status) {
     const int frame = first_frame + blockIdx.x, lane = threadIdx.x;
-    __shared__ double s_sub[kMaxSubsetCap + 1][20];
+    extern __shared__ __align__(16) double sm_asm[];
+    double(*s_sub)[20] = reinterpret_cast<double(*)[20]>(sm_asm);                 // [kMaxSubsetCap + 1][20]
+    double *s_conn = sm_asm + (kMaxSubsetCap + 1) * 20;                           // [kAsmConnRows][3]: idA, idB, score
+    double *s_score = s_conn + kAsmConnRows * 3;                                  // [18 * max_peaks] peak scores
+    __shared__ int s_off[kLimbs + 1];
     const double *cand = candidate + (size_t)frame * kParts * max_peaks * 4;
+    // ---- one pass over global memory: connection rows and peak scores of the frame ----
+    int ntot = 0;
+    for (int q = 0; q < kParts; q++) ntot += n_peaks[frame * kParts + q];
+    if (lane == 0) {
+        int o = 0;
+        for (int k = 0; k < kLimbs; k++) { s_off[k] = o; o += max(n_conn[frame * kLimbs + k], 0); }
+        s_off[kLimbs] = o;
+    }
+    __syncwarp();
+    for (int i = lane; i < ntot; i += 32) s_score[i] = cand[(size_t)i * 4 + 2];
+    for (int k = 0; k < kLimbs; k++) {
+        const int nck = s_off[k + 1] - s_off[k];
+        const double *conn = connections + ((size_t)frame * kLimbs + k) * max_peaks * 5;
+        for (int i = lane; i < nck * 3; i += 32) {
+            const int r = i / 3, c = i - 3 * r;
+            if (s_off[k] + r < kAsmConnRows) s_conn[(s_off[k] + r) * 3 + c] = conn[r * 5 + c];
+        }
+    }
+    __syncwarp();
     int nrows = 0;
     int st = 0;
     for (int k = 0; k < kLimbs; k++) {
@@ -849,7 +878,9 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
         const int ia = c_dec_a[k], ib = c_dec_b[k];
         const double *conn = connections + ((size_t)frame * kLimbs + k) * max_peaks * 5;
         for (int i = 0; i < nc; i++) {
-            const double pA = conn[i * 5 + 0], pB = conn[i * 5 + 1], sc = conn[i * 5 + 2];
+            const bool in_smem = s_off[k] + i < kAsmConnRows;
+            const double *row = in_smem ? s_conn + (s_off[k] + i) * 3 : conn + i * 5;
+            const double pA = row[0], pB = row[1], sc = row[2];
             int found = 0, j1 = -1, j2 = -1;
             for (int j0 = 0; j0 < nrows; j0 += 32) {
                 int j = j0 + lane;
@@ -869,7 +900,7 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
                 if (lane == 0 && s_sub[j1][ib] != pB) {
                     s_sub[j1][ib] = pB;
                     s_sub[j1][19] = __dadd_rn(s_sub[j1][19], 1.0);
-                    s_sub[j1][18] = __dadd_rn(s_sub[j1][18], __dadd_rn(cand[(size_t)(int)pB * 4 + 2], sc));
+                    s_sub[j1][18] = __dadd_rn(s_sub[j1][18], __dadd_rn(s_score[(int)pB], sc));
                 }
             } else if (found == 2) {
                 bool both = (lane < kParts) && (s_sub[j1][lane] >= 0.0) && (s_sub[j2][lane] >= 0.0);
@@ -889,7 +920,7 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
                 } else if (lane == 0) {
                     s_sub[j1][ib] = pB;
                     s_sub[j1][19] = __dadd_rn(s_sub[j1][19], 1.0);
-                    s_sub[j1][18] = __dadd_rn(s_sub[j1][18], __dadd_rn(cand[(size_t)(int)pB * 4 + 2], sc));
+                    s_sub[j1][18] = __dadd_rn(s_sub[j1][18], __dadd_rn(s_score[(int)pB], sc));
                 }
             } else if (found == 0 && k < 17) {
                 if (nrows < max_persons && nrows < kMaxSubsetCap) {
@@ -899,7 +930,7 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
                         s_sub[nrows][ia] = pA;
                         s_sub[nrows][ib] = pB;
                         s_sub[nrows][19] = 2.0;
-                        double s2 = __dadd_rn(__dadd_rn(0.0, cand[(size_t)(int)pA * 4 + 2]), cand[(size_t)(int)pB * 4 + 2]);
+                        double s2 = __dadd_rn(__dadd_rn(0.0, s_score[(int)pA]), s_score[(int)pB]);
                         s_sub[nrows][18] = __dadd_rn(s2, sc);
                     }
                     nrows++;
@@ -1094,6 +1125,8 @@ static int ensure_smooth_attr() {
                                        (int)smooth_smem_bytes(false)));
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_limbs, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kMaxCandCap * 12 + 2 * kMaxPeaksCap));
+    RMPE_CUDA_TRY(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(((kMaxSubsetCap + 1) * 20 + kAsmConnRows * 3 + kParts * kMaxPeaksCap) * 8)));
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_heat_screen<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)screen_smem_bytes(kScrMaxSrcRows, 64)));
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_heat_screen<kScrMaxKW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1193,7 +1226,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
             // ---- screen in float32 straight from the blobs, decide exactly per surviving pixel ----
             AxisJobs aj{};
             ScreenJobs sj{};
-            int m = 0, max_tiles = 0, max_len = 0, nr = 0, nc = 0, kwx_max = 0;
+            int m = 0, n_tab = 0, max_tiles = 0, max_len = 0, nr = 0, nc = 0, kwx_max = 0;
             for (int i = 0; i < n; i++) {
                 if (!plans[i].screen) continue;
                 const RmpeFrameDesc &f = fr[i];
@@ -1202,8 +1235,15 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                 int *loy = (int *)(Ky + (size_t)f.height * p.kwy);
                 float *Kx = (float *)(loy + f.height);
                 int *lox = (int *)(Kx + (size_t)f.width * p.kwx);
-                aj.j[2 * m] = AxisJob{f.height, f.grid_h[0], p.kwy, Ky, loy};
-                aj.j[2 * m + 1] = AxisJob{f.width, f.grid_w[0], p.kwx, Kx, lox};
+                // frames of one shape share their operators: build each (dst, src) table once per chunk
+                auto table = [&](int dst, int src, int kw, float *&K, int *&lo) {
+                    for (int q = 0; q < n_tab; q++)
+                        if (aj.j[q].dst == dst && aj.j[q].src == src && aj.j[q].kw == kw) { K = aj.j[q].K; lo = aj.j[q].lo; return; }
+                    aj.j[n_tab++] = AxisJob{dst, src, kw, K, lo};
+                    max_len = std::max(max_len, dst);
+                };
+                table(f.height, f.grid_h[0], p.kwy, Ky, loy);
+                table(f.width, f.grid_w[0], p.kwx, Kx, lox);
                 ScreenJob &J = sj.j[m];
                 J.heat = b->heat + f.heat_offset[0];
                 J.Ky = Ky; J.Kx = Kx; J.loy = loy; J.lox = lox;
@@ -1212,13 +1252,12 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                 J.tiles_x = (f.width + kScrTW - 1) / kScrTW;
                 J.tiles = J.tiles_x * ((f.height + kScrTH - 1) / kScrTH);
                 max_tiles = std::max(max_tiles, J.tiles);
-                max_len = std::max(max_len, std::max(f.height, f.width));
                 nr = std::max(nr, p.nrows_b); nc = std::max(nc, p.ncols_b); kwx_max = std::max(kwx_max, p.kwx);
                 m++;
             }
             const int cand_cap = (int)std::min<size_t>(per_list * 2, (size_t)n * kParts * MP * 2);
             if (f0 > 0) RMPE_CUDA_TRY(cudaMemsetAsync(cand_count, 0, 4, st));
-            { ProfScope ps("k_axis_tables", st); k_axis_tables<<<dim3((max_len + 127) / 128, 2 * m), 128, 0, st>>>(aj, tab_err); }
+            { ProfScope ps("k_axis_tables", st); k_axis_tables<<<dim3((max_len + 127) / 128, n_tab), 128, 0, st>>>(aj, tab_err); }
             {
                 ProfScope ps("k_heat_screen", st);
                 const size_t smem = screen_smem_bytes(nr, nc);
@@ -1288,8 +1327,9 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
         }
         {
             ProfScope ps("k_assemble", st);
-            k_assemble<<<B, 32, 0, st>>>(0, MP, b->max_persons, b->candidate, b->connections, b->n_conn, b->subset,
-                                         b->n_subset, b->status);
+            const size_t asm_smem = ((size_t)(kMaxSubsetCap + 1) * 20 + (size_t)kAsmConnRows * 3 + (size_t)kParts * MP) * 8;
+            k_assemble<<<B, 32, asm_smem, st>>>(0, MP, b->max_persons, b->candidate, b->connections, b->n_conn, b->n_peaks,
+                                                b->subset, b->n_subset, b->status);
         }
         count_launch(2);
     }
