@@ -351,12 +351,36 @@ constexpr float kScreenDelta = 2.0e-5f;
 
 struct AxisJob {
     int dst, src, kw;
-    float *K;    // [dst][kw]
-    int *lo;     // [dst]
+    int mid, stride;   // mid > 0: chain  src -> x stride -> crop to mid -> dst  (process_multi_scale)
+    float wscale;      // folded into the operator (1 / n_scales on the vertical axis)
+    float *K;          // [dst][kw]
+    int *lo;           // [dst]
 };
 struct AxisJobs {
     AxisJob j[2 * kChunkFrames];
 };
+
+// weights of destination index dp over the source axis, cv2.resize coefficient arithmetic
+template <typename F>
+__device__ inline void axis_taps(const AxisJob &J, int dp, F &&emit) {
+    if (J.mid == 0) {
+        float co[4];
+        const int s0 = resize_axis(dp, resize_scale(J.dst, J.src, 0.0), co);
+#pragma unroll
+        for (int k = 0; k < 4; k++) emit(clampi(s0 - 1 + k, 0, J.src - 1), (double)co[k]);
+    } else {
+        float c2[4];
+        const int s2 = resize_axis(dp, resize_scale(J.dst, J.mid, 0.0), c2);
+        const double scale1 = resize_scale(J.src * J.stride, J.src, (double)J.stride);
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) {
+            float c1[4];
+            const int s1 = resize_axis(clampi(s2 - 1 + k, 0, J.mid - 1), scale1, c1);
+#pragma unroll
+            for (int q = 0; q < 4; q++) emit(clampi(s1 - 1 + q, 0, J.src - 1), (double)c2[k] * (double)c1[q]);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(128) k_axis_tables(const __grid_constant__ AxisJobs jobs, int32_t *__restrict__ err) {
     const AxisJob &J = jobs.j[blockIdx.y];
@@ -364,29 +388,20 @@ __global__ void __launch_bounds__(128) k_axis_tables(const __grid_constant__ Axi
     __shared__ double s_acc[128][25];     // one accumulator row per thread (odd pitch: conflict-free)
     if (d >= J.dst) return;
     double *acc = s_acc[threadIdx.x];
-    const double scale = resize_scale(J.dst, J.src, 0.0);
     int lo = INT_MAX, hi = INT_MIN;
-    for (int t = -kSR; t <= kSR; t++) {
-        float co[4];
-        const int s = resize_axis(reflect_idx(d + t, J.dst), scale, co);
-        lo = min(lo, clampi(s - 1, 0, J.src - 1));
-        hi = max(hi, clampi(s + 2, 0, J.src - 1));
-    }
+    for (int t = -kSR; t <= kSR; t++)
+        axis_taps(J, reflect_idx(d + t, J.dst), [&](int idx, double) { lo = min(lo, idx); hi = max(hi, idx); });
     const int kw = min(J.kw, 24);
-    if (hi - lo + 1 > kw || J.kw > 24) { atomicOr(err, 1); hi = lo + kw - 1; }
+    if (hi - lo + 1 > kw || J.kw > 24) atomicOr(err, 1);
     for (int i = 0; i < kw; i++) acc[i] = 0.0;
     for (int t = -kSR; t <= kSR; t++) {
-        float co[4];
-        const int s = resize_axis(reflect_idx(d + t, J.dst), scale, co);
         const double g = c_gauss[12 - abs(t)];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int idx = clampi(s - 1 + k, 0, J.src - 1) - lo;
-            if (idx < kw) acc[idx] = fma(g, (double)co[k], acc[idx]);
-        }
+        axis_taps(J, reflect_idx(d + t, J.dst), [&](int idx, double wgt) {
+            if (idx - lo < kw) acc[idx - lo] = fma(g, wgt, acc[idx - lo]);
+        });
     }
     J.lo[d] = lo;
-    for (int i = 0; i < kw; i++) J.K[(size_t)d * J.kw + i] = (float)acc[i];
+    for (int i = 0; i < kw; i++) J.K[(size_t)d * J.kw + i] = (float)(acc[i] * (double)J.wscale);
 }
 
 struct ScreenJob {
@@ -553,20 +568,272 @@ __global__ void __launch_bounds__(kScrThreads) k_heat_screen(const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_heat_screen_ms: the same screening for process_multi_scale frames.  The scale-averaged,
+// smoothed map is  S = sum_s Ky_s * blob_s * Kx_s^T  (1/n_scales folded into Ky_s; each K_s is the
+// composite of the Gaussian, the resize to (H,W), the crop and the x8 resize), so a tile stages the
+// blob region of every scale, runs the horizontal pass per scale and accumulates the vertical
+// passes in registers.  Rounding budget: two cv2.resize per scale in the reference (28 float32
+// roundings), ~40 in S~; all partial sums are bounded by A = 1.375^4 mean_s max|blob_s|, so
+// |S~ - S| <= 70 * 2^-24 * A = 4.2e-6 A; kScreenDeltaMs = 1.2e-5 A.
+// ------------------------------------------------------------------------------------------
+constexpr int kMsKW = 12;            // non-zeros per row of Kx_s
+constexpr int kMsMaxRows = 24;       // staged blob rows per scale and tile
+constexpr int kMsJobsPerLaunch = 12;
+constexpr float kMsAmp = 3.5745f;    // 1.375^4
+constexpr float kScreenDeltaMs = 1.2e-5f;
+
+struct MsScale {
+    const float *heat;
+    const float *Ky, *Kx;
+    const int *loy, *lox;
+    int h, w, kwy, kwx;
+};
+struct MsJob {
+    MsScale sc[RMPE_MAX_SCALES];
+    int H, W, n_scales, frame, tiles_x, tiles;
+};
+struct MsJobs {
+    MsJob j[kMsJobsPerLaunch];
+};
+
+template <int NR>
+__device__ __forceinline__ void ms_vertical(const float *__restrict__ sT, const float *__restrict__ sKy, int col, int half,
+                                            int nrows, float acc[kScrRows / 2]) {
+    float tcol[NR];
+#pragma unroll
+    for (int i = 0; i < NR; i++) tcol[i] = (i < nrows) ? sT[i * kScrCols + col] : 0.f;
+#pragma unroll
+    for (int q = 0; q < kScrRows / 2; q++) {
+        const float4 *ky = reinterpret_cast<const float4 *>(sKy + (half * (kScrRows / 2) + q) * kMsMaxRows);
+        float a = acc[q];
+#pragma unroll
+        for (int i4 = 0; i4 < NR / 4; i4++) {
+            const float4 k4 = ky[i4];
+            a = fmaf(k4.x, tcol[4 * i4 + 0], a);
+            a = fmaf(k4.y, tcol[4 * i4 + 1], a);
+            a = fmaf(k4.z, tcol[4 * i4 + 2], a);
+            a = fmaf(k4.w, tcol[4 * i4 + 3], a);
+        }
+        acc[q] = a;
+    }
+}
+
+__global__ void __launch_bounds__(kScrThreads) k_heat_screen_ms(const __grid_constant__ MsJobs jobs, float thre1,
+                                                                 int cand_cap, int32_t *__restrict__ cand_key,
+                                                                 int32_t *__restrict__ cand_fp,
+                                                                 int32_t *__restrict__ cand_count,
+                                                                 const int32_t *__restrict__ tab_err,
+                                                                 int32_t *__restrict__ status) {
+    const MsJob &J = jobs.j[blockIdx.y];
+    if ((int)blockIdx.x >= J.tiles) return;
+    if (*tab_err) {
+        if (threadIdx.x == 0) atomicOr(status + J.frame, RMPE_ST_PEAK_OVERFLOW);
+        return;
+    }
+    const int H = J.H, W = J.W, NS = J.n_scales;
+    const int ty = blockIdx.x / J.tiles_x, tx = blockIdx.x - ty * J.tiles_x;
+    const int y0 = ty * kScrTH, x0 = tx * kScrTW;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int col = tid & (kScrCols - 1), half = tid >> 7;
+
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    __shared__ int s_rng[RMPE_MAX_SCALES][4];
+    __shared__ int s_bmax[RMPE_MAX_SCALES][kHeatC];
+    __shared__ int s_loy[RMPE_MAX_SCALES][kScrRows];
+    __shared__ int s_boff[RMPE_MAX_SCALES + 1], s_toff[RMPE_MAX_SCALES + 1];
+
+    if (tid < 4 * RMPE_MAX_SCALES) s_rng[tid >> 2][tid & 3] = (tid & 1) ? INT_MIN : INT_MAX;
+    __syncthreads();
+    const int xg = clampi(x0 - 1 + col, 0, W - 1);
+    int mylox[RMPE_MAX_SCALES];
+#pragma unroll
+    for (int sc = 0; sc < RMPE_MAX_SCALES; sc++) {
+        mylox[sc] = 0;
+        if (sc < NS) {
+            const MsScale &S = J.sc[sc];
+            if (tid < kScrRows) {
+                const int lo = S.loy[clampi(y0 - 1 + tid, 0, H - 1)];
+                s_loy[sc][tid] = lo;
+                atomicMin(&s_rng[sc][0], lo);
+                atomicMax(&s_rng[sc][1], min(lo + S.kwy - 1, S.h - 1));
+            }
+            mylox[sc] = S.lox[xg];
+            if (half == 0) {
+                atomicMin(&s_rng[sc][2], mylox[sc]);
+                atomicMax(&s_rng[sc][3], min(mylox[sc] + S.kwx - 1, S.w - 1));
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int bo = 0, to = 0;
+        for (int sc = 0; sc < NS; sc++) {
+            const int nr = s_rng[sc][1] - s_rng[sc][0] + 1, nc = s_rng[sc][3] - s_rng[sc][2] + 1;
+            s_boff[sc] = bo; bo += (nr * nc * kHeatC + 3) & ~3;
+            s_toff[sc] = to; to += nr * kScrCols;
+        }
+        s_boff[NS] = bo; s_toff[NS] = to;
+    }
+    __syncthreads();
+    float *sBall = reinterpret_cast<float *>(sm_raw);
+    float *sTall = sBall + s_boff[NS];
+    float *sS = sTall + s_toff[NS];
+    float *sKyAll = sS + kScrRows * kScrCols;                         // [NS][34][kMsMaxRows]
+    float *sKxAll = sKyAll + NS * kScrRows * kMsMaxRows;              // [NS][128][kMsKW]
+    bool bad = false;
+    for (int sc = 0; sc < NS; sc++) bad = bad || (s_rng[sc][1] - s_rng[sc][0] + 1 > kMsMaxRows);
+    if (bad) {   // host sized the launch for this never to happen
+        if (tid == 0) atomicOr(status + J.frame, RMPE_ST_PEAK_OVERFLOW);
+        return;
+    }
+    for (int sc = 0; sc < NS; sc++) {
+        const MsScale &S = J.sc[sc];
+        const int r0 = s_rng[sc][0], c0 = s_rng[sc][2];
+        const int nrows = s_rng[sc][1] - r0 + 1, ncols = s_rng[sc][3] - c0 + 1;
+        float *sB = sBall + s_boff[sc];
+        const int rowlen = ncols * kHeatC;
+        for (int i = tid; i < nrows * rowlen; i += kScrThreads) {
+            const int r = i / rowlen, e = i - r * rowlen;
+            sB[i] = S.heat[((size_t)(r0 + r) * S.w + c0) * kHeatC + e];
+        }
+        float *sKy = sKyAll + sc * kScrRows * kMsMaxRows;
+        for (int i = tid; i < kScrRows * kMsMaxRows; i += kScrThreads) {
+            const int r = i / kMsMaxRows, q = i - r * kMsMaxRows;
+            const int y = clampi(y0 - 1 + r, 0, H - 1);
+            const int k = q - (s_loy[sc][r] - r0);
+            sKy[i] = (k >= 0 && k < S.kwy) ? S.Ky[(size_t)y * S.kwy + k] : 0.f;
+        }
+        if (half == 0) {
+            float *kx = sKxAll + ((size_t)sc * kScrCols + col) * kMsKW;
+            for (int j = 0; j < kMsKW; j++) kx[j] = (j < S.kwx) ? S.Kx[(size_t)xg * S.kwx + j] : 0.f;
+        }
+    }
+    __syncthreads();
+    for (int i = tid >> 5; i < NS * kParts; i += kScrThreads / 32) {
+        const int sc = i / kParts, part = i - sc * kParts;
+        const int n = (s_rng[sc][1] - s_rng[sc][0] + 1) * (s_rng[sc][3] - s_rng[sc][2] + 1);
+        const float *sB = sBall + s_boff[sc];
+        float m = 0.f;
+        for (int e = lane; e < n; e += 32) m = fmaxf(m, fabsf(sB[e * kHeatC + part]));
+        const int mi = __reduce_max_sync(0xffffffffu, __float_as_int(m));
+        if (lane == 0) s_bmax[sc][part] = mi;
+    }
+    __syncthreads();
+
+    for (int part = 0; part < kParts; part++) {
+        float bsum = 0.f;
+        for (int sc = 0; sc < NS; sc++) bsum += __int_as_float(s_bmax[sc][part]);
+        const float A = kMsAmp * bsum / (float)NS * 1.0001f;     // bound on |S| and on every partial sum
+        const float delta = kScreenDeltaMs * A;
+        if (A + delta <= thre1) continue;                        // block-uniform: no peak of this part in the tile
+        // ---- horizontal passes ----
+        for (int sc = 0; sc < NS; sc++) {
+            const int c0 = s_rng[sc][2];
+            const int nrows = s_rng[sc][1] - s_rng[sc][0] + 1, ncols = s_rng[sc][3] - c0 + 1;
+            const float *sB = sBall + s_boff[sc];
+            float *sT = sTall + s_toff[sc];
+            const float4 *kx4 = reinterpret_cast<const float4 *>(sKxAll + ((size_t)sc * kScrCols + col) * kMsKW);
+            float kxw[kMsKW];
+#pragma unroll
+            for (int j4 = 0; j4 < kMsKW / 4; j4++) {
+                const float4 v = kx4[j4];
+                kxw[4 * j4] = v.x; kxw[4 * j4 + 1] = v.y; kxw[4 * j4 + 2] = v.z; kxw[4 * j4 + 3] = v.w;
+            }
+            const int off = mylox[sc] - c0;
+            for (int i = half; i < nrows; i += 2) {
+                const float *b = sB + ((size_t)i * ncols + off) * kHeatC + part;
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < kMsKW; j++)
+                    if (off + j < ncols) acc = fmaf(kxw[j], b[j * kHeatC], acc);
+                sT[i * kScrCols + col] = acc;
+            }
+        }
+        __syncthreads();
+        // ---- vertical passes, accumulated over the scales ----
+        float acc[kScrRows / 2];
+#pragma unroll
+        for (int q = 0; q < kScrRows / 2; q++) acc[q] = 0.f;
+        for (int sc = 0; sc < NS; sc++) {
+            const int nrows = s_rng[sc][1] - s_rng[sc][0] + 1;
+            const float *sT = sTall + s_toff[sc];
+            const float *sKy = sKyAll + sc * kScrRows * kMsMaxRows;
+            if (nrows <= 8) ms_vertical<8>(sT, sKy, col, half, nrows, acc);
+            else if (nrows <= 16) ms_vertical<16>(sT, sKy, col, half, nrows, acc);
+            else ms_vertical<kMsMaxRows>(sT, sKy, col, half, nrows, acc);
+        }
+#pragma unroll
+        for (int q = 0; q < kScrRows / 2; q++) sS[(half * (kScrRows / 2) + q) * kScrCols + col] = acc[q];
+        __syncthreads();
+        // ---- conservative 4-neighbour test on the interior ----
+        const float lim = thre1 - delta, d2 = 2.f * delta;
+        for (int q = 0; q < kScrTH / 2; q++) {
+            const int r = 1 + half * (kScrTH / 2) + q;
+            const int y = y0 + r - 1, x = x0 + col - 1;
+            bool cand = false;
+            if (col >= 1 && col <= kScrTW && y < H && x < W) {
+                const float sv = sS[r * kScrCols + col];
+                if (sv > lim) {
+                    const float up = (y > 0) ? sS[(r - 1) * kScrCols + col] : 0.f;
+                    const float dn = (y < H - 1) ? sS[(r + 1) * kScrCols + col] : 0.f;
+                    const float lf = (x > 0) ? sS[r * kScrCols + col - 1] : 0.f;
+                    const float rt = (x < W - 1) ? sS[r * kScrCols + col + 1] : 0.f;
+                    cand = (sv >= up - d2) && (sv >= dn - d2) && (sv >= lf - d2) && (sv >= rt - d2);
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, cand);
+            if (bal) {
+                const int leader = __ffs(bal) - 1;
+                int slot0 = 0;
+                if (lane == leader) slot0 = atomicAdd(cand_count, __popc(bal));
+                slot0 = __shfl_sync(0xffffffffu, slot0, leader);
+                if (cand) {
+                    const int slot = slot0 + __popc(bal & ((1u << lane) - 1));
+                    if (slot < cand_cap) {
+                        cand_key[slot] = y * W + x;
+                        cand_fp[slot] = J.frame * kParts + part;
+                    } else {
+                        atomicOr(status + J.frame, RMPE_ST_PEAK_OVERFLOW);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // one CTA per screened pixel: exact S at the pixel and its four neighbours
 constexpr int kVerThreads = 128;
 constexpr int kVerN = 2 * kSR + 3;   // 27: the pixel +-1, +-12
 
+// heat value of the (scale-averaged) up-sampled map at an integer point, the reference's arithmetic
+__device__ inline double heat_point(const RmpeFrameDesc &f, const float *__restrict__ heat, int stride, int c, int y,
+                                    int x) {
+    if (f.n_scales == 1)
+        return (double)resize_point_blob(heat + f.heat_offset[0], f.grid_h[0], f.grid_w[0], kHeatC, c, y, x, f.height,
+                                         f.width, 0.0);
+    double acc = 0.0;
+    for (int s = 0; s < f.n_scales; s++) {
+        int Hc = f.grid_h[s] * stride - f.pad_down[s], Wc = f.grid_w[s] * stride - f.pad_right[s];
+        float v = resize_chain_point(heat + f.heat_offset[s], f.grid_h[s], f.grid_w[s], kHeatC, c, y, x, f.height,
+                                     f.width, Hc, Wc, stride);
+        acc = __dadd_rn(acc, (double)__fdiv_rn(v, (float)f.n_scales));
+    }
+    return acc;
+}
+
 __global__ void __launch_bounds__(kVerThreads) k_peak_verify(const RmpeFrameDesc *__restrict__ frames,
-                                                            const float *__restrict__ heat, float thre1, int cand_cap,
-                                                            const int32_t *__restrict__ cand_key,
+                                                            const float *__restrict__ heat, int stride, double thre1,
+                                                            int cand_cap, const int32_t *__restrict__ cand_key,
                                                             const int32_t *__restrict__ cand_fp,
                                                             const int32_t *__restrict__ cand_count, int max_peaks,
                                                             int32_t *__restrict__ raw_key, double *__restrict__ raw_score,
                                                             int32_t *__restrict__ raw_count, int32_t *__restrict__ status) {
-    __shared__ float sU[kVerN][kVerN + 1];
-    __shared__ float sA[3][kVerN + 1];
-    __shared__ float sS5[5];
+    // doubles hold both map dtypes: float32 maps (single scale) are rounded to float32 where the
+    // reference stores float32, and comparing float32 values as doubles is the float32 comparison
+    __shared__ double sU[kVerN][kVerN + 1];
+    __shared__ double sA[3][kVerN + 1];
+    __shared__ double sS5[5];
     const int total = min(*cand_count, cand_cap);
     const int tid = threadIdx.x;
     for (int ci = blockIdx.x; ci < total; ci += gridDim.x) {
@@ -575,50 +842,50 @@ __global__ void __launch_bounds__(kVerThreads) k_peak_verify(const RmpeFrameDesc
         const RmpeFrameDesc f = frames[frame];
         const int H = f.height, W = f.width;
         const int y = key / W, x = key - y * W;
-        const float *blob = heat + f.heat_offset[0];
-        // U on the 27x27 reflected neighbourhood, cv2.resize arithmetic
+        const bool f32map = f.n_scales == 1;
+        // U on the 27x27 reflected neighbourhood
         for (int i = tid; i < kVerN * kVerN; i += kVerThreads) {
             const int a = i / kVerN, b = i - a * kVerN;
-            sU[a][b] = resize_point_blob(blob, f.grid_h[0], f.grid_w[0], kHeatC, part, reflect_idx(y - kSR - 1 + a, H),
-                                         reflect_idx(x - kSR - 1 + b, W), H, W, 0.0);
+            sU[a][b] = heat_point(f, heat, stride, part, reflect_idx(y - kSR - 1 + a, H), reflect_idx(x - kSR - 1 + b, W));
         }
         __syncthreads();
-        // axis 0 on rows y-1, y, y+1 (scipy order, f64 accumulate, float32 store)
+        // axis 0 on rows y-1, y, y+1 (scipy order, f64 accumulate, store in the map dtype)
         for (int i = tid; i < 3 * kVerN; i += kVerThreads) {
             const int rr = i / kVerN, b = i - rr * kVerN;
             const int a = kSR + rr;   // local row of y-1+rr
-            double tmp = __dmul_rn((double)sU[a][b], c_gauss[12]);
+            double tmp = __dmul_rn(sU[a][b], c_gauss[12]);
 #pragma unroll
             for (int j = -kSR; j < 0; j++) {
-                const double pair = __dadd_rn((double)sU[a + j][b], (double)sU[a - j][b]);
+                const double pair = __dadd_rn(sU[a + j][b], sU[a - j][b]);
                 tmp = __dadd_rn(tmp, __dmul_rn(pair, c_gauss[12 + j]));
             }
-            sA[rr][b] = (float)tmp;
+            sA[rr][b] = f32map ? (double)(float)tmp : tmp;
         }
         __syncthreads();
         // axis 1 at (y,x), (y-1,x), (y+1,x), (y,x-1), (y,x+1)
         if (tid < 5) {
             const int rr = (tid == 1) ? 0 : (tid == 2) ? 2 : 1;
             const int b = kSR + 1 + ((tid == 3) ? -1 : (tid == 4) ? 1 : 0);
-            double tmp = __dmul_rn((double)sA[rr][b], c_gauss[12]);
+            double tmp = __dmul_rn(sA[rr][b], c_gauss[12]);
 #pragma unroll
             for (int j = -kSR; j < 0; j++) {
-                const double pair = __dadd_rn((double)sA[rr][b + j], (double)sA[rr][b - j]);
+                const double pair = __dadd_rn(sA[rr][b + j], sA[rr][b - j]);
                 tmp = __dadd_rn(tmp, __dmul_rn(pair, c_gauss[12 + j]));
             }
-            sS5[tid] = (float)tmp;
+            sS5[tid] = f32map ? (double)(float)tmp : tmp;
         }
         __syncthreads();
         if (tid == 0) {
-            const float sv = sS5[0];
-            const float up = (y > 0) ? sS5[1] : 0.f, dn = (y < H - 1) ? sS5[2] : 0.f;
-            const float lf = (x > 0) ? sS5[3] : 0.f, rt = (x < W - 1) ? sS5[4] : 0.f;
-            if ((sv >= up) && (sv >= dn) && (sv >= lf) && (sv >= rt) && (sv > thre1)) {
+            const double thr = f32map ? (double)(float)thre1 : thre1;
+            const double sv = sS5[0];
+            const double up = (y > 0) ? sS5[1] : 0.0, dn = (y < H - 1) ? sS5[2] : 0.0;
+            const double lf = (x > 0) ? sS5[3] : 0.0, rt = (x < W - 1) ? sS5[4] : 0.0;
+            if ((sv >= up) && (sv >= dn) && (sv >= lf) && (sv >= rt) && (sv > thr)) {
                 const int slot = atomicAdd(raw_count + fp, 1);
                 if (slot < max_peaks) {
                     const size_t o = (size_t)fp * max_peaks + slot;
                     raw_key[o] = key;
-                    raw_score[o] = (double)sU[kSR + 1][kSR + 1];
+                    raw_score[o] = sU[kSR + 1][kSR + 1];
                 } else {
                     atomicOr(status + frame, RMPE_ST_PEAK_OVERFLOW);
                 }
@@ -961,9 +1228,11 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
 // host side
 // ==========================================================================================
 struct FramePlan {
-    bool screen;         // single-scale frame decoded through k_heat_screen / k_peak_verify
-    int kwy, kwx;        // non-zeros per row of the composite operators
-    int nrows_b, ncols_b;  // bounds on the staged blob region of a screening tile
+    bool screen;         // frame decoded through k_heat_screen[_ms] / k_peak_verify
+    int kwy[RMPE_MAX_SCALES], kwx[RMPE_MAX_SCALES];          // non-zeros per row of the composite operators
+    int nrows_b[RMPE_MAX_SCALES], ncols_b[RMPE_MAX_SCALES];  // bounds on the staged blob region of a screening tile
+    size_t tab_elems;    // 4-byte elements of the frame's operator tables
+    size_t smem;         // dynamic shared memory of its screening kernel
     bool multi;
     size_t u_elems;      // 18*H*W (T)
     size_t p1_elems;     // floats
@@ -976,23 +1245,52 @@ static size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 static int ceil_div_d(double a) { return (int)ceil(a - 1e-9); }
 
+static size_t screen_smem_bytes(int nrows_b, int ncols_b) {
+    return ((size_t)((nrows_b * ncols_b * kHeatC + 3) & ~3) + (size_t)nrows_b * kScrCols + (size_t)kScrRows * kScrCols +
+            (size_t)kScrRows * kScrMaxSrcRows) * 4;
+}
+
 static FramePlan plan_frame(const RmpeFrameDesc &f, int stride, bool allow_screen = true) {
     FramePlan p{};
     p.multi = f.n_scales > 1;
     p.u_elems = (size_t)kParts * f.height * f.width;
-    if (!p.multi) {
-        // composite operator supports: a 25-tap window of destination pixels spans 24*src/dst source pixels
-        const int h = f.grid_h[0], w = f.grid_w[0];
-        p.kwy = ceil_div_d(24.0 * h / f.height) + 6;
-        p.kwx = ceil_div_d(24.0 * w / f.width) + 6;
-        p.nrows_b = std::min(h, ceil_div_d((double)kScrRows * h / f.height) + p.kwy + 1);
-        p.ncols_b = std::min(w, ceil_div_d((double)kScrCols * w / f.width) + p.kwx + 1);
-        static const bool off = getenv("RMPE_DECODE_EXACT_MAPS") != nullptr;   // debugging: force the full-map path
-        p.screen = allow_screen && !off && p.kwy <= 24 && p.kwx <= kScrMaxKW && p.nrows_b <= kScrMaxSrcRows && p.ncols_b <= 64;
+    static const bool off = getenv("RMPE_DECODE_EXACT_MAPS") != nullptr;   // debugging: force the full-map path
+    // composite operator supports: a 25-tap window of destination pixels spans 24*mid/dst pixels of the
+    // (cropped) x-stride map, i.e. (that + 5)/stride blob cells, plus the taps of one more bicubic
+    bool ok = allow_screen && !off;
+    size_t smem_ms = (size_t)kScrRows * kScrCols * 4;
+    for (int s = 0; s < f.n_scales && ok; s++) {
+        const int h = f.grid_h[s], w = f.grid_w[s];
+        // Support of one operator row.  25 destination taps span 24*scale source pixels, floor() of positions
+        // over a span L takes values at most ceil(L) apart, and a bicubic adds taps -1..+2:
+        //   single resize:  ceil(24 src/dst) + 4;   chain: D = ceil(24 mid/dst) + 3 pixels of the x-stride map,
+        //   then ceil(D/stride) + 4 blob cells.  (+1 spare; k_axis_tables flags any row that does not fit.)
+        if (!p.multi) {
+            p.kwy[s] = ceil_div_d(24.0 * h / f.height) + 5;
+            p.kwx[s] = ceil_div_d(24.0 * w / f.width) + 5;
+        } else {
+            const double Hc = (double)h * stride - f.pad_down[s], Wc = (double)w * stride - f.pad_right[s];
+            p.kwy[s] = ceil_div_d((ceil_div_d(24.0 * Hc / f.height) + 3.0) / stride) + 5;
+            p.kwx[s] = ceil_div_d((ceil_div_d(24.0 * Wc / f.width) + 3.0) / stride) + 5;
+        }
+        // a tile's 34 rows / 128 columns move the first source index by at most ceil(33 h/H) + 1
+        p.nrows_b[s] = std::min(h, ceil_div_d((double)(kScrRows - 1) * h / f.height) + 1 + p.kwy[s]);
+        p.ncols_b[s] = std::min(w, ceil_div_d((double)(kScrCols - 1) * w / f.width) + 1 + p.kwx[s]);
+        p.tab_elems += (size_t)f.height * (p.kwy[s] + 1) + (size_t)f.width * (p.kwx[s] + 1);
+        if (!p.multi) {
+            ok = p.kwy[s] <= 24 && p.kwx[s] <= kScrMaxKW && p.nrows_b[s] <= kScrMaxSrcRows && p.ncols_b[s] <= 64;
+            p.smem = screen_smem_bytes(p.nrows_b[s], p.ncols_b[s]);
+        } else {
+            ok = p.kwy[s] <= 24 && p.kwx[s] <= kMsKW && p.nrows_b[s] <= kMsMaxRows;
+            smem_ms += ((size_t)((p.nrows_b[s] * p.ncols_b[s] * kHeatC + 3) & ~3) + (size_t)p.nrows_b[s] * kScrCols +
+                        (size_t)kScrRows * kMsMaxRows + (size_t)kScrCols * kMsKW) * 4;
+        }
     }
+    if (p.multi) { p.smem = smem_ms; ok = ok && smem_ms <= 224 * 1024; }
+    p.screen = ok;
     if (p.screen) {
         p.u_elems = 0;
-        p.bytes = al256(((size_t)f.height * (p.kwy + 1) + (size_t)f.width * (p.kwx + 1)) * 4);
+        p.bytes = al256(p.tab_elems * 4);
         return p;
     }
     if (!p.multi) {
@@ -1008,11 +1306,6 @@ static FramePlan plan_frame(const RmpeFrameDesc &f, int stride, bool allow_scree
     }
     p.bytes = al256(p.u_elems * (p.multi ? 8 : 4)) + al256(p.p1_elems * 4) + al256(p.i1_elems * 4) + al256(p.p2_elems * 4);
     return p;
-}
-
-static size_t screen_smem_bytes(int nrows_b, int ncols_b) {
-    return ((size_t)((nrows_b * ncols_b * kHeatC + 3) & ~3) + (size_t)nrows_b * kScrCols + (size_t)kScrRows * kScrCols +
-            (size_t)kScrRows * kScrMaxSrcRows) * 4;
 }
 
 static size_t fixed_ws_bytes(int batch, int max_peaks, int max_cand) {
@@ -1127,6 +1420,7 @@ static int ensure_smooth_attr() {
                                        kMaxCandCap * 12 + 2 * kMaxPeaksCap));
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(((kMaxSubsetCap + 1) * 20 + kAsmConnRows * 3 + kParts * kMaxPeaksCap) * 8)));
+    RMPE_CUDA_TRY(cudaFuncSetAttribute(k_heat_screen_ms, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_heat_screen<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)screen_smem_bytes(kScrMaxSrcRows, 64)));
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_heat_screen<kScrMaxKW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1226,39 +1520,73 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
             // ---- screen in float32 straight from the blobs, decide exactly per surviving pixel ----
             AxisJobs aj{};
             ScreenJobs sj{};
+            std::vector<MsJob> msj;
             int m = 0, n_tab = 0, max_tiles = 0, max_len = 0, nr = 0, nc = 0, kwx_max = 0;
+            size_t ms_smem = 0;
+            const int cand_cap = (int)std::min<size_t>(per_list * 2, (size_t)n * kParts * MP * 2);
+            if (f0 > 0) RMPE_CUDA_TRY(cudaMemsetAsync(cand_count, 0, 4, st));
+            auto flush_tables = [&]() {
+                if (!n_tab) return;
+                ProfScope ps("k_axis_tables", st);
+                k_axis_tables<<<dim3((max_len + 127) / 128, n_tab), 128, 0, st>>>(aj, tab_err);
+                count_launch();
+                n_tab = 0; max_len = 0;
+            };
             for (int i = 0; i < n; i++) {
                 if (!plans[i].screen) continue;
                 const RmpeFrameDesc &f = fr[i];
                 const FramePlan &p = plans[i];
-                float *Ky = (float *)u_ptr[i];
-                int *loy = (int *)(Ky + (size_t)f.height * p.kwy);
-                float *Kx = (float *)(loy + f.height);
-                int *lox = (int *)(Kx + (size_t)f.width * p.kwx);
-                // frames of one shape share their operators: build each (dst, src) table once per chunk
-                auto table = [&](int dst, int src, int kw, float *&K, int *&lo) {
-                    for (int q = 0; q < n_tab; q++)
-                        if (aj.j[q].dst == dst && aj.j[q].src == src && aj.j[q].kw == kw) { K = aj.j[q].K; lo = aj.j[q].lo; return; }
-                    aj.j[n_tab++] = AxisJob{dst, src, kw, K, lo};
-                    max_len = std::max(max_len, dst);
+                if (n_tab + 2 * f.n_scales > 2 * kChunkFrames) flush_tables();
+                // frames of one shape share their operators: build each table once per launch of k_axis_tables
+                auto table = [&](const AxisJob &want, float *&K, int *&lo) {
+                    for (int q = 0; q < n_tab; q++) {
+                        const AxisJob &o = aj.j[q];
+                        if (o.dst == want.dst && o.src == want.src && o.kw == want.kw && o.mid == want.mid &&
+                            o.stride == want.stride && o.wscale == want.wscale) { K = o.K; lo = o.lo; return; }
+                    }
+                    aj.j[n_tab] = want; aj.j[n_tab].K = K; aj.j[n_tab].lo = lo;
+                    n_tab++;
+                    max_len = std::max(max_len, want.dst);
                 };
-                table(f.height, f.grid_h[0], p.kwy, Ky, loy);
-                table(f.width, f.grid_w[0], p.kwx, Kx, lox);
-                ScreenJob &J = sj.j[m];
-                J.heat = b->heat + f.heat_offset[0];
-                J.Ky = Ky; J.Kx = Kx; J.loy = loy; J.lox = lox;
-                J.H = f.height; J.W = f.width; J.h = f.grid_h[0]; J.w = f.grid_w[0]; J.kwy = p.kwy; J.kwx = p.kwx;
-                J.frame = f0 + i;
-                J.tiles_x = (f.width + kScrTW - 1) / kScrTW;
-                J.tiles = J.tiles_x * ((f.height + kScrTH - 1) / kScrTH);
-                max_tiles = std::max(max_tiles, J.tiles);
-                nr = std::max(nr, p.nrows_b); nc = std::max(nc, p.ncols_b); kwx_max = std::max(kwx_max, p.kwx);
-                m++;
+                uint8_t *tp = u_ptr[i];
+                MsJob mj{};
+                for (int sI = 0; sI < f.n_scales; sI++) {
+                    float *Ky = (float *)tp; tp += (size_t)f.height * p.kwy[sI] * 4;
+                    int *loy = (int *)tp; tp += (size_t)f.height * 4;
+                    float *Kx = (float *)tp; tp += (size_t)f.width * p.kwx[sI] * 4;
+                    int *lox = (int *)tp; tp += (size_t)f.width * 4;
+                    const int h = f.grid_h[sI], w = f.grid_w[sI];
+                    if (!p.multi) {
+                        table(AxisJob{f.height, h, p.kwy[sI], 0, 1, 1.0f, nullptr, nullptr}, Ky, loy);
+                        table(AxisJob{f.width, w, p.kwx[sI], 0, 1, 1.0f, nullptr, nullptr}, Kx, lox);
+                        ScreenJob &J = sj.j[m];
+                        J.heat = b->heat + f.heat_offset[0];
+                        J.Ky = Ky; J.Kx = Kx; J.loy = loy; J.lox = lox;
+                        J.H = f.height; J.W = f.width; J.h = h; J.w = w; J.kwy = p.kwy[0]; J.kwx = p.kwx[0];
+                        J.frame = f0 + i;
+                        J.tiles_x = (f.width + kScrTW - 1) / kScrTW;
+                        J.tiles = J.tiles_x * ((f.height + kScrTH - 1) / kScrTH);
+                        max_tiles = std::max(max_tiles, J.tiles);
+                        nr = std::max(nr, p.nrows_b[0]); nc = std::max(nc, p.ncols_b[0]); kwx_max = std::max(kwx_max, p.kwx[0]);
+                        m++;
+                    } else {
+                        table(AxisJob{f.height, h, p.kwy[sI], h * b->stride - f.pad_down[sI], b->stride,
+                                      1.0f / (float)f.n_scales, nullptr, nullptr}, Ky, loy);
+                        table(AxisJob{f.width, w, p.kwx[sI], w * b->stride - f.pad_right[sI], b->stride, 1.0f, nullptr, nullptr},
+                              Kx, lox);
+                        mj.sc[sI] = MsScale{b->heat + f.heat_offset[sI], Ky, Kx, loy, lox, h, w, p.kwy[sI], p.kwx[sI]};
+                    }
+                }
+                if (p.multi) {
+                    mj.H = f.height; mj.W = f.width; mj.n_scales = f.n_scales; mj.frame = f0 + i;
+                    mj.tiles_x = (f.width + kScrTW - 1) / kScrTW;
+                    mj.tiles = mj.tiles_x * ((f.height + kScrTH - 1) / kScrTH);
+                    ms_smem = std::max(ms_smem, p.smem);
+                    msj.push_back(mj);
+                }
             }
-            const int cand_cap = (int)std::min<size_t>(per_list * 2, (size_t)n * kParts * MP * 2);
-            if (f0 > 0) RMPE_CUDA_TRY(cudaMemsetAsync(cand_count, 0, 4, st));
-            { ProfScope ps("k_axis_tables", st); k_axis_tables<<<dim3((max_len + 127) / 128, n_tab), 128, 0, st>>>(aj, tab_err); }
-            {
+            flush_tables();
+            if (m) {
                 ProfScope ps("k_heat_screen", st);
                 const size_t smem = screen_smem_bytes(nr, nc);
                 if (kwx_max <= 10)
@@ -1267,14 +1595,24 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                 else
                     k_heat_screen<kScrMaxKW><<<dim3(max_tiles, m), kScrThreads, smem, st>>>(
                         sj, (float)b->thre1, cand_cap, cand_key, cand_fp, cand_count, tab_err, b->status);
+                count_launch();
+            }
+            for (size_t q0 = 0; q0 < msj.size(); q0 += kMsJobsPerLaunch) {
+                MsJobs mjs{};
+                int mm = 0, mt = 0;
+                for (size_t q = q0; q < msj.size() && mm < kMsJobsPerLaunch; q++) { mjs.j[mm++] = msj[q]; mt = std::max(mt, msj[q].tiles); }
+                ProfScope ps("k_heat_screen_ms", st);
+                k_heat_screen_ms<<<dim3(mt, mm), kScrThreads, ms_smem, st>>>(mjs, (float)b->thre1, cand_cap, cand_key, cand_fp,
+                                                                          cand_count, tab_err, b->status);
+                count_launch();
             }
             {
                 ProfScope ps("k_peak_verify", st);
                 const int grid = std::min(cand_cap, 8 * tables().sm_count);
-                k_peak_verify<<<grid, kVerThreads, 0, st>>>(b->frames, b->heat, (float)b->thre1, cand_cap, cand_key, cand_fp,
+                k_peak_verify<<<grid, kVerThreads, 0, st>>>(b->frames, b->heat, b->stride, b->thre1, cand_cap, cand_key, cand_fp,
                                                            cand_count, MP, raw_key, raw_score, raw_count, b->status);
+                count_launch();
             }
-            count_launch(3);
         }
         if (any_single || any_multi) {
             rc = launch_heat_up(fr, n, b->heat, b->stride, u_ptr, p1_ptr, i1_ptr, p2_ptr, plans, st);

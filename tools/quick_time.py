@@ -80,6 +80,14 @@ def main():
     dp = rmpe_b200.batch.DecodeDevicePlan(frames)
     ms = ev_time(dp.run, iters=3, warm=1)
     print("decode multi-scale 480x640 x4: %.3f ms -> %.1f frames/s" % (ms, 4 / ms * 1e3), flush=True)
+    L.profile_enable(True)
+    for _ in range(3):
+        dp.run()
+    torch.cuda.synchronize()
+    L.profile_enable(False, reset=False)
+    for k, (tms, n) in L.profile_read().items():
+        print("   %-20s %.3f ms/launch x %d" % (k, tms / max(n, 1), n // 3))
+    L.profile_enable(False, reset=True)
 
 
 if __name__ == "__main__":
