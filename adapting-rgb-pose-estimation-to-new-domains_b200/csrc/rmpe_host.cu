@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <string>
@@ -121,6 +122,7 @@ struct State {
     void *tab_mem = nullptr;
     Arena arena;
     cudaStream_t stream = nullptr;
+    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};   // chunk pipeline of the host-buffer GT wrapper
     std::mutex mu;
 };
 static State g;
@@ -213,6 +215,7 @@ extern "C" int rmpe_init(int device) {
     g.tab.bicubic_dp4a = (const uint32_t *)((uint8_t *)g.tab_mem + b16);
     g.tab.sm_count = prop.multiProcessorCount;
     RMPE_CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; i++) RMPE_CUDA_TRY(cudaStreamCreateWithFlags(&g.pipe[i], cudaStreamNonBlocking));
     g.device = device;
     g.init = true;
     return RMPE_OK;
@@ -226,6 +229,7 @@ extern "C" void rmpe_shutdown(void) {
     if (g.tab_mem) cudaFree(g.tab_mem);
     if (g.arena.dev) cudaFree(g.arena.dev);
     if (g.stream) cudaStreamDestroy(g.stream);
+    for (int i = 0; i < 3; i++) { if (g.pipe[i]) cudaStreamDestroy(g.pipe[i]); g.pipe[i] = nullptr; }
     g.init = false; g.device = -1; g.tab = DeviceTables{}; g.tab_mem = nullptr;
     g.arena = Arena{}; g.stream = nullptr;
 }
@@ -404,9 +408,6 @@ extern "C" int rmpe_gt_batch_host(const RmpeGtBatchHost *h) {
     g.arena.reset();
     cudaStream_t st = g.stream;
 
-    RmpeGtBatch d;
-    memset(&d, 0, sizeof(d));
-    d.batch = B; d.max_persons = h->max_persons; d.flags = h->flags;
     uint8_t *d_img = (uint8_t *)g.arena.take(img_b);
     uint8_t *d_msk = (uint8_t *)g.arena.take(msk_b);
     RmpeSrcDesc *d_desc = (RmpeSrcDesc *)g.arena.take(B * sizeof(RmpeSrcDesc));
@@ -428,28 +429,57 @@ extern "C" int rmpe_gt_batch_host(const RmpeGtBatchHost *h) {
         desc[i].height = h->src_height; desc[i].width = h->src_width;
         desc[i].img_pitch = 3 * h->src_width; desc[i].mask_pitch = h->src_width;
     }
-    if (img_b) RMPE_CUDA_TRY(cudaMemcpyAsync(d_img, h->src_img, img_b, cudaMemcpyHostToDevice, st));
-    if (msk_b) RMPE_CUDA_TRY(cudaMemcpyAsync(d_msk, h->src_mask, msk_b, cudaMemcpyHostToDevice, st));
+    // small per-sample tables first, on the main stream; the chunk streams wait for them
     RMPE_CUDA_TRY(cudaMemcpyAsync(d_desc, desc.data(), B * sizeof(RmpeSrcDesc), cudaMemcpyHostToDevice, st));
     if (jnt_b) RMPE_CUDA_TRY(cudaMemcpyAsync(d_j, h->joints, jnt_b, cudaMemcpyHostToDevice, st));
     RMPE_CUDA_TRY(cudaMemcpyAsync(d_np, h->n_persons, B * 4, cudaMemcpyHostToDevice, st));
     if (!no_transform) {
         RMPE_CUDA_TRY(cudaMemcpyAsync(d_M, h->M, B * 48, cudaMemcpyHostToDevice, st));
         RMPE_CUDA_TRY(cudaMemcpyAsync(d_flip, h->flip, B, cudaMemcpyHostToDevice, st));
-    } else {
-        RMPE_CUDA_TRY(cudaMemcpyAsync(d_omsk, h->out_mask, omsk_b, cudaMemcpyHostToDevice, st));
     }
-    d.src_img = d_img; d.src_mask = d_msk; d.src_desc = d_desc; d.joints = d_j; d.n_persons = d_np;
-    d.M = d_M; d.flip = d_flip;
-    d.out_img = no_warp ? nullptr : d_oimg; d.out_mask = d_omsk; d.out_labels = d_olab;
-    d.out_joints = d_jo; d.out_count = h->out_count ? d_ocnt : nullptr; d.status = d_st;
-    rc = rmpe_gt_batch(&d, st);
-    if (rc != RMPE_OK) return rc;
-    if (h->out_img && oimg_b) RMPE_CUDA_TRY(cudaMemcpyAsync(h->out_img, d_oimg, oimg_b, cudaMemcpyDeviceToHost, st));
+    RMPE_CUDA_TRY(cudaStreamSynchronize(st));
+
+    // Chunk pipeline: sources in, kernels, results out, round-robin over three streams, so that the
+    // host-to-device copy of chunk c+1, the kernels of chunk c and the device-to-host copy of chunk c-1
+    // overlap (separate copy engines per direction).  Chunks are independent: samples never interact.
+    const int chunk = B <= 16 ? B : std::max(16, (B + 7) / 8);
+    const size_t src_img_b = (size_t)h->src_height * h->src_width * 3, src_msk_b = (size_t)h->src_height * h->src_width;
+    for (int c0 = 0, ci = 0; c0 < B; c0 += chunk, ci++) {
+        const int n = std::min(chunk, B - c0);
+        cudaStream_t cs = g.pipe[ci % 3];
+        if (img_b) RMPE_CUDA_TRY(cudaMemcpyAsync(d_img + c0 * src_img_b, h->src_img + c0 * src_img_b, n * src_img_b, cudaMemcpyHostToDevice, cs));
+        if (msk_b) RMPE_CUDA_TRY(cudaMemcpyAsync(d_msk + c0 * src_msk_b, h->src_mask + c0 * src_msk_b, n * src_msk_b, cudaMemcpyHostToDevice, cs));
+        if (no_transform)
+            RMPE_CUDA_TRY(cudaMemcpyAsync((uint8_t *)d_omsk + (size_t)c0 * kCells * esz, (const uint8_t *)h->out_mask + (size_t)c0 * kCells * esz,
+                                          (size_t)n * kCells * esz, cudaMemcpyHostToDevice, cs));
+        RmpeGtBatch d;
+        memset(&d, 0, sizeof(d));
+        d.batch = n; d.max_persons = h->max_persons; d.flags = h->flags;
+        d.src_img = d_img; d.src_mask = d_msk; d.src_desc = d_desc + c0;     // descriptor offsets are batch-relative
+        d.joints = d_j + (size_t)c0 * h->max_persons * kParts * 3; d.n_persons = d_np + c0;
+        d.M = d_M + 6 * c0; d.flip = d_flip + c0;
+        d.out_img = no_warp ? nullptr : d_oimg + (size_t)c0 * 3 * kOutW * kOutH;
+        d.out_mask = (uint8_t *)d_omsk + (size_t)c0 * kCells * esz;
+        d.out_labels = (uint8_t *)d_olab + (size_t)c0 * kLayers * kCells * esz;
+        d.out_joints = d_jo + (size_t)c0 * h->max_persons * kParts * 3;
+        d.out_count = h->out_count ? d_ocnt + (size_t)c0 * kLimbs * kCells : nullptr;
+        d.status = d_st + c0;
+        rc = rmpe_gt_batch(&d, cs);
+        if (rc != RMPE_OK) return rc;
+        if (h->out_img && oimg_b)
+            RMPE_CUDA_TRY(cudaMemcpyAsync(h->out_img + (size_t)c0 * 3 * kOutW * kOutH, d.out_img, (size_t)n * 3 * kOutW * kOutH, cudaMemcpyDeviceToHost, cs));
+        if (h->out_labels)
+            RMPE_CUDA_TRY(cudaMemcpyAsync((uint8_t *)h->out_labels + (size_t)c0 * kLayers * kCells * esz, d.out_labels,
+                                          (size_t)n * kLayers * kCells * esz, cudaMemcpyDeviceToHost, cs));
+        if (h->out_count)
+            RMPE_CUDA_TRY(cudaMemcpyAsync(h->out_count + (size_t)c0 * kLimbs * kCells, d.out_count, (size_t)n * kLimbs * kCells * 4, cudaMemcpyDeviceToHost, cs));
+    }
+    for (int i = 0; i < 3; i++) RMPE_CUDA_TRY(cudaStreamSynchronize(g.pipe[i]));
+    // the small outputs leave in one piece at the end: their host buffers are usually pageable, and a
+    // device-to-host copy into pageable memory blocks the issuing thread -- inside the loop it would
+    // serialise the chunk pipeline
     if (h->out_mask && !no_transform) RMPE_CUDA_TRY(cudaMemcpyAsync(h->out_mask, d_omsk, omsk_b, cudaMemcpyDeviceToHost, st));
-    if (h->out_labels) RMPE_CUDA_TRY(cudaMemcpyAsync(h->out_labels, d_olab, olab_b, cudaMemcpyDeviceToHost, st));
     if (h->out_joints && jnt_b) RMPE_CUDA_TRY(cudaMemcpyAsync(h->out_joints, d_jo, jnt_b, cudaMemcpyDeviceToHost, st));
-    if (h->out_count) RMPE_CUDA_TRY(cudaMemcpyAsync(h->out_count, d_ocnt, ocnt_b, cudaMemcpyDeviceToHost, st));
     if (h->status) RMPE_CUDA_TRY(cudaMemcpyAsync(h->status, d_st, B * 4, cudaMemcpyDeviceToHost, st));
     RMPE_CUDA_TRY(cudaStreamSynchronize(st));
     return RMPE_OK;

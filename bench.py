@@ -403,13 +403,27 @@ def main():
         dprof = {k: {"ms_per_launch": v[0] / v[1], "launches": v[1]} for k, v in L.profile_read().items() if v[1]}
         L.profile_enable(False, reset=True)
         fb = decode_bytes_per_frame(H, W, h, w)
+        # heat half of the staged dataflow (what k_heat_screen + k_peak_verify replace): blob in, 18 maps
+        # written by the resize and read back by the smoothing; the PAF half (38 up-sampled planes) is never
+        # produced at all -- k_limbs samples it from the blob
+        heat_b = 4 * (19 * h * w + 36 * H * W)
+        dtop = max(dprof, key=lambda k: dprof[k]["ms_per_launch"] * dprof[k]["launches"]) if dprof else None
+        droof = None
+        if dtop:
+            kms = dprof[dtop]["ms_per_launch"]
+            ach = heat_b * DEC_FRAMES / (kms * 1e-3) / 1e9 if dtop.startswith("k_heat_screen") else None
+            droof = {"bound": "hbm", "kernel": dtop, "kernel_ms": kms, "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": (ach / peak) if ach else None, "traffic": traffic_db.get(dtop),
+                     "algorithmic": "staged reference dataflow of the heat maps, 4*(19hw + 36HW) B/frame; "
+                                    "the fused kernel itself reads only the 4*19hw B blob",
+                     "fused_blob_bytes_per_frame": 4 * 57 * h * w}
         decode = {"metric": "decoded_frames_per_s", "value": world * DEC_FRAMES / (dms * 1e-3), "unit": "frames/s",
                   "ms_per_step": dms, "steps": dsteps, "gpu_launches": int(dl),
                   "config": {"workload": "single_scale_decode_674x712_84x89_blobs_3persons (configs[2] per-GPU share)",
                              "frames_per_gpu": DEC_FRAMES},
                   "staged_bytes_per_frame": fb,
                   "staged_frac_of_hbm": fb * DEC_FRAMES / (dms * 1e-3) / 1e9 / peak,
-                  "kernels": dprof}
+                  "roofline": droof, "kernels": dprof}
 
     clocks = sampler.finish()
     if world > 1:
