@@ -788,6 +788,159 @@ __global__ void __launch_bounds__(kRasterThreads) k_raster(RasterArgs a) {
 }
 
 // ==========================================================================================
+// k_raster_small: the same rasteriser for the common case of <= 4 persons per sample (COCO crops).
+// grid = (pixel slices, batch), one slice by default (measured best: the per-CTA tables are built once
+// per sample); a thread owns ONE float4 run of pixels and writes it for all 57 planes.  Everything the planes need is built once per CTA -- transformed joints, the separable
+// exp tables of all 18 parts x persons, the limb records of all 19 limbs x persons -- so the plane
+// loop has no barrier and every store is an independent coalesced 128-bit write.
+// ==========================================================================================
+constexpr int kRsMaxP = 4;
+constexpr int kRsSlices = 1;         // default pixel slices per sample (gridDim.x); blockDim.x = runs per slice, rounded to warps
+
+template <typename T>
+__global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
+    const int b = blockIdx.y;
+    const int slice = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int kRsThreads = blockDim.x;
+    const int kRsRuns = (kCellVec + gridDim.x - 1) / gridDim.x;
+    const int P = min(a.n_persons[b], kRsMaxP);
+
+    // dynamic shared memory sized for the launch's max_persons (raster_small_smem): 24 KB at 3 persons
+    extern __shared__ __align__(16) uint8_t rs_smem[];
+    const int PM = a.max_persons;
+    LimbRec *s_rec = reinterpret_cast<LimbRec *>(rs_smem);                     // [19][PM]
+    double *s_j = reinterpret_cast<double *>(s_rec + kLimbs * PM);             // [PM][18][3]
+    float *s_ex = reinterpret_cast<float *>(s_j + PM * kParts * 3);            // [18][P][46]
+    float *s_ey = s_ex + kParts * PM * kGrid;
+
+    // ---- T4: keypoint transform + flip swap (py_rmpe_transformer.py:100-111) ----
+    for (int i = tid; i < P * kParts; i += kRsThreads) {
+        int p = i / kParts, part = i - p * kParts;
+        const double *jin = a.joints + ((size_t)b * a.max_persons + p) * (kParts * 3);
+        double ox, oy, ov;
+        if (a.no_transform) {
+            ox = jin[part * 3 + 0]; oy = jin[part * 3 + 1]; ov = jin[part * 3 + 2];
+        } else {
+            int sp = a.flip[b] ? c_flip_partner[part] : part;
+            double x = jin[sp * 3 + 0], y = jin[sp * 3 + 1];
+            ov = jin[sp * 3 + 2];
+            const double *M = a.M + 6 * b;
+            ox = __dadd_rn(__fma_rn(M[1], y, __dmul_rn(M[0], x)), M[2]);
+            oy = __dadd_rn(__fma_rn(M[4], y, __dmul_rn(M[3], x)), M[5]);
+        }
+        s_j[i * 3 + 0] = ox; s_j[i * 3 + 1] = oy; s_j[i * 3 + 2] = ov;
+        if (slice == 0 && a.out_joints) {
+            double *jo = a.out_joints + ((size_t)b * a.max_persons + p) * (kParts * 3) + part * 3;
+            jo[0] = ox; jo[1] = oy; jo[2] = ov;
+        }
+    }
+    __syncthreads();
+
+    // ---- H1/H2 tables: ex/ey[part][person][cell], cell centres 8i + 3.5 (py_rmpe_heatmapper.py:22-23, 51-57) ----
+    const float inv2s2 = (float)(1.0 / (2.0 * a.sigma * a.sigma));
+    for (int i = tid; i < kParts * P * kGrid; i += kRsThreads) {
+        const int cidx = i % kGrid, pp = i / kGrid;           // pp = part * P + p
+        const int part = pp / P, p = pp - part * P;
+        const double *j = s_j + (p * kParts + part) * 3;
+        const double g = 8.0 * cidx + 3.5;
+        const float dx = (float)(g - j[0]), dy = (float)(g - j[1]);
+        const bool vis = j[2] < 2.0;
+        s_ex[i] = vis ? expf(-(dx * dx) * inv2s2) : 0.f;
+        s_ey[i] = vis ? expf(-(dy * dy) * inv2s2) : 0.f;
+    }
+    // ---- H4 limb records: [limb][person] ----
+    const double thre = a.thre;
+    for (int i = tid; i < kLimbs * P; i += kRsThreads) {
+        const int k = i / P, p = i - k * P;
+        const double *jf = s_j + (p * kParts + c_limb_from[k]) * 3, *jt = s_j + (p * kParts + c_limb_to[k]) * 3;
+        LimbRec r;
+        r.minx = r.maxx = r.miny = r.maxy = 0;
+        r.x1 = jf[0]; r.y1 = jf[1];
+        const double x2 = jt[0], y2 = jt[1];
+        r.xD = __dsub_rn(x2, r.x1); r.yD = __dsub_rn(y2, r.y1);
+        r.norm2 = __dsqrt_rn(__dadd_rn(__dmul_rn(r.xD, r.xD), __dmul_rn(r.yD, r.yD)));
+        r.ux = r.uy = 0.f;
+        if (jf[2] < 2.0 && jt[2] < 2.0) {
+            if (r.norm2 == 0.0) {
+                if (slice == 0) atomicOr(a.status + b, RMPE_ST_ZERO_LIMB);
+            } else {
+                r.ux = (float)__ddiv_rn(r.xD, r.norm2);
+                r.uy = (float)__ddiv_rn(r.yD, r.norm2);
+                const double mnx = r.x1 < x2 ? r.x1 : x2, mxx = r.x1 < x2 ? x2 : r.x1;
+                const double mny = r.y1 < y2 ? r.y1 : y2, mxy = r.y1 < y2 ? y2 : r.y1;
+                const int a0 = py_round(__ddiv_rn(__dsub_rn(mnx, thre), 8.0));
+                const int b0 = py_round(__ddiv_rn(__dsub_rn(mny, thre), 8.0));
+                const int a1 = py_round(__ddiv_rn(__dadd_rn(mxx, thre), 8.0));
+                const int b1 = py_round(__ddiv_rn(__dadd_rn(mxy, thre), 8.0));
+                if (a1 >= 0 && b1 >= 0) {
+                    r.minx = max(a0, 0); r.miny = max(b0, 0);
+                    r.maxx = min(a1, kGrid); r.maxy = min(b1, kGrid);
+                    if (r.maxy <= r.miny) r.maxx = r.minx;  // empty slice
+                }
+            }
+        }
+        s_rec[i] = r;
+    }
+    __syncthreads();
+
+    const int run = slice * kRsRuns + tid;
+    if (tid >= kRsRuns || run >= kCellVec) return;
+    const int pix = 4 * run;
+    int y[4], x[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { y[q] = (pix + q) / kGrid; x[q] = (pix + q) - y[q] * kGrid; }
+    T m[4];
+    {
+        const T *mk = reinterpret_cast<const T *>(a.mask) + (size_t)b * kCells + pix;
+#pragma unroll
+        for (int q = 0; q < 4; q++) m[q] = mk[q];
+    }
+    T *lab = reinterpret_cast<T *>(a.labels) + (size_t)b * kLayers * kCells + pix;
+
+    // ---- H2/H3: Gaussian part maps with max merge, background = 1 - max ----
+    float bk[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (int part = 0; part < kParts; part++) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int p = 0; p < P; p++) {
+            const float *ex = s_ex + (part * P + p) * kGrid, *ey = s_ey + (part * P + p) * kGrid;
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[q] = fmaxf(v[q], ey[y[q]] * ex[x[q]]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) bk[q] = fmaxf(bk[q], v[q]);
+        store4<T>(lab + (size_t)(38 + part) * kCells, v[0], v[1], v[2], v[3], m);
+    }
+    store4<T>(lab + (size_t)56 * kCells, 1.f - bk[0], 1.f - bk[1], 1.f - bk[2], 1.f - bk[3], m);
+
+    // ---- H4: part-affinity fields ----
+    const int ymin = y[0], ymax = y[3];
+    for (int k = 0; k < kLimbs; k++) {
+        float vx[4] = {0.f, 0.f, 0.f, 0.f}, vy[4] = {0.f, 0.f, 0.f, 0.f};
+        int cnt[4] = {0, 0, 0, 0};
+        for (int p = 0; p < P; p++) {
+            const LimbRec &r = s_rec[k * P + p];
+            if (r.maxx <= r.minx || r.maxy <= ymin || r.miny > ymax) continue;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (x[q] >= r.minx && x[q] < r.maxx && y[q] >= r.miny && y[q] < r.maxy) {
+                    const double X = (double)(8 * x[q]), Y = (double)(8 * y[q]);
+                    double dd = __dsub_rn(__dmul_rn(r.xD, __dsub_rn(r.y1, Y)), __dmul_rn(__dsub_rn(r.x1, X), r.yD));
+                    dd = __ddiv_rn(dd, r.norm2);
+                    if (fabs(dd) <= thre) { vx[q] = r.ux; vy[q] = r.uy; cnt[q]++; }
+                }
+            }
+        }
+        store4<T>(lab + (size_t)(2 * k) * kCells, vx[0], vx[1], vx[2], vx[3], m);
+        store4<T>(lab + (size_t)(2 * k + 1) * kCells, vy[0], vy[1], vy[2], vy[3], m);
+        if (a.out_count)
+            *reinterpret_cast<int4 *>(a.out_count + ((size_t)b * kLimbs + k) * kCells + pix) =
+                make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
+    }
+}
+
+// ==========================================================================================
 // host entry
 // ==========================================================================================
 constexpr int kMaxSmemOptin = 227 * 1024;
@@ -893,10 +1046,24 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
         ra.out_count = b->out_count; ra.status = b->status; ra.max_persons = b->max_persons;
         ra.f64 = (b->flags & RMPE_GT_LABELS_F64) ? 1 : 0; ra.no_transform = no_transform ? 1 : 0;
         ra.sigma = 7.0; ra.thre = 8.0;
-        dim3 grid(3, b->batch);
         ProfScope ps("k_raster", st);
-        if (ra.f64) k_raster<double><<<grid, kRasterThreads, 0, st>>>(ra);
-        else k_raster<float><<<grid, kRasterThreads, 0, st>>>(ra);
+        if (b->max_persons <= kRsMaxP && !simple) {
+            static const int slices = [] {
+                const char *e = getenv("RMPE_RASTER_SLICES");
+                int v = e ? atoi(e) : kRsSlices;
+                return (v >= 1 && v <= 8) ? v : kRsSlices;
+            }();
+            dim3 grid(slices, b->batch);
+            const int kRsThreads = (((kCellVec + slices - 1) / slices) + 31) & ~31;
+            const int pm = b->max_persons;
+            const size_t smem = (size_t)kLimbs * pm * sizeof(LimbRec) + (size_t)pm * kParts * 3 * 8 + 2 * (size_t)kParts * pm * kGrid * 4;
+            if (ra.f64) k_raster_small<double><<<grid, kRsThreads, smem, st>>>(ra);
+            else k_raster_small<float><<<grid, kRsThreads, smem, st>>>(ra);
+        } else {
+            dim3 grid(3, b->batch);
+            if (ra.f64) k_raster<double><<<grid, kRasterThreads, 0, st>>>(ra);
+            else k_raster<float><<<grid, kRasterThreads, 0, st>>>(ra);
+        }
         count_launch();
     }
     RMPE_CUDA_TRY(cudaGetLastError());

@@ -37,9 +37,17 @@ def main():
     for simple in (True, False):
         ms = ev_time(lambda: plan.run(simple=simple))
         print("GT batch %d %s: %.3f ms  -> %.0f samples/s" % (B, "simple" if simple else "tile", ms, B / ms * 1e3), flush=True)
+    L = rmpe_b200.lib
+    L.profile_enable(True)
+    for _ in range(5):
+        plan.run()
+    torch.cuda.synchronize()
+    L.profile_enable(False, reset=False)
+    for k, (tms, n) in L.profile_read().items():
+        print("   %-20s %.4f ms/launch" % (k, tms / max(n, 1)))
+    L.profile_enable(False, reset=True)
     # per-kernel split via flags
     d = plan.desc_struct
-    L = rmpe_b200.lib
     full_flags = d.flags
     d.flags = full_flags | L.GT_NO_WARP
     ms = ev_time(lambda: plan.run())
