@@ -32,7 +32,7 @@ EXPORTS = [
     "rmpe_decode_workspace_bytes", "rmpe_decode_batch", "rmpe_decode_batch_host",
     "rmpe_debug_heat_maps", "rmpe_debug_paf_points", "rmpe_pad_right_down_corner",
     "rmpe_launch_count", "rmpe_profile_enable", "rmpe_profile_reset", "rmpe_profile_count",
-    "rmpe_profile_get",
+    "rmpe_profile_get", "rmpe_keras_batch", "rmpe_keras_batch_host",
 ]
 
 _vp = C.c_void_p
@@ -63,6 +63,11 @@ class GtBatchHost(C.Structure):
                 ("M", _vp), ("flip", _vp),
                 ("out_img", _vp), ("out_mask", _vp), ("out_labels", _vp), ("out_joints", _vp),
                 ("out_count", _vp), ("status", _vp)]
+
+
+class KerasBatch(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("flags", C.c_int32), ("labels", _vp), ("mask", _vp),
+                ("vec_weights", _vp), ("heat_weights", _vp), ("vec_label", _vp), ("heat_label", _vp)]
 
 
 class FrameDesc(C.Structure):
@@ -150,6 +155,10 @@ def load():
     lib.rmpe_profile_count.restype = C.c_int
     lib.rmpe_profile_get.argtypes = [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.rmpe_profile_get.restype = C.c_int
+    lib.rmpe_keras_batch.argtypes = [C.POINTER(KerasBatch), _vp]
+    lib.rmpe_keras_batch.restype = C.c_int
+    lib.rmpe_keras_batch_host.argtypes = [C.POINTER(KerasBatch)]
+    lib.rmpe_keras_batch_host.restype = C.c_int
     lib.rmpe_debug_bicubic_table.argtypes = [_vp]
     lib.rmpe_debug_bicubic_table.restype = C.c_int
     _lib = lib

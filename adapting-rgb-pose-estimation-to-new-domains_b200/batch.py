@@ -132,6 +132,29 @@ def heatmaps_host(joints, n_persons, mask, *, f64=True, want_count=False):
     return dict(labels=labels, count=count, status=status)
 
 
+def keras_batch_host(labels, mask):
+    """DataIteratorBase.gen's batch assembly (training/ds_generators.py:47-77) for a whole batch:
+    labels (B,57,46,46), mask (B,46,46) of one float dtype -> dict(x1 (B,46,46,38) mask repeated,
+    x2 (B,46,46,19), y1 (B,46,46,38) = labels[:, :38] as NHWC, y2 (B,46,46,19))."""
+    lib = L.ensure_init()
+    labels = np.ascontiguousarray(labels)
+    f64 = labels.dtype == np.float64
+    ft = np.float64 if f64 else np.float32
+    labels = L.c_contig(labels, ft)
+    mask = L.c_contig(mask, ft)
+    B = labels.shape[0]
+    assert labels.shape == (B, NL, GRID, GRID) and mask.shape == (B, GRID, GRID)
+    out = dict(x1=np.empty((B, GRID, GRID, 38), ft), x2=np.empty((B, GRID, GRID, 19), ft),
+               y1=np.empty((B, GRID, GRID, 38), ft), y2=np.empty((B, GRID, GRID, 19), ft))
+    k = L.KerasBatch()
+    k.batch, k.flags = B, (L.GT_LABELS_F64 if f64 else 0)
+    k.labels, k.mask = L.ptr(labels), L.ptr(mask)
+    k.vec_weights, k.heat_weights, k.vec_label, k.heat_label = (L.ptr(out["x1"]), L.ptr(out["x2"]), L.ptr(out["y1"]),
+                                                                L.ptr(out["y2"]))
+    L.check(lib.rmpe_keras_batch_host(C.byref(k)))
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # GT, device-resident (torch tensors)
 # ------------------------------------------------------------------------------------------
@@ -140,7 +163,7 @@ class GtDevicePlan:
     the current torch stream and returns immediately."""
 
     def __init__(self, batch, max_persons, src_hw=(368, 368), f64=False, chw=False, want_count=False,
-                 device=None):
+                 device=None, keras=False):
         import torch
         self.torch = torch
         self.lib = L.ensure_init(device)
@@ -181,6 +204,18 @@ class GtDevicePlan:
         d.out_count = L.ptr(self.out_count)
         d.status = L.ptr(self.status)
         self.desc_struct = d
+        self.keras = None
+        if keras:   # Keras-ready NHWC tensors (DataIteratorBase.gen) produced on the device right after the labels
+            self.x1 = torch.empty((batch, GRID, GRID, 38), dtype=ft, device=dev)
+            self.x2 = torch.empty((batch, GRID, GRID, 19), dtype=ft, device=dev)
+            self.y1 = torch.empty((batch, GRID, GRID, 38), dtype=ft, device=dev)
+            self.y2 = torch.empty((batch, GRID, GRID, 19), dtype=ft, device=dev)
+            k = L.KerasBatch()
+            k.batch, k.flags = batch, (L.GT_LABELS_F64 if f64 else 0)
+            k.labels, k.mask = L.ptr(self.out_labels), L.ptr(self.out_mask)
+            k.vec_weights, k.heat_weights, k.vec_label, k.heat_label = (L.ptr(self.x1), L.ptr(self.x2), L.ptr(self.y1),
+                                                                        L.ptr(self.y2))
+            self.keras = k
 
     def upload(self, imgs, masks, joints, n_persons, M, flip, non_blocking=False):
         t = self.torch
@@ -200,6 +235,8 @@ class GtDevicePlan:
         if stream is None:
             stream = self.torch.cuda.current_stream(self.device).cuda_stream
         L.check(self.lib.rmpe_gt_batch(C.byref(d), C.c_void_p(stream)))
+        if self.keras is not None:
+            L.check(self.lib.rmpe_keras_batch(C.byref(self.keras), C.c_void_p(stream)))
 
 
 # ------------------------------------------------------------------------------------------

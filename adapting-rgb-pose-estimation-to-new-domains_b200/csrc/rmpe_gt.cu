@@ -941,6 +941,42 @@ __global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
 }
 
 // ==========================================================================================
+// k_keras_batch: DataIteratorBase.gen's per-sample transposes / repeats (training/ds_generators.py:47-63)
+// as one pass: a CTA takes two grid rows (92 pixels) of one sample, reads the 57 label planes as
+// coalesced row segments into shared memory and writes the four NHWC tensors as contiguous runs.
+// ==========================================================================================
+constexpr int kKbPix = 2 * kGrid;     // 92 pixels per CTA
+constexpr int kKbThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kKbThreads) k_keras_batch(RmpeKerasBatch a) {
+    __shared__ T s_lab[kLayers][kKbPix + 1];
+    __shared__ T s_m[kKbPix];
+    const int b = blockIdx.y, p0 = blockIdx.x * kKbPix, tid = threadIdx.x;
+    const T *lab = reinterpret_cast<const T *>(a.labels) + (size_t)b * kLayers * kCells + p0;
+    if (a.vec_label || a.heat_label)
+        for (int i = tid; i < kLayers * kKbPix; i += kKbThreads) {
+            const int c = i / kKbPix, p = i - c * kKbPix;
+            s_lab[c][p] = lab[(size_t)c * kCells + p];
+        }
+    if (tid < kKbPix) s_m[tid] = reinterpret_cast<const T *>(a.mask)[(size_t)b * kCells + p0 + tid];
+    __syncthreads();
+    const size_t o38 = ((size_t)b * kCells + p0) * 38, o19 = ((size_t)b * kCells + p0) * 19;
+    T *y1 = reinterpret_cast<T *>(a.vec_label), *y2 = reinterpret_cast<T *>(a.heat_label);
+    T *x1 = reinterpret_cast<T *>(a.vec_weights), *x2 = reinterpret_cast<T *>(a.heat_weights);
+    for (int i = tid; i < kKbPix * 38; i += kKbThreads) {
+        const int p = i / 38, c = i - p * 38;
+        if (y1) y1[o38 + i] = s_lab[c][p];
+        if (x1) x1[o38 + i] = s_m[p];
+    }
+    for (int i = tid; i < kKbPix * 19; i += kKbThreads) {
+        const int p = i / 19, c = i - p * 19;
+        if (y2) y2[o19 + i] = s_lab[38 + c][p];
+        if (x2) x2[o19 + i] = s_m[p];
+    }
+}
+
+// ==========================================================================================
 // host entry
 // ==========================================================================================
 constexpr int kMaxSmemOptin = 227 * 1024;
@@ -1066,6 +1102,22 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
         }
         count_launch();
     }
+    RMPE_CUDA_TRY(cudaGetLastError());
+    return RMPE_OK;
+}
+
+extern "C" int rmpe_keras_batch(const RmpeKerasBatch *b, void *stream_) {
+    if (!is_initialised()) { set_error("rmpe_init not called"); return RMPE_E_NOTINIT; }
+    RMPE_REQUIRE(b != nullptr && b->batch >= 0, "descriptor");
+    if (b->batch == 0) return RMPE_OK;
+    RMPE_REQUIRE(b->mask != nullptr, "mask is required");
+    RMPE_REQUIRE(b->labels != nullptr || (!b->vec_label && !b->heat_label), "labels is required for y1 / y2");
+    cudaStream_t st = (cudaStream_t)stream_;
+    dim3 grid(kCells / kKbPix, b->batch);
+    ProfScope ps("k_keras_batch", st);
+    if (b->flags & RMPE_GT_LABELS_F64) k_keras_batch<double><<<grid, kKbThreads, 0, st>>>(*b);
+    else k_keras_batch<float><<<grid, kKbThreads, 0, st>>>(*b);
+    count_launch();
     RMPE_CUDA_TRY(cudaGetLastError());
     return RMPE_OK;
 }

@@ -2,6 +2,7 @@
 // matrix / RNG (T1), the host-buffer wrappers and padRightDownCorner.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -442,7 +443,12 @@ extern "C" int rmpe_gt_batch_host(const RmpeGtBatchHost *h) {
     // Chunk pipeline: sources in, kernels, results out, round-robin over three streams, so that the
     // host-to-device copy of chunk c+1, the kernels of chunk c and the device-to-host copy of chunk c-1
     // overlap (separate copy engines per direction).  Chunks are independent: samples never interact.
-    const int chunk = B <= 16 ? B : std::max(16, (B + 7) / 8);
+    static const int n_chunks = [] {
+        const char *e = getenv("RMPE_HOST_CHUNKS");
+        int v = e ? atoi(e) : 16;
+        return (v >= 1 && v <= 64) ? v : 16;
+    }();
+    const int chunk = B <= 8 ? B : std::max(8, (B + n_chunks - 1) / n_chunks);
     const size_t src_img_b = (size_t)h->src_height * h->src_width * 3, src_msk_b = (size_t)h->src_height * h->src_width;
     for (int c0 = 0, ci = 0; c0 < B; c0 += chunk, ci++) {
         const int n = std::min(chunk, B - c0);
@@ -481,6 +487,41 @@ extern "C" int rmpe_gt_batch_host(const RmpeGtBatchHost *h) {
     if (h->out_mask && !no_transform) RMPE_CUDA_TRY(cudaMemcpyAsync(h->out_mask, d_omsk, omsk_b, cudaMemcpyDeviceToHost, st));
     if (h->out_joints && jnt_b) RMPE_CUDA_TRY(cudaMemcpyAsync(h->out_joints, d_jo, jnt_b, cudaMemcpyDeviceToHost, st));
     if (h->status) RMPE_CUDA_TRY(cudaMemcpyAsync(h->status, d_st, B * 4, cudaMemcpyDeviceToHost, st));
+    RMPE_CUDA_TRY(cudaStreamSynchronize(st));
+    return RMPE_OK;
+}
+
+extern "C" int rmpe_keras_batch_host(const RmpeKerasBatch *h) {
+    if (!g.init) { set_error("rmpe_init not called"); return RMPE_E_NOTINIT; }
+    RMPE_REQUIRE(h != nullptr && h->batch >= 0, "descriptor");
+    if (h->batch == 0) return RMPE_OK;
+    RMPE_REQUIRE(h->mask != nullptr, "mask is required");
+    std::lock_guard<std::mutex> lk(g.mu);
+    RMPE_CUDA_TRY(cudaSetDevice(g.device));
+    const size_t esz = (h->flags & RMPE_GT_LABELS_F64) ? 8 : 4;
+    const size_t B = (size_t)h->batch;
+    const size_t lab_b = h->labels ? B * kLayers * kCells * esz : 0, msk_b = B * kCells * esz;
+    const size_t o38 = B * kCells * 38 * esz, o19 = B * kCells * 19 * esz;
+    int rc = g.arena.reserve(Arena::need(lab_b) + Arena::need(msk_b) + 2 * Arena::need(o38) + 2 * Arena::need(o19));
+    if (rc != RMPE_OK) return rc;
+    g.arena.reset();
+    cudaStream_t st = g.stream;
+    RmpeKerasBatch d = *h;
+    void *d_lab = lab_b ? g.arena.take(lab_b) : nullptr;
+    void *d_msk = g.arena.take(msk_b);
+    if (lab_b) RMPE_CUDA_TRY(cudaMemcpyAsync(d_lab, h->labels, lab_b, cudaMemcpyHostToDevice, st));
+    RMPE_CUDA_TRY(cudaMemcpyAsync(d_msk, h->mask, msk_b, cudaMemcpyHostToDevice, st));
+    d.labels = d_lab; d.mask = d_msk;
+    d.vec_weights = h->vec_weights ? g.arena.take(o38) : nullptr;
+    d.heat_weights = h->heat_weights ? g.arena.take(o19) : nullptr;
+    d.vec_label = h->vec_label ? g.arena.take(o38) : nullptr;
+    d.heat_label = h->heat_label ? g.arena.take(o19) : nullptr;
+    rc = rmpe_keras_batch(&d, st);
+    if (rc != RMPE_OK) return rc;
+    if (h->vec_weights) RMPE_CUDA_TRY(cudaMemcpyAsync(h->vec_weights, d.vec_weights, o38, cudaMemcpyDeviceToHost, st));
+    if (h->heat_weights) RMPE_CUDA_TRY(cudaMemcpyAsync(h->heat_weights, d.heat_weights, o19, cudaMemcpyDeviceToHost, st));
+    if (h->vec_label) RMPE_CUDA_TRY(cudaMemcpyAsync(h->vec_label, d.vec_label, o38, cudaMemcpyDeviceToHost, st));
+    if (h->heat_label) RMPE_CUDA_TRY(cudaMemcpyAsync(h->heat_label, d.heat_label, o19, cudaMemcpyDeviceToHost, st));
     RMPE_CUDA_TRY(cudaStreamSynchronize(st));
     return RMPE_OK;
 }

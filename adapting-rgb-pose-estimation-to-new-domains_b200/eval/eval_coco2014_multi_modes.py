@@ -108,3 +108,52 @@ def process_multi_scale(input_image, model, params, model_params, draw=True, **c
     frame = dict(H=oriImg.shape[0], W=oriImg.shape[1], scales=scales)
     r = decode_frames([frame], params, model_params, **caps)[0]
     return _finish(input_image, oriImg, r, draw)
+
+
+# ------------------------------------------------------------------------------------------
+# result writer (reference write_json, eval/eval_coco2014_multi_modes.py:514-548): the step right
+# after the decode path.  Pure host formatting of (candidate, subset) -- no arithmetic on maps.
+# ------------------------------------------------------------------------------------------
+def coco_keypoint_records(candidate_set, subset_set, image_id_set, category_id=1):
+    """List of COCO keypoint result dicts exactly as the reference builds them: 17 parts in
+    orderCOCO with the neck skipped, (int x, int y, 2) or (0, 0, 0) for a missing part, score =
+    subset[-2] (total score, not the mean)."""
+    output_data = []
+    for i in range(len(subset_set)):
+        cand = np.asarray(candidate_set[i], dtype=np.float64).reshape(-1, 4)
+        for person in np.asarray(subset_set[i], dtype=np.float64).reshape(-1, 20):
+            keypoints = []
+            for part in range(18):
+                part_idx = orderCOCO[part]
+                if part_idx == 1:      # skip neck for coco eval
+                    continue
+                idx = int(person[part_idx])
+                if idx == -1:
+                    keypoints += [0, 0, 0]
+                else:
+                    keypoints += [cand[idx, 0].astype(int), cand[idx, 1].astype(int), 2]
+            output_data.append({"image_id": image_id_set[i], "category_id": category_id,
+                                "keypoints": keypoints, "score": person[-2]})
+    return output_data
+
+
+def write_json(candidate_set, subset_set, image_id_set, json_file):
+    """Same signature as the reference: `json_file` is an open text file, closed on return."""
+    import json
+
+    def _plain(o):
+        if isinstance(o, np.generic):
+            return o.item()
+        raise TypeError(type(o))
+
+    with json_file as outfile:
+        json.dump(coco_keypoint_records(candidate_set, subset_set, image_id_set), outfile, default=_plain)
+
+
+def gather_records(local_records, n_images):
+    """Optional multi-GPU gather of the per-rank record lists: every rank decodes the
+    images i % world == rank; rank order is restored by image position.  local_records: list of
+    (position, [records of that image])."""
+    from .. import shard as _shard
+    merged = _shard.gather_results([dict(index=int(p), records=r) for p, r in local_records], n_images)
+    return [rec for m in merged for rec in m["records"]]

@@ -1,0 +1,114 @@
+"""Drop-in for the batching half of the reference's training/ds_generators.py (DataIteratorBase.gen
+:31-106, DataIterator :189-218): the step right after the GT path.
+
+`gen(n_stages)` yields `[x (B,368,368,3) u8, x1 (B,46,46,38), x2 (B,46,46,19)], [y1 (B,46,46,38),
+y2 (B,46,46,19)] * n_stages` like the reference.  The per-sample transposes / repeats / concatenations
+of the reference (:47-77) run as ONE pass of k_keras_batch over the whole batch (rmpe_keras_batch);
+`FusedDataIterator` additionally runs warp + mask + labels for the whole batch in one call instead
+of sample by sample.  The ZMQ client (DataGeneratorClient) is transport, not arithmetic: out of scope."""
+import numpy as np
+
+from .. import batch as _batch
+from ..py_rmpe_server.py_rmpe_data_iterator import RawDataIterator
+from ..py_rmpe_server.py_rmpe_transformer import AugmentSelection
+
+
+class DataIteratorBase:
+
+    def __init__(self, batch_size=10):
+        self.batch_size = batch_size
+        self.split_point = 38
+        self.vec_num = 38
+        self.heat_num = 19
+        self.keypoints = [None] * self.batch_size  # not passed to the NN; read by accuracy code
+
+    def _recv_arrays(self):
+        raise NotImplementedError
+
+    def gen_raw(self):
+        while True:
+            yield tuple(self._recv_arrays())
+
+    def gen(self, n_stages):
+        imgs, masks, labels = [], [], []
+        for foo in self.gen_raw():
+            if len(foo) == 4:
+                data_img, mask_img, label, kpts = foo
+            else:
+                data_img, mask_img, label = foo
+                kpts = None
+            imgs.append(np.transpose(data_img, (1, 2, 0)))
+            masks.append(mask_img)
+            labels.append(label)
+            self.keypoints[len(imgs) - 1] = kpts
+            if len(imgs) == self.batch_size:
+                kb = _batch.keras_batch_host(np.stack(labels), np.stack(masks))
+                batch_x = np.stack(imgs)
+                imgs, masks, labels = [], [], []
+                yield [batch_x, kb["x1"], kb["x2"]], [kb["y1"], kb["y2"]] * n_stages
+                self.keypoints = [None] * self.batch_size
+
+
+class DataIterator(DataIteratorBase):
+    """In-process iterator over an HDF5 file, sample by sample like the reference (:189-218)."""
+
+    def __init__(self, file, shuffle=True, augment=True, batch_size=10, limit=None):
+        super(DataIterator, self).__init__(batch_size)
+        self.limit = limit
+        self.records = 0
+        self.raw_data_iterator = RawDataIterator(file, shuffle=shuffle, augment=augment)
+        self.generator = self.raw_data_iterator.gen()
+
+    def _recv_arrays(self):
+        while True:
+            if self.limit is not None and self.records > self.limit:
+                raise StopIteration
+            tpl = next(self.generator, None)
+            if tpl is not None:
+                self.records += 1
+                return tpl
+            if self.limit is None or self.records < self.limit:
+                print("Staring next generator loop cycle")
+                self.generator = self.raw_data_iterator.gen()
+            else:
+                raise StopIteration
+
+
+class FusedDataIterator(DataIteratorBase):
+    """Batched superset: `source` yields raw (img HxWx3 u8, mask HxW u8, meta) triples of one
+    geometry (what RawDataIterator.read_data returns); a whole batch goes through ONE
+    rmpe_gt_batch_host call and ONE rmpe_keras_batch_host call."""
+
+    def __init__(self, source, augment=True, batch_size=10):
+        super(FusedDataIterator, self).__init__(batch_size)
+        self.source = source
+        self.augment = augment
+
+    def gen(self, n_stages):
+        buf = []
+        for img, mask, meta in self.source:
+            buf.append((np.asarray(img), np.asarray(mask), meta))
+            if len(buf) < self.batch_size:
+                continue
+            augs = [AugmentSelection.random() if self.augment else AugmentSelection.unrandom() for _ in buf]
+            P = max(np.asarray(m['joints']).shape[0] for _, _, m in buf)
+            joints = np.zeros((len(buf), max(P, 1), 18, 3))
+            joints[:, :, :, 2] = 2.0                     # padding persons are "absent"
+            n_persons = np.zeros(len(buf), np.int32)
+            for i, (_, _, m) in enumerate(buf):
+                j = np.asarray(m['joints'], dtype=np.float64)
+                joints[i, :j.shape[0]] = j
+                n_persons[i] = j.shape[0]
+            M = _batch.aug_affine([a.flip for a in augs], [a.degree for a in augs], [a.crop for a in augs],
+                                  [a.scale for a in augs], [m['objpos'][0] for _, _, m in buf],
+                                  [m['scale_provided'][0] for _, _, m in buf])
+            r = _batch.gt_batch_host(np.stack([b[0] for b in buf]), np.stack([b[1] for b in buf]), joints, n_persons, M,
+                                     [1 if a.flip else 0 for a in augs], f64=True)
+            kb = _batch.keras_batch_host(r["labels"], r["mask"])
+            for i, (_, _, m) in enumerate(buf):
+                if n_persons[i]:
+                    m['joints'][:, :, :] = r["joints"][i, :n_persons[i]]
+                self.keypoints[i] = m['joints']
+            buf = []
+            yield [r["img"], kb["x1"], kb["x2"]], [kb["y1"], kb["y2"]] * n_stages
+            self.keypoints = [None] * self.batch_size

@@ -151,6 +151,26 @@ typedef struct RmpeGtBatchHost {
 int rmpe_gt_batch_host(const RmpeGtBatchHost *b);
 
 /* ---------------------------------------------------------------------------------------- */
+/* Batch assembly of DataIteratorBase.gen (training/ds_generators.py:31-106): the step right     */
+/* after the GT path.  Turns the planar labels / mask of rmpe_gt_batch into the Keras-ready NHWC  */
+/* tensors  x1 = mask repeated to 38 channels, x2 = mask repeated to 19, y1 = labels[0:38] as     */
+/* (46,46,38), y2 = labels[38:57] as (46,46,19)  (reference :52-63).  Any output may be NULL.     */
+/* ---------------------------------------------------------------------------------------- */
+typedef struct RmpeKerasBatch {
+    int32_t batch;
+    int32_t flags;            /* RMPE_GT_LABELS_F64: all six arrays are float64 instead of float32 */
+    const void *labels;       /* [batch][57][46][46] */
+    const void *mask;         /* [batch][46][46] */
+    void *vec_weights;        /* x1 [batch][46][46][38] */
+    void *heat_weights;       /* x2 [batch][46][46][19] */
+    void *vec_label;          /* y1 [batch][46][46][38] */
+    void *heat_label;         /* y2 [batch][46][46][19] */
+} RmpeKerasBatch;
+
+int rmpe_keras_batch(const RmpeKerasBatch *b, void *stream);      /* device pointers, asynchronous */
+int rmpe_keras_batch_host(const RmpeKerasBatch *b);               /* host pointers, synchronous */
+
+/* ---------------------------------------------------------------------------------------- */
 /* D1-D6: process_single_scale / process_multi_scale from the network blobs on               */
 /*   (eval/eval_coco2014_multi_modes.py:263-415 and :58-231)                                  */
 /* ---------------------------------------------------------------------------------------- */

