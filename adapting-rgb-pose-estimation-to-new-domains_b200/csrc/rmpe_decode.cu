@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(kScrThreads) k_heat_screen(const __grid_consta
     const int mylox = J.lox[xg];
     if (half == 0) {
         atomicMin(&s_rng[2], mylox);
-        atomicMax(&s_rng[3], min(mylox + KWX - 1, w - 1));
+        atomicMax(&s_rng[3], min(mylox + J.kwx - 1, w - 1));   // J.kwx, not KWX: the host sizes the tile for it
     }
     __syncthreads();
     const int r0 = s_rng[0], c0 = s_rng[2];
@@ -1364,7 +1364,7 @@ static int launch_heat_up(const RmpeFrameDesc *fr, int n, const float *heat, int
         int m = 0, c1 = 0, r1 = 0, r2 = 0, c3 = 0, r4 = 0;
         for (int i = 0; i < n; i++) {
             const RmpeFrameDesc &f = fr[i];
-            if (f.n_scales <= 1 || s >= f.n_scales) continue;
+            if (f.n_scales <= 1 || s >= f.n_scales || (plans && plans[i].screen)) continue;
             int hs = f.grid_h[s], ws = f.grid_w[s];
             int Hc = hs * stride - f.pad_down[s], Wc = ws * stride - f.pad_right[s];
             // (1) horizontal x stride: blob (hs, ws) -> P1 (hs, Wc)   [columns beyond the crop never read]

@@ -189,3 +189,17 @@ def test_full_size_properties_ski_batch(rmpe):
         assert r["status"] == 0 and len(r["subset"]) >= 1
     cand, sub = do.single_scale(frames[1]["scales"][0][0], frames[1]["scales"][0][1], H, W)
     assert np.array_equal(res[1]["candidate"], cand) and np.array_equal(res[1]["subset"], sub)
+
+
+def test_mixed_screened_and_materialised_frames(rmpe):
+    """One batch holding frames of both heat paths: the float32 screening path and -- for frames whose
+    up-sampling factor is too small for its tiles (240x320 at scale 2) -- the materialised exact path."""
+    cases = [("m0", 240, 320, 3, 21, True), ("m1", 427, 640, 4, 22, True), ("m2", 96, 120, 2, 23, False),
+             ("m3", 480, 640, 2, 24, True), ("m4", 240, 320, 2, 25, True)]
+    frames = [frames_of(c) for c in cases]
+    res = rmpe.batch.decode_batch_host(frames)
+    for c, r in zip(cases, res):
+        o = _oracle(c, detail=False)
+        assert r["status"] == 0
+        assert np.array_equal(r["candidate"], o[0]), c[0]
+        assert np.array_equal(r["subset"], o[1]), c[0]
