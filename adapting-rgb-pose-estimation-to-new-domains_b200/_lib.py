@@ -25,6 +25,7 @@ ST_FOUND_GT2 = 0x10
 ST_SINGULAR = 0x20
 
 MAX_SCALES = 4
+DECODE_REUSE_TABLES = 0x1
 
 EXPORTS = [
     "rmpe_init", "rmpe_shutdown", "rmpe_last_error", "rmpe_abi_version", "rmpe_device",

@@ -358,6 +358,8 @@ class DecodeDevicePlan:
         if stream is None:
             stream = self.torch.cuda.current_stream(self.device).cuda_stream
         L.check(self.lib.rmpe_decode_batch(C.byref(self.d), C.c_void_p(stream)))
+        # the operator tables in the workspace depend on the frame geometry only: later runs of this plan reuse them
+        self.d.flags |= L.DECODE_REUSE_TABLES
 
     def results(self):
         self.torch.cuda.synchronize(self.device)

@@ -1119,28 +1119,37 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
     __shared__ int s_off[kLimbs + 1];
     const double *cand = candidate + (size_t)frame * kParts * max_peaks * 4;
     // ---- one pass over global memory: connection rows and peak scores of the frame ----
-    int ntot = 0;
-    for (int q = 0; q < kParts; q++) ntot += n_peaks[frame * kParts + q];
-    if (lane == 0) {
-        int o = 0;
-        for (int k = 0; k < kLimbs; k++) { s_off[k] = o; o += max(n_conn[frame * kLimbs + k], 0); }
-        s_off[kLimbs] = o;
+    // counts in one parallel load per lane (a serial loop pays one global round trip per element)
+    __shared__ int s_nc[kLimbs];
+    int ntot = (lane < kParts) ? n_peaks[frame * kParts + lane] : 0;
+    const int my_nc = (lane < kLimbs) ? n_conn[frame * kLimbs + lane] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ntot += __shfl_xor_sync(0xffffffffu, ntot, o);
+    int incl = max(my_nc, 0);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
     }
+    if (lane < kLimbs) { s_off[lane] = incl - max(my_nc, 0); s_nc[lane] = my_nc; }
+    if (lane == kLimbs - 1) s_off[kLimbs] = incl;
     __syncwarp();
     for (int i = lane; i < ntot; i += 32) s_score[i] = cand[(size_t)i * 4 + 2];
-    for (int k = 0; k < kLimbs; k++) {
-        const int nck = s_off[k + 1] - s_off[k];
-        const double *conn = connections + ((size_t)frame * kLimbs + k) * max_peaks * 5;
-        for (int i = lane; i < nck * 3; i += 32) {
-            const int r = i / 3, c = i - 3 * r;
-            if (s_off[k] + r < kAsmConnRows) s_conn[(s_off[k] + r) * 3 + c] = conn[r * 5 + c];
+    {   // all limbs' rows in one flat pass (a loop over limbs would pay one global round trip per limb)
+        const int rows_all = min(s_off[kLimbs], kAsmConnRows);
+        for (int i = lane; i < rows_all * 3; i += 32) {
+            const int row = i / 3, c = i - 3 * row;
+            int k = 0;
+#pragma unroll
+            for (int q = 1; q < kLimbs; q++) k += (s_off[q] <= row) ? 1 : 0;   // s_off is non-decreasing
+            s_conn[i] = connections[((size_t)frame * kLimbs + k) * max_peaks * 5 + (size_t)(row - s_off[k]) * 5 + c];
         }
     }
     __syncwarp();
     int nrows = 0;
     int st = 0;
     for (int k = 0; k < kLimbs; k++) {
-        const int nc = n_conn[frame * kLimbs + k];
+        const int nc = s_nc[k];
         if (nc < 0) continue;
         const int ia = c_dec_a[k], ib = c_dec_b[k];
         const double *conn = connections + ((size_t)frame * kLimbs + k) * max_peaks * 5;
@@ -1525,8 +1534,10 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
             size_t ms_smem = 0;
             const int cand_cap = (int)std::min<size_t>(per_list * 2, (size_t)n * kParts * MP * 2);
             if (f0 > 0) RMPE_CUDA_TRY(cudaMemsetAsync(cand_count, 0, 4, st));
+            const bool reuse_tables = (b->flags & RMPE_DECODE_REUSE_TABLES) != 0;
             auto flush_tables = [&]() {
                 if (!n_tab) return;
+                if (reuse_tables) { n_tab = 0; max_len = 0; return; }
                 ProfScope ps("k_axis_tables", st);
                 k_axis_tables<<<dim3((max_len + 127) / 128, n_tab), 128, 0, st>>>(aj, tab_err);
                 count_launch();

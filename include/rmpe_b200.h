@@ -189,6 +189,11 @@ typedef struct RmpeFrameDesc {
     int64_t paf_offset[RMPE_MAX_SCALES];
 } RmpeFrameDesc;
 
+/* RmpeDecodeBatch.flags */
+#define RMPE_DECODE_REUSE_TABLES 0x1 /* the workspace still holds the up-sampling/smoothing operator tables of a
+                                        previous call with the same frames, capacities and workspace: skip rebuilding
+                                        them (they depend on frame geometry only) */
+
 typedef struct RmpeDecodeBatch {
     int32_t batch;
     int32_t max_peaks;     /* capacity per part (<= 1024) */
