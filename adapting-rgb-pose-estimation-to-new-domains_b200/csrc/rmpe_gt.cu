@@ -1034,7 +1034,7 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
     const bool want_mask = !no_transform && !warp_only;
     bool mask_done = false;
     if (!no_warp) {
-        RMPE_REQUIRE(((size_t)b->out_img & 15) == 0, "out_img must be 16-byte aligned");
+        RMPE_REQUIRE(((size_t)b->out_img & 3) == 0, "out_img must be 4-byte aligned");
         if (simple) {
             WarpArgs wa;
             wa.src_img = b->src_img; wa.desc = b->src_desc; wa.M = b->M; wa.out_img = b->out_img;
