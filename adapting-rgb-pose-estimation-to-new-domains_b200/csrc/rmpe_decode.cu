@@ -327,27 +327,24 @@ __global__ void __launch_bounds__(kSmoothThreads) k_smooth_peaks(const __grid_co
 // both linear and separable, so the smoothed map is  S = Ky * blob * Kx^T  with composite
 // per-axis operators  K = G * R  that have ~(24 h/H + 5) non-zeros per row.
 //   k_axis_tables  builds K (f64 accumulation, stored f32) and the first source index per row.
-//   k_heat_screen  evaluates S~ = Ky * blob * Kx^T straight from the NHWC blob (the 57x larger
-//                  up-sampled map is never written), and emits every pixel that could be a peak
-//                  once a rigorous bound delta on |S~ - S| is allowed for: S~ > thre1 - delta and
-//                  S~ >= neighbour~ - 2 delta for the four neighbours.
+//   k_screen_plan / k_screen_pairs  evaluate S~ = Ky * blob * Kx^T straight from the NHWC blob
+//                  (the 57x larger up-sampled map is never written) and emit every pixel that could
+//                  be a peak once a rigorous bound delta on |S~ - S| is allowed for:
+//                  S~ > thre1 - delta and S~ >= neighbour~ - 2 delta for the four neighbours.
 //   k_peak_verify  re-evaluates each such pixel and its four neighbours EXACTLY -- cv2's float32
 //                  tap order, scipy's f64 accumulation order and per-axis float32 store -- and
 //                  applies the reference's test; survivors go to the same raw lists that
 //                  k_smooth_peaks fills, so ordering/ids are restored by k_peaks_finalize.
-// delta: S and S~ are sums of <= ~60 rounded float32 operations on terms bounded by
-// (sum|Ky|)(sum|Kx|) max|blob| <= 1.9 max|blob| (bicubic a=-0.75: sum|c| <= 1.375; Gaussian: 1),
-// i.e. |S~ - S| <= 60 * 2^-24 * 1.9 * max|blob| = 6.8e-6 max|blob|; kScreenDelta = 2e-5 of the
-// tile's max|blob| leaves a 3x margin.
 // ------------------------------------------------------------------------------------------
 constexpr int kScrTW = 126;          // interior columns of a screening tile
 constexpr int kScrTH = 32;           // interior rows
 constexpr int kScrCols = kScrTW + 2; // with the 1-pixel ring the 4-neighbour test needs
 constexpr int kScrRows = kScrTH + 2;
 constexpr int kScrThreads = 256;
-constexpr int kScrMaxSrcRows = 16;   // staged blob rows per tile (dense vertical operator)
-constexpr int kScrMaxKW = 12;        // non-zeros per row of Kx
-constexpr float kScreenDelta = 2.0e-5f;
+constexpr int kScrMaxSrcRows = 16;   // single scale: staged blob rows per tile (dense vertical operator)
+constexpr int kScrMaxKW = 12;        // single scale: non-zeros per row of Kx (a 10-wide variant covers stride 8)
+constexpr int kMsKW = 12;            // multi scale: non-zeros per row of Kx_s
+constexpr int kMsMaxRows = 24;       // multi scale: staged blob rows per scale and tile
 
 struct AxisJob {
     int dst, src, kw;
@@ -401,187 +398,40 @@ __global__ void __launch_bounds__(128) k_axis_tables(const __grid_constant__ Axi
         });
     }
     J.lo[d] = lo;
-    for (int i = 0; i < kw; i++) J.K[(size_t)d * J.kw + i] = (float)(acc[i] * (double)J.wscale);
-}
-
-struct ScreenJob {
-    const float *heat;    // NHWC (h,w,19) blob of the frame
-    const float *Ky, *Kx;
-    const int *loy, *lox;
-    int H, W, h, w, kwy, kwx;
-    int frame, tiles_x, tiles;
-};
-struct ScreenJobs {
-    ScreenJob j[kChunkFrames];
-};
-
-template <int KWX>
-__global__ void __launch_bounds__(kScrThreads) k_heat_screen(const __grid_constant__ ScreenJobs jobs, float thre1,
-                                                              int cand_cap, int32_t *__restrict__ cand_key,
-                                                              int32_t *__restrict__ cand_fp,
-                                                              int32_t *__restrict__ cand_count,
-                                                              const int32_t *__restrict__ tab_err,
-                                                              int32_t *__restrict__ status) {
-    const ScreenJob &J = jobs.j[blockIdx.y];
-    if ((int)blockIdx.x >= J.tiles) return;
-    if (*tab_err) {   // an operator row did not fit its table (cannot happen with plan_frame's bound): never screen on it
-        if (threadIdx.x == 0) atomicOr(status + J.frame, RMPE_ST_PEAK_OVERFLOW);
-        return;
+    double pos = 0.0, neg = 0.0;
+    for (int i = 0; i < kw; i++) {
+        const double v = acc[i] * (double)J.wscale;
+        J.K[(size_t)d * J.kw + i] = (float)v;
+        if (v > 0.0) pos += v; else neg -= v;
     }
-    const int H = J.H, W = J.W, h = J.h, w = J.w;
-    const int ty = blockIdx.x / J.tiles_x, tx = blockIdx.x - ty * J.tiles_x;
-    const int y0 = ty * kScrTH, x0 = tx * kScrTW;          // first interior pixel
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int col = tid & (kScrCols - 1), half = tid >> 7;  // 128 columns x 2 row halves
-
-    extern __shared__ __align__(16) uint8_t sm_raw[];
-    __shared__ int s_rng[4];            // r0, r1, c0, c1 of the staged blob region
-    __shared__ int s_bmax[kHeatC];      // max |blob| per channel over the staged region (float bits)
-    __shared__ int s_loy[kScrRows];
-
-    // ---- staged source region ----
-    if (tid < 4) s_rng[tid] = (tid & 1) ? INT_MIN : INT_MAX;
-    if (tid < kHeatC) s_bmax[tid] = 0;
-    __syncthreads();
-    if (tid < kScrRows) {
-        const int y = clampi(y0 - 1 + tid, 0, H - 1);
-        const int lo = J.loy[y];
-        s_loy[tid] = lo;
-        atomicMin(&s_rng[0], lo);
-        atomicMax(&s_rng[1], min(lo + J.kwy - 1, h - 1));
-    }
-    const int xg = clampi(x0 - 1 + col, 0, W - 1);          // this thread's (clamped) column
-    const int mylox = J.lox[xg];
-    if (half == 0) {
-        atomicMin(&s_rng[2], mylox);
-        atomicMax(&s_rng[3], min(mylox + J.kwx - 1, w - 1));   // J.kwx, not KWX: the host sizes the tile for it
-    }
-    __syncthreads();
-    const int r0 = s_rng[0], c0 = s_rng[2];
-    const int nrows = s_rng[1] - r0 + 1, ncols = s_rng[3] - c0 + 1;
-    float *sB = reinterpret_cast<float *>(sm_raw);                   // [nrows][ncols][19]
-    float *sT = sB + ((nrows * ncols * kHeatC + 3) & ~3);            // [nrows][128]
-    float *sS = sT + nrows * kScrCols;                               // [34][128]
-    float *sKy = sS + kScrRows * kScrCols;                           // [34][kScrMaxSrcRows] dense over staged rows
-    if (nrows > kScrMaxSrcRows) {   // host sized the launch for this never to happen
-        if (tid == 0) atomicOr(status + J.frame, RMPE_ST_PEAK_OVERFLOW);
-        return;
-    }
-    {
-        const int rowlen = ncols * kHeatC;
-        for (int i = tid; i < nrows * rowlen; i += kScrThreads) {
-            const int r = i / rowlen, e = i - r * rowlen;
-            sB[i] = J.heat[((size_t)(r0 + r) * w + c0) * kHeatC + e];
-        }
-        // dense vertical operator of the tile: sKy[row][i] = Ky[y][i - (loy[y]-r0)] or 0
-        for (int i = tid; i < kScrRows * kScrMaxSrcRows; i += kScrThreads) {
-            const int r = i / kScrMaxSrcRows, q = i - r * kScrMaxSrcRows;
-            const int y = clampi(y0 - 1 + r, 0, H - 1);
-            const int k = q - (s_loy[r] - r0);
-            sKy[i] = (k >= 0 && k < J.kwy) ? J.Ky[(size_t)y * J.kwy + k] : 0.f;
-        }
-    }
-    float kxw[KWX];
-#pragma unroll
-    for (int j = 0; j < KWX; j++) kxw[j] = (j < J.kwx) ? J.Kx[(size_t)xg * J.kwx + j] : 0.f;
-    const int off = mylox - c0;     // first staged column of this thread's taps
-    __syncthreads();
-    // max |blob| per part over the staged region: scales delta and lets whole parts be skipped
-    for (int part = tid >> 5; part < kParts; part += kScrThreads / 32) {
-        float m = 0.f;
-        for (int i = lane; i < nrows * ncols; i += 32) m = fmaxf(m, fabsf(sB[i * kHeatC + part]));
-        const int mi = __reduce_max_sync(0xffffffffu, __float_as_int(m));
-        if (lane == 0) s_bmax[part] = mi;
-    }
-    __syncthreads();
-
-    for (int part = 0; part < kParts; part++) {
-        // A part whose staged blob values are all small cannot produce a peak in this tile:
-        // |S| <= (sum|Ky|)(sum|Kx|) max|blob| <= 1.375^2 max|blob| (+ rounding), a peak needs S > thre1.
-        const float bmax = __int_as_float(s_bmax[part]);
-        if (1.8907f * bmax + kScreenDelta * bmax <= thre1) continue;    // block-uniform
-        // ---- horizontal: T[i][col] = sum_j Kx[col][j] * B[i][lox+j][part] ----
-        for (int i = half; i < nrows; i += 2) {
-            const float *b = sB + ((size_t)i * ncols + off) * kHeatC + part;
-            float acc = 0.f;
-#pragma unroll
-            for (int j = 0; j < KWX; j++)
-                if (off + j < ncols) acc = fmaf(kxw[j], b[j * kHeatC], acc);   // beyond: zero padding of Kx
-            sT[i * kScrCols + col] = acc;
-        }
-        __syncthreads();
-        // ---- vertical: S[r][col] = sum_i sKy[r][i] * T[i][col], 17 rows per thread ----
-        float tcol[kScrMaxSrcRows];
-#pragma unroll
-        for (int i = 0; i < kScrMaxSrcRows; i++) tcol[i] = (i < nrows) ? sT[i * kScrCols + col] : 0.f;
-#pragma unroll 1
-        for (int q = 0; q < kScrRows / 2; q++) {
-            const int r = half * (kScrRows / 2) + q;
-            const float4 *ky = reinterpret_cast<const float4 *>(sKy + r * kScrMaxSrcRows);
-            float acc = 0.f;
-#pragma unroll
-            for (int i4 = 0; i4 < kScrMaxSrcRows / 4; i4++) {
-                const float4 k4 = ky[i4];
-                acc = fmaf(k4.x, tcol[4 * i4 + 0], acc);
-                acc = fmaf(k4.y, tcol[4 * i4 + 1], acc);
-                acc = fmaf(k4.z, tcol[4 * i4 + 2], acc);
-                acc = fmaf(k4.w, tcol[4 * i4 + 3], acc);
-            }
-            sS[r * kScrCols + col] = acc;
-        }
-        __syncthreads();
-        // ---- conservative 4-neighbour test on the interior ----
-        const float delta = kScreenDelta * bmax;
-        const float lim = thre1 - delta, d2 = 2.f * delta;
-        for (int q = 0; q < kScrTH / 2; q++) {
-            const int r = 1 + half * (kScrTH / 2) + q;
-            const int y = y0 + r - 1, x = x0 + col - 1;
-            bool cand = false;
-            if (col >= 1 && col <= kScrTW && y < H && x < W) {
-                const float sv = sS[r * kScrCols + col];
-                if (sv > lim) {
-                    const float up = (y > 0) ? sS[(r - 1) * kScrCols + col] : 0.f;
-                    const float dn = (y < H - 1) ? sS[(r + 1) * kScrCols + col] : 0.f;
-                    const float lf = (x > 0) ? sS[r * kScrCols + col - 1] : 0.f;
-                    const float rt = (x < W - 1) ? sS[r * kScrCols + col + 1] : 0.f;
-                    cand = (sv >= up - d2) && (sv >= dn - d2) && (sv >= lf - d2) && (sv >= rt - d2);
-                }
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, cand);
-            if (bal) {
-                const int leader = __ffs(bal) - 1;
-                int slot0 = 0;
-                if (lane == leader) slot0 = atomicAdd(cand_count, __popc(bal));
-                slot0 = __shfl_sync(0xffffffffu, slot0, leader);
-                if (cand) {
-                    const int slot = slot0 + __popc(bal & ((1u << lane) - 1));
-                    if (slot < cand_cap) {
-                        cand_key[slot] = y * W + x;
-                        cand_fp[slot] = J.frame * kParts + part;
-                    } else {
-                        atomicOr(status + J.frame, RMPE_ST_PEAK_OVERFLOW);
-                    }
-                }
-            }
-        }
-        // sT / sS are rewritten only after the next part's barriers
-    }
+    // largest positive / negative row mass of the operator (float bits; the table block is zeroed before):
+    // bounds S by P * max(blob,0) + N * max(-blob,0) in k_screen_plan
+    atomicMax(&J.lo[J.dst], __float_as_int((float)(pos * 1.000001)));
+    atomicMax(&J.lo[J.dst + 1], __float_as_int((float)(neg * 1.000001)));
 }
 
 // ------------------------------------------------------------------------------------------
-// k_heat_screen_ms: the same screening for process_multi_scale frames.  The scale-averaged,
-// smoothed map is  S = sum_s Ky_s * blob_s * Kx_s^T  (1/n_scales folded into Ky_s; each K_s is the
-// composite of the Gaussian, the resize to (H,W), the crop and the x8 resize), so a tile stages the
-// blob region of every scale, runs the horizontal pass per scale and accumulates the vertical
-// passes in registers.  Rounding budget: two cv2.resize per scale in the reference (28 float32
-// roundings), ~40 in S~; all partial sums are bounded by A = 1.375^4 mean_s max|blob_s|, so
-// |S~ - S| <= 70 * 2^-24 * A = 4.2e-6 A; kScreenDeltaMs = 1.2e-5 A.
+// Screening kernels.  S = sum_s Ky_s * blob_s * Kx_s^T (one scale for process_single_scale; for
+// process_multi_scale each K_s is the composite of the Gaussian, the resize to (H,W), the crop and the
+// x8 resize, with 1/n_scales folded into Ky_s).
+//   k_screen_plan   per (tile, frame): max(blob,0) and max(-blob,0) of every part over the blob region the tile
+//                   depends on.  With P / N the positive / negative mass of Ky (x) Kx (row masses left behind
+//                   the tables by k_axis_tables),  S <= sum_s P_s max(B_s,0) + N_s max(-B_s,0);  a part whose
+//                   bound + delta <= thre1 cannot hold a peak in the tile and is dropped, the others become
+//                   work items of up to `group` parts of one tile.  Heat maps are near zero away from
+//                   keypoints (and network noise stays below thre1 / P), so most of the 18 x tiles pairs
+//                   disappear here.
+//   k_screen_pairs  persistent CTAs over the work items (a tile with many active parts does not serialise them
+//                   in one CTA): operators of the tile once per item; per part: blob region per scale through
+//                   cp.async (the next part's copy in flight), horizontal pass, vertical pass accumulated over
+//                   the scales in registers, conservative 4-neighbour test.
+// Rounding budget: the reference spends <= 14 float32 roundings per cv2.resize (two per scale in the
+// multi-scale chain) plus two stores per Gaussian axis, S~ ~40; all partial sums are bounded by
+// A = sum_s (P_s + N_s) max|B_s|, so |S~ - S| <= 70 * 2^-24 * A = 4.2e-6 A; kScreenDelta = 1.2e-5 A.
 // ------------------------------------------------------------------------------------------
-constexpr int kMsKW = 12;            // non-zeros per row of Kx_s
-constexpr int kMsMaxRows = 24;       // staged blob rows per scale and tile
-constexpr int kMsJobsPerLaunch = 12;
-constexpr float kMsAmp = 3.5745f;    // 1.375^4
-constexpr float kScreenDeltaMs = 1.2e-5f;
+constexpr int kMsJobsPerLaunch = kChunkFrames;
+constexpr float kScreenDelta = 1.2e-5f;
+constexpr int kPlanThreads = 256;
 
 struct MsScale {
     const float *heat;
@@ -596,8 +446,122 @@ struct MsJob {
 struct MsJobs {
     MsJob j[kMsJobsPerLaunch];
 };
+struct ActEntry {          // one work item of k_screen_pairs: up to `group` active parts of one tile
+    int job, tile;
+    unsigned parts;         // bit p = part p is screened by this item
+    int slot;               // index of its 18 bounds in act_A
+};
 
-template <int NR>
+// blob region of every scale that a tile's 34 x 128 smoothed values depend on: s_rng[sc] = {r0, r1, c0, c1};
+// also the first source row of each tile row (s_loy) and this thread's first source column (mylox)
+__device__ __forceinline__ void tile_ranges(const MsJob &J, int y0, int x0, int tid, int col, int half,
+                                            int (*s_rng)[4], int (*s_loy)[kScrRows], int mylox[RMPE_MAX_SCALES]) {
+    if (tid < 4 * RMPE_MAX_SCALES) s_rng[tid >> 2][tid & 3] = (tid & 1) ? INT_MIN : INT_MAX;
+    __syncthreads();
+    const int xg = clampi(x0 - 1 + col, 0, J.W - 1);
+#pragma unroll
+    for (int sc = 0; sc < RMPE_MAX_SCALES; sc++) {
+        mylox[sc] = 0;
+        if (sc < J.n_scales) {
+            const MsScale &S = J.sc[sc];
+            if (tid < kScrRows) {
+                const int lo = S.loy[clampi(y0 - 1 + tid, 0, J.H - 1)];
+                s_loy[sc][tid] = lo;
+                atomicMin(&s_rng[sc][0], lo);
+                atomicMax(&s_rng[sc][1], min(lo + S.kwy - 1, S.h - 1));
+            }
+            mylox[sc] = S.lox[xg];
+            if (half == 0) {
+                atomicMin(&s_rng[sc][2], mylox[sc]);
+                atomicMax(&s_rng[sc][3], min(mylox[sc] + S.kwx - 1, S.w - 1));
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kPlanThreads) k_screen_plan(const __grid_constant__ MsJobs jobs, float thre1, int act_cap,
+                                                              int group, ActEntry *__restrict__ act,
+                                                              float *__restrict__ act_A, int32_t *__restrict__ act_count,
+                                                              const int32_t *__restrict__ tab_err,
+                                                              int32_t *__restrict__ status) {
+    const MsJob &J = jobs.j[blockIdx.y];
+    if ((int)blockIdx.x >= J.tiles) return;
+    if (*tab_err) {   // an operator row did not fit its table (cannot happen with plan_frame's bound): never screen on it
+        if (threadIdx.x == 0) atomicOr(status + J.frame, RMPE_ST_PEAK_OVERFLOW);
+        return;
+    }
+    const int NS = J.n_scales;
+    const int ty = blockIdx.x / J.tiles_x, tx = blockIdx.x - ty * J.tiles_x;
+    const int tid = threadIdx.x;
+    __shared__ int s_rng[RMPE_MAX_SCALES][4];
+    __shared__ int s_loy[RMPE_MAX_SCALES][kScrRows];
+    __shared__ int s_bpos[RMPE_MAX_SCALES][kHeatC + 1], s_bneg[RMPE_MAX_SCALES][kHeatC + 1];
+    int mylox[RMPE_MAX_SCALES];
+    if (tid < RMPE_MAX_SCALES * (kHeatC + 1)) { (&s_bpos[0][0])[tid] = 0; (&s_bneg[0][0])[tid] = 0; }
+    tile_ranges(J, ty * kScrTH, tx * kScrTW, tid, tid & (kScrCols - 1), tid >> 7, s_rng, s_loy, mylox);
+    for (int sc = 0; sc < NS; sc++) {
+        const MsScale &S = J.sc[sc];
+        const int r0 = s_rng[sc][0], c0 = s_rng[sc][2];
+        const int nrows = s_rng[sc][1] - r0 + 1, rowlen = (s_rng[sc][3] - c0 + 1) * kHeatC;
+        // coalesced row segments of the NHWC blob; element e of a segment belongs to channel e % 19
+        for (int r = 0; r < nrows; r++) {
+            const float *row = S.heat + ((size_t)(r0 + r) * S.w + c0) * kHeatC;
+            for (int e = tid; e < rowlen; e += kPlanThreads) {
+                const float v = row[e];
+                int *dst = (v > 0.f) ? &s_bpos[sc][0] : &s_bneg[sc][0];       // one atomic per element, no divergence
+                atomicMax(dst + e % kHeatC, __float_as_int(fabsf(v)));
+            }
+        }
+    }
+    __syncthreads();
+    // S = sum_s sum_ij Ky_s[i] Kx_s[j] B_s[i][j]: the positive entries of Ky (x) Kx weigh max(B,0), the negative ones
+    // max(-B,0); P = Py+ Px+ + Py- Px-, N = Py+ Px- + Py- Px+ with the row masses k_axis_tables left behind the tables
+    __shared__ float s_A[kParts];
+    __shared__ int s_on[kParts];
+    if (tid < kParts) {
+        float bound = 0.f, atot = 0.f;
+        for (int sc = 0; sc < NS; sc++) {
+            const MsScale &S = J.sc[sc];
+            const float yp = __int_as_float(S.loy[J.H]), yn = __int_as_float(S.loy[J.H + 1]);
+            const float xp = __int_as_float(S.lox[J.W]), xn = __int_as_float(S.lox[J.W + 1]);
+            const float P = yp * xp + yn * xn, N = yp * xn + yn * xp;
+            const float bp = __int_as_float(s_bpos[sc][tid]), bn = __int_as_float(s_bneg[sc][tid]);
+            bound += P * bp + N * bn;
+            atot += (P + N) * fmaxf(bp, bn);
+        }
+        bound *= 1.0001f; atot *= 1.0001f;      // atot bounds every partial sum: scales the rounding allowance
+        s_A[tid] = atot;
+        s_on[tid] = (bound + kScreenDelta * atot > thre1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // active parts (a peak needs S > thre1), cut into work items of at most `group` parts
+        unsigned m = 0;
+        int n = 0;
+        for (int p = 0; p <= kParts; p++) {
+            const bool on = p < kParts && s_on[p];
+            if (on) { m |= 1u << p; n++; }
+            if ((n == group || p == kParts) && m) {
+                const int slot = atomicAdd(act_count, 1);
+                if (slot < act_cap) {
+                    act[slot] = ActEntry{(int)blockIdx.y, (int)blockIdx.x, m, slot};
+                    for (int q = 0; q < kParts; q++) act_A[(size_t)slot * kParts + q] = s_A[q];
+                } else {
+                    atomicOr(status + J.frame, RMPE_ST_PEAK_OVERFLOW);
+                }
+                m = 0; n = 0;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void cp_async4(float *smem_dst, const float *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int NR, int MAXROWS>
 __device__ __forceinline__ void ms_vertical(const float *__restrict__ sT, const float *__restrict__ sKy, int col, int half,
                                             int nrows, float acc[kScrRows / 2]) {
     float tcol[NR];
@@ -605,7 +569,7 @@ __device__ __forceinline__ void ms_vertical(const float *__restrict__ sT, const 
     for (int i = 0; i < NR; i++) tcol[i] = (i < nrows) ? sT[i * kScrCols + col] : 0.f;
 #pragma unroll
     for (int q = 0; q < kScrRows / 2; q++) {
-        const float4 *ky = reinterpret_cast<const float4 *>(sKy + (half * (kScrRows / 2) + q) * kMsMaxRows);
+        const float4 *ky = reinterpret_cast<const float4 *>(sKy + (half * (kScrRows / 2) + q) * MAXROWS);
         float a = acc[q];
 #pragma unroll
         for (int i4 = 0; i4 < NR / 4; i4++) {
@@ -619,168 +583,152 @@ __device__ __forceinline__ void ms_vertical(const float *__restrict__ sT, const 
     }
 }
 
-__global__ void __launch_bounds__(kScrThreads) k_heat_screen_ms(const __grid_constant__ MsJobs jobs, float thre1,
-                                                                 int cand_cap, int32_t *__restrict__ cand_key,
-                                                                 int32_t *__restrict__ cand_fp,
-                                                                 int32_t *__restrict__ cand_count,
-                                                                 const int32_t *__restrict__ tab_err,
-                                                                 int32_t *__restrict__ status) {
-    const MsJob &J = jobs.j[blockIdx.y];
-    if ((int)blockIdx.x >= J.tiles) return;
-    if (*tab_err) {
-        if (threadIdx.x == 0) atomicOr(status + J.frame, RMPE_ST_PEAK_OVERFLOW);
-        return;
-    }
-    const int H = J.H, W = J.W, NS = J.n_scales;
-    const int ty = blockIdx.x / J.tiles_x, tx = blockIdx.x - ty * J.tiles_x;
-    const int y0 = ty * kScrTH, x0 = tx * kScrTW;
+template <int KWX, int MAXROWS>
+__global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_constant__ MsJobs jobs, float thre1, int act_cap,
+                                                              const ActEntry *__restrict__ act,
+                                                              const float *__restrict__ act_A,
+                                                              const int32_t *__restrict__ act_count, int cand_cap,
+                                                              int32_t *__restrict__ cand_key,
+                                                              int32_t *__restrict__ cand_fp,
+                                                              int32_t *__restrict__ cand_count,
+                                                              int32_t *__restrict__ status) {
     const int tid = threadIdx.x, lane = tid & 31;
-    const int col = tid & (kScrCols - 1), half = tid >> 7;
-
+    const int col = tid & (kScrCols - 1), half = tid >> 7;   // 128 columns x 2 row halves
     extern __shared__ __align__(16) uint8_t sm_raw[];
     __shared__ int s_rng[RMPE_MAX_SCALES][4];
-    __shared__ int s_bmax[RMPE_MAX_SCALES][kHeatC];
     __shared__ int s_loy[RMPE_MAX_SCALES][kScrRows];
     __shared__ int s_boff[RMPE_MAX_SCALES + 1], s_toff[RMPE_MAX_SCALES + 1];
+    const int n_act = min(*act_count, act_cap);
 
-    if (tid < 4 * RMPE_MAX_SCALES) s_rng[tid >> 2][tid & 3] = (tid & 1) ? INT_MIN : INT_MAX;
-    __syncthreads();
-    const int xg = clampi(x0 - 1 + col, 0, W - 1);
-    int mylox[RMPE_MAX_SCALES];
-#pragma unroll
-    for (int sc = 0; sc < RMPE_MAX_SCALES; sc++) {
-        mylox[sc] = 0;
-        if (sc < NS) {
-            const MsScale &S = J.sc[sc];
-            if (tid < kScrRows) {
-                const int lo = S.loy[clampi(y0 - 1 + tid, 0, H - 1)];
-                s_loy[sc][tid] = lo;
-                atomicMin(&s_rng[sc][0], lo);
-                atomicMax(&s_rng[sc][1], min(lo + S.kwy - 1, S.h - 1));
+    for (int ai = blockIdx.x; ai < n_act; ai += gridDim.x) {
+        const ActEntry E = act[ai];
+        const MsJob &J = jobs.j[E.job];
+        const int H = J.H, W = J.W, NS = J.n_scales;
+        const int ty = E.tile / J.tiles_x, tx = E.tile - ty * J.tiles_x;
+        const int y0 = ty * kScrTH, x0 = tx * kScrTW;          // first interior pixel
+        int mylox[RMPE_MAX_SCALES];
+        __syncthreads();                                        // the previous item's shared memory is free
+        tile_ranges(J, y0, x0, tid, col, half, s_rng, s_loy, mylox);
+        if (tid == 0) {
+            int bo = 0, to = 0;
+            for (int sc = 0; sc < NS; sc++) {
+                const int nr = s_rng[sc][1] - s_rng[sc][0] + 1, nc = s_rng[sc][3] - s_rng[sc][2] + 1;
+                s_boff[sc] = bo; bo += (nr * (nc + KWX) + 3) & ~3;      // rows padded with KWX zeros: no tap predicate
+                s_toff[sc] = to; to += nr * kScrCols;
             }
-            mylox[sc] = S.lox[xg];
-            if (half == 0) {
-                atomicMin(&s_rng[sc][2], mylox[sc]);
-                atomicMax(&s_rng[sc][3], min(mylox[sc] + S.kwx - 1, S.w - 1));
-            }
+            s_boff[NS] = bo; s_toff[NS] = to;
         }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int bo = 0, to = 0;
+        __syncthreads();
+        float *sBall = reinterpret_cast<float *>(sm_raw);                 // 2 x [sc][nrows][ncols + KWX]: this part / next part
+        float *sTall = sBall + 2 * s_boff[NS];                            // [sc][nrows][128]
+        float *sS = sTall + s_toff[NS];                                   // [34][128]
+        float *sKyAll = sS + kScrRows * kScrCols;                         // [NS][34][MAXROWS] dense over staged rows
+        float *sKxAll = sKyAll + NS * kScrRows * MAXROWS;                 // [NS][128][KWX]
+        bool bad = false;
+        for (int sc = 0; sc < NS; sc++) bad = bad || (s_rng[sc][1] - s_rng[sc][0] + 1 > MAXROWS);
+        if (bad) {   // host sized the launch for this never to happen
+            if (tid == 0) atomicOr(status + J.frame, RMPE_ST_PEAK_OVERFLOW);
+            continue;
+        }
+        const int xg = clampi(x0 - 1 + col, 0, W - 1);
+        // operators of the tile, once per item
         for (int sc = 0; sc < NS; sc++) {
-            const int nr = s_rng[sc][1] - s_rng[sc][0] + 1, nc = s_rng[sc][3] - s_rng[sc][2] + 1;
-            s_boff[sc] = bo; bo += (nr * nc * kHeatC + 3) & ~3;
-            s_toff[sc] = to; to += nr * kScrCols;
+            const MsScale &S = J.sc[sc];
+            const int r0 = s_rng[sc][0];
+            float *sKy = sKyAll + sc * kScrRows * MAXROWS;
+            for (int i = tid; i < kScrRows * MAXROWS; i += kScrThreads) {
+                const int r = i / MAXROWS, q = i - r * MAXROWS;
+                const int y = clampi(y0 - 1 + r, 0, H - 1);
+                const int k = q - (s_loy[sc][r] - r0);
+                sKy[i] = (k >= 0 && k < S.kwy) ? S.Ky[(size_t)y * S.kwy + k] : 0.f;
+            }
+            if (half == 0) {
+                float *kx = sKxAll + ((size_t)sc * kScrCols + col) * KWX;
+                for (int j = 0; j < KWX; j++) kx[j] = (j < S.kwx) ? S.Kx[(size_t)xg * S.kwx + j] : 0.f;
+            }
         }
-        s_boff[NS] = bo; s_toff[NS] = to;
-    }
-    __syncthreads();
-    float *sBall = reinterpret_cast<float *>(sm_raw);
-    float *sTall = sBall + s_boff[NS];
-    float *sS = sTall + s_toff[NS];
-    float *sKyAll = sS + kScrRows * kScrCols;                         // [NS][34][kMsMaxRows]
-    float *sKxAll = sKyAll + NS * kScrRows * kMsMaxRows;              // [NS][128][kMsKW]
-    bool bad = false;
-    for (int sc = 0; sc < NS; sc++) bad = bad || (s_rng[sc][1] - s_rng[sc][0] + 1 > kMsMaxRows);
-    if (bad) {   // host sized the launch for this never to happen
-        if (tid == 0) atomicOr(status + J.frame, RMPE_ST_PEAK_OVERFLOW);
-        return;
-    }
-    for (int sc = 0; sc < NS; sc++) {
-        const MsScale &S = J.sc[sc];
-        const int r0 = s_rng[sc][0], c0 = s_rng[sc][2];
-        const int nrows = s_rng[sc][1] - r0 + 1, ncols = s_rng[sc][3] - c0 + 1;
-        float *sB = sBall + s_boff[sc];
-        const int rowlen = ncols * kHeatC;
-        for (int i = tid; i < nrows * rowlen; i += kScrThreads) {
-            const int r = i / rowlen, e = i - r * rowlen;
-            sB[i] = S.heat[((size_t)(r0 + r) * S.w + c0) * kHeatC + e];
-        }
-        float *sKy = sKyAll + sc * kScrRows * kMsMaxRows;
-        for (int i = tid; i < kScrRows * kMsMaxRows; i += kScrThreads) {
-            const int r = i / kMsMaxRows, q = i - r * kMsMaxRows;
-            const int y = clampi(y0 - 1 + r, 0, H - 1);
-            const int k = q - (s_loy[sc][r] - r0);
-            sKy[i] = (k >= 0 && k < S.kwy) ? S.Ky[(size_t)y * S.kwy + k] : 0.f;
-        }
-        if (half == 0) {
-            float *kx = sKxAll + ((size_t)sc * kScrCols + col) * kMsKW;
-            for (int j = 0; j < kMsKW; j++) kx[j] = (j < S.kwx) ? S.Kx[(size_t)xg * S.kwx + j] : 0.f;
-        }
-    }
-    __syncthreads();
-    for (int i = tid >> 5; i < NS * kParts; i += kScrThreads / 32) {
-        const int sc = i / kParts, part = i - sc * kParts;
-        const int n = (s_rng[sc][1] - s_rng[sc][0] + 1) * (s_rng[sc][3] - s_rng[sc][2] + 1);
-        const float *sB = sBall + s_boff[sc];
-        float m = 0.f;
-        for (int e = lane; e < n; e += 32) m = fmaxf(m, fabsf(sB[e * kHeatC + part]));
-        const int mi = __reduce_max_sync(0xffffffffu, __float_as_int(m));
-        if (lane == 0) s_bmax[sc][part] = mi;
-    }
-    __syncthreads();
-
-    for (int part = 0; part < kParts; part++) {
-        float bsum = 0.f;
-        for (int sc = 0; sc < NS; sc++) bsum += __int_as_float(s_bmax[sc][part]);
-        const float A = kMsAmp * bsum / (float)NS * 1.0001f;     // bound on |S| and on every partial sum
-        const float delta = kScreenDeltaMs * A;
-        if (A + delta <= thre1) continue;                        // block-uniform: no peak of this part in the tile
-        // ---- horizontal passes ----
+        const int x = x0 + col - 1;
+        const bool col_ok = col >= 1 && col <= kScrTW && x < W;
+        // blob values of one part -> shared memory with cp.async (4-byte gathers out of the NHWC blob): the copy
+        // of the NEXT part is in flight while this part is screened
+        for (int i = tid; i < 2 * s_boff[NS]; i += kScrThreads) sBall[i] = 0.f;   // incl. the zero padding of every row
+        auto stage_part = [&](int part, int buf) {
+            for (int sc = 0; sc < NS; sc++) {
+                const MsScale &S = J.sc[sc];
+                const int r0 = s_rng[sc][0], c0 = s_rng[sc][2];
+                const int nrows = s_rng[sc][1] - r0 + 1, ncols = s_rng[sc][3] - c0 + 1;
+                float *sB = sBall + buf * s_boff[NS] + s_boff[sc];
+                const int bp = ncols + KWX;
+                for (int i = tid; i < nrows * ncols; i += kScrThreads) {
+                    const int r = i / ncols, c = i - r * ncols;
+                    cp_async4(sB + r * bp + c, S.heat + ((size_t)(r0 + r) * S.w + c0 + c) * kHeatC + part);
+                }
+            }
+        };
+        __syncthreads();                                        // zero fill done before the first copies land
+        stage_part(__ffs(E.parts) - 1, 0);
+        int buf = 0;
+      for (unsigned pm = E.parts; pm; pm &= pm - 1, buf ^= 1) {
+        const int part = __ffs(pm) - 1;
+        const float A = act_A[(size_t)E.slot * kParts + part];
+        cp_async_wait_all();
+        __syncthreads();                                        // this part's blob values landed; previous sT / sS are free
+        if (pm & (pm - 1)) stage_part(__ffs(pm & (pm - 1)) - 1, buf ^ 1);
+        // ---- horizontal passes: T_s[i][col] = sum_j Kx_s[col][j] * B_s[i][lox+j] ----
         for (int sc = 0; sc < NS; sc++) {
             const int c0 = s_rng[sc][2];
             const int nrows = s_rng[sc][1] - s_rng[sc][0] + 1, ncols = s_rng[sc][3] - c0 + 1;
-            const float *sB = sBall + s_boff[sc];
+            const float *sB = sBall + buf * s_boff[NS] + s_boff[sc];
             float *sT = sTall + s_toff[sc];
-            const float4 *kx4 = reinterpret_cast<const float4 *>(sKxAll + ((size_t)sc * kScrCols + col) * kMsKW);
-            float kxw[kMsKW];
+            const float *kx = sKxAll + ((size_t)sc * kScrCols + col) * KWX;
+            float kxw[KWX];
 #pragma unroll
-            for (int j4 = 0; j4 < kMsKW / 4; j4++) {
-                const float4 v = kx4[j4];
-                kxw[4 * j4] = v.x; kxw[4 * j4 + 1] = v.y; kxw[4 * j4 + 2] = v.z; kxw[4 * j4 + 3] = v.w;
-            }
-            const int off = mylox[sc] - c0;
+            for (int j = 0; j < KWX; j++) kxw[j] = kx[j];
+            const int off = mylox[sc] - c0, bp = ncols + KWX;
             for (int i = half; i < nrows; i += 2) {
-                const float *b = sB + ((size_t)i * ncols + off) * kHeatC + part;
+                const float *b = sB + i * bp + off;
                 float acc = 0.f;
 #pragma unroll
-                for (int j = 0; j < kMsKW; j++)
-                    if (off + j < ncols) acc = fmaf(kxw[j], b[j * kHeatC], acc);
+                for (int j = 0; j < KWX; j++) acc = fmaf(kxw[j], b[j], acc);   // beyond the region: zero x zero padding
                 sT[i * kScrCols + col] = acc;
             }
         }
         __syncthreads();
-        // ---- vertical passes, accumulated over the scales ----
-        float acc[kScrRows / 2];
+        // ---- vertical passes, accumulated over the scales: S[r][col] = sum_s sum_i Ky_s[r][i] * T_s[i][col] ----
+        {
+            float acc[kScrRows / 2];
 #pragma unroll
-        for (int q = 0; q < kScrRows / 2; q++) acc[q] = 0.f;
-        for (int sc = 0; sc < NS; sc++) {
-            const int nrows = s_rng[sc][1] - s_rng[sc][0] + 1;
-            const float *sT = sTall + s_toff[sc];
-            const float *sKy = sKyAll + sc * kScrRows * kMsMaxRows;
-            if (nrows <= 8) ms_vertical<8>(sT, sKy, col, half, nrows, acc);
-            else if (nrows <= 16) ms_vertical<16>(sT, sKy, col, half, nrows, acc);
-            else ms_vertical<kMsMaxRows>(sT, sKy, col, half, nrows, acc);
+            for (int q = 0; q < kScrRows / 2; q++) acc[q] = 0.f;
+            for (int sc = 0; sc < NS; sc++) {
+                const int nrows = s_rng[sc][1] - s_rng[sc][0] + 1;
+                const float *sT = sTall + s_toff[sc];
+                const float *sKy = sKyAll + sc * kScrRows * MAXROWS;
+                if (MAXROWS > 16 && nrows > 16) ms_vertical<MAXROWS, MAXROWS>(sT, sKy, col, half, nrows, acc);
+                else if (nrows > 8) ms_vertical<16, MAXROWS>(sT, sKy, col, half, nrows, acc);
+                else ms_vertical<8, MAXROWS>(sT, sKy, col, half, nrows, acc);
+            }
+#pragma unroll
+            for (int q = 0; q < kScrRows / 2; q++) sS[(half * (kScrRows / 2) + q) * kScrCols + col] = acc[q];
         }
-#pragma unroll
-        for (int q = 0; q < kScrRows / 2; q++) sS[(half * (kScrRows / 2) + q) * kScrCols + col] = acc[q];
         __syncthreads();
-        // ---- conservative 4-neighbour test on the interior ----
+        // ---- conservative 4-neighbour test on the interior (most rows of a tile hold nothing above thre1:
+        //      one shared-memory read, one compare and one vote per row then) ----
+        const float delta = kScreenDelta * A;
         const float lim = thre1 - delta, d2 = 2.f * delta;
+#pragma unroll 1
         for (int q = 0; q < kScrTH / 2; q++) {
             const int r = 1 + half * (kScrTH / 2) + q;
-            const int y = y0 + r - 1, x = x0 + col - 1;
+            const int y = y0 + r - 1;
+            const float sv = sS[r * kScrCols + col];
+            const bool hot = col_ok && y < H && sv > lim;
+            if (!__any_sync(0xffffffffu, hot)) continue;
             bool cand = false;
-            if (col >= 1 && col <= kScrTW && y < H && x < W) {
-                const float sv = sS[r * kScrCols + col];
-                if (sv > lim) {
-                    const float up = (y > 0) ? sS[(r - 1) * kScrCols + col] : 0.f;
-                    const float dn = (y < H - 1) ? sS[(r + 1) * kScrCols + col] : 0.f;
-                    const float lf = (x > 0) ? sS[r * kScrCols + col - 1] : 0.f;
-                    const float rt = (x < W - 1) ? sS[r * kScrCols + col + 1] : 0.f;
-                    cand = (sv >= up - d2) && (sv >= dn - d2) && (sv >= lf - d2) && (sv >= rt - d2);
-                }
+            if (hot) {
+                const float up = (y > 0) ? sS[(r - 1) * kScrCols + col] : 0.f;
+                const float dn = (y < H - 1) ? sS[(r + 1) * kScrCols + col] : 0.f;
+                const float lf = (x > 0) ? sS[r * kScrCols + col - 1] : 0.f;
+                const float rt = (x < W - 1) ? sS[r * kScrCols + col + 1] : 0.f;
+                cand = (sv >= up - d2) && (sv >= dn - d2) && (sv >= lf - d2) && (sv >= rt - d2);
             }
             const unsigned bal = __ballot_sync(0xffffffffu, cand);
             if (bal) {
@@ -799,6 +747,7 @@ __global__ void __launch_bounds__(kScrThreads) k_heat_screen_ms(const __grid_con
                 }
             }
         }
+      }   // parts of the item
     }
 }
 
@@ -1251,12 +1200,14 @@ struct FramePlan {
 };
 
 static size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+constexpr int kActCap = 1 << 15;   // work items per kernel variant and chunk (0.5 MB + 2.3 MB of bounds each)
 
 static int ceil_div_d(double a) { return (int)ceil(a - 1e-9); }
 
-static size_t screen_smem_bytes(int nrows_b, int ncols_b) {
-    return ((size_t)((nrows_b * ncols_b * kHeatC + 3) & ~3) + (size_t)nrows_b * kScrCols + (size_t)kScrRows * kScrCols +
-            (size_t)kScrRows * kScrMaxSrcRows) * 4;
+// dynamic shared memory of k_screen_pairs<KWX, MAXROWS> for one scale's share
+static size_t pairs_smem_scale(int nrows_b, int ncols_b, int kwx_t, int maxrows_t) {
+    return (2 * (size_t)((nrows_b * (ncols_b + kwx_t) + 3) & ~3) + (size_t)nrows_b * kScrCols + (size_t)kScrRows * maxrows_t +
+            (size_t)kScrCols * kwx_t) * 4;
 }
 
 static FramePlan plan_frame(const RmpeFrameDesc &f, int stride, bool allow_screen = true) {
@@ -1267,7 +1218,7 @@ static FramePlan plan_frame(const RmpeFrameDesc &f, int stride, bool allow_scree
     // composite operator supports: a 25-tap window of destination pixels spans 24*mid/dst pixels of the
     // (cropped) x-stride map, i.e. (that + 5)/stride blob cells, plus the taps of one more bicubic
     bool ok = allow_screen && !off;
-    size_t smem_ms = (size_t)kScrRows * kScrCols * 4;
+    size_t smem = (size_t)kScrRows * kScrCols * 4;     // sS
     for (int s = 0; s < f.n_scales && ok; s++) {
         const int h = f.grid_h[s], w = f.grid_w[s];
         // Support of one operator row.  25 destination taps span 24*scale source pixels, floor() of positions
@@ -1285,17 +1236,17 @@ static FramePlan plan_frame(const RmpeFrameDesc &f, int stride, bool allow_scree
         // a tile's 34 rows / 128 columns move the first source index by at most ceil(33 h/H) + 1
         p.nrows_b[s] = std::min(h, ceil_div_d((double)(kScrRows - 1) * h / f.height) + 1 + p.kwy[s]);
         p.ncols_b[s] = std::min(w, ceil_div_d((double)(kScrCols - 1) * w / f.width) + 1 + p.kwx[s]);
-        p.tab_elems += (size_t)f.height * (p.kwy[s] + 1) + (size_t)f.width * (p.kwx[s] + 1);
+        p.tab_elems += (size_t)f.height * (p.kwy[s] + 1) + (size_t)f.width * (p.kwx[s] + 1) + 4;   // + row masses
         if (!p.multi) {
-            ok = p.kwy[s] <= 24 && p.kwx[s] <= kScrMaxKW && p.nrows_b[s] <= kScrMaxSrcRows && p.ncols_b[s] <= 64;
-            p.smem = screen_smem_bytes(p.nrows_b[s], p.ncols_b[s]);
+            ok = p.kwy[s] <= 24 && p.kwx[s] <= kScrMaxKW && p.nrows_b[s] <= kScrMaxSrcRows;
+            smem += pairs_smem_scale(p.nrows_b[s], p.ncols_b[s], p.kwx[s] <= 10 ? 10 : kScrMaxKW, kScrMaxSrcRows);
         } else {
             ok = p.kwy[s] <= 24 && p.kwx[s] <= kMsKW && p.nrows_b[s] <= kMsMaxRows;
-            smem_ms += ((size_t)((p.nrows_b[s] * p.ncols_b[s] * kHeatC + 3) & ~3) + (size_t)p.nrows_b[s] * kScrCols +
-                        (size_t)kScrRows * kMsMaxRows + (size_t)kScrCols * kMsKW) * 4;
+            smem += pairs_smem_scale(p.nrows_b[s], p.ncols_b[s], kMsKW, kMsMaxRows);
         }
     }
-    if (p.multi) { p.smem = smem_ms; ok = ok && smem_ms <= 224 * 1024; }
+    p.smem = smem;
+    ok = ok && smem <= 160 * 1024;
     p.screen = ok;
     if (p.screen) {
         p.u_elems = 0;
@@ -1322,7 +1273,8 @@ static size_t fixed_ws_bytes(int batch, int max_peaks, int max_cand) {
     return al256(per_list * 4) /*raw_key*/ + al256(per_list * 8) /*raw_score*/ + al256((size_t)batch * kParts * 4) /*raw_count*/ +
            al256(per_list * 4) * 2 /*pk_x, pk_y*/ + al256(per_list * 8) /*pk_s*/ +
            al256((size_t)batch * kLimbs * max_cand * 4 * 8) /*ws_cand*/ +
-           al256(per_list * 2 * 4) * 2 /*cand_key, cand_fp*/ + 256 /*cand_count, tab_err*/ + 4096;
+           al256(per_list * 2 * 4) * 2 /*cand_key, cand_fp*/ + 256 /*cand_count, tab_err*/ +
+           al256((size_t)3 * kActCap * sizeof(ActEntry)) + al256((size_t)3 * kActCap * kParts * 4) /*work items*/ + 4096;
 }
 
 static bool frame_ok(const RmpeFrameDesc &f, int stride) {
@@ -1429,11 +1381,9 @@ static int ensure_smooth_attr() {
                                        kMaxCandCap * 12 + 2 * kMaxPeaksCap));
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(((kMaxSubsetCap + 1) * 20 + kAsmConnRows * 3 + kParts * kMaxPeaksCap) * 8)));
-    RMPE_CUDA_TRY(cudaFuncSetAttribute(k_heat_screen_ms, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    RMPE_CUDA_TRY(cudaFuncSetAttribute(k_heat_screen<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)screen_smem_bytes(kScrMaxSrcRows, 64)));
-    RMPE_CUDA_TRY(cudaFuncSetAttribute(k_heat_screen<kScrMaxKW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)screen_smem_bytes(kScrMaxSrcRows, 64)));
+    RMPE_CUDA_TRY(cudaFuncSetAttribute(k_screen_pairs<10, kScrMaxSrcRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    RMPE_CUDA_TRY(cudaFuncSetAttribute(k_screen_pairs<kScrMaxKW, kScrMaxSrcRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    RMPE_CUDA_TRY(cudaFuncSetAttribute(k_screen_pairs<kMsKW, kMsMaxRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     done = true;
     return RMPE_OK;
 }
@@ -1487,8 +1437,11 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
     double *ws_cand = (double *)take((size_t)B * kLimbs * MC * 4 * 8);
     int32_t *cand_key = (int32_t *)take(per_list * 2 * 4);
     int32_t *cand_fp = (int32_t *)take(per_list * 2 * 4);
-    int32_t *cand_count = (int32_t *)take(256);
-    int32_t *tab_err = cand_count + 1;
+    int32_t *cand_count = (int32_t *)take(256);      // [0] candidates, [1..3] work items per kernel variant, [8] table error
+    int32_t *tab_err = cand_count + 8;
+    const int act_cap = kActCap;
+    ActEntry *act = (ActEntry *)take((size_t)3 * kActCap * sizeof(ActEntry));
+    float *act_A = (float *)take((size_t)3 * kActCap * kParts * sizeof(float));
     RMPE_REQUIRE(off <= b->workspace_bytes, "workspace too small (see rmpe_decode_workspace_bytes)");
     const size_t frame_ws0 = off;
 
@@ -1528,12 +1481,12 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
         if (any_screen) {
             // ---- screen in float32 straight from the blobs, decide exactly per surviving pixel ----
             AxisJobs aj{};
-            ScreenJobs sj{};
-            std::vector<MsJob> msj;
-            int m = 0, n_tab = 0, max_tiles = 0, max_len = 0, nr = 0, nc = 0, kwx_max = 0;
-            size_t ms_smem = 0;
+            MsJobs jobs1{}, jobs2{}, jobsM{};      // single scale (Kx <= 10 / <= 12 wide), multi scale
+            int n1 = 0, n2 = 0, nM = 0, t1 = 0, t2 = 0, tM = 0;
+            size_t sm1 = 0, sm2 = 0, smM = 0;
+            int n_tab = 0, max_len = 0;
             const int cand_cap = (int)std::min<size_t>(per_list * 2, (size_t)n * kParts * MP * 2);
-            if (f0 > 0) RMPE_CUDA_TRY(cudaMemsetAsync(cand_count, 0, 4, st));
+            if (f0 > 0) RMPE_CUDA_TRY(cudaMemsetAsync(cand_count, 0, 16, st));
             const bool reuse_tables = (b->flags & RMPE_DECODE_REUSE_TABLES) != 0;
             auto flush_tables = [&]() {
                 if (!n_tab) return;
@@ -1560,66 +1513,71 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                     max_len = std::max(max_len, want.dst);
                 };
                 uint8_t *tp = u_ptr[i];
+                if (!reuse_tables) RMPE_CUDA_TRY(cudaMemsetAsync(tp, 0, p.bytes, st));   // row-mass maxima start at 0
                 MsJob mj{};
                 for (int sI = 0; sI < f.n_scales; sI++) {
                     float *Ky = (float *)tp; tp += (size_t)f.height * p.kwy[sI] * 4;
-                    int *loy = (int *)tp; tp += (size_t)f.height * 4;
+                    int *loy = (int *)tp; tp += (size_t)(f.height + 2) * 4;
                     float *Kx = (float *)tp; tp += (size_t)f.width * p.kwx[sI] * 4;
-                    int *lox = (int *)tp; tp += (size_t)f.width * 4;
+                    int *lox = (int *)tp; tp += (size_t)(f.width + 2) * 4;
                     const int h = f.grid_h[sI], w = f.grid_w[sI];
                     if (!p.multi) {
                         table(AxisJob{f.height, h, p.kwy[sI], 0, 1, 1.0f, nullptr, nullptr}, Ky, loy);
                         table(AxisJob{f.width, w, p.kwx[sI], 0, 1, 1.0f, nullptr, nullptr}, Kx, lox);
-                        ScreenJob &J = sj.j[m];
-                        J.heat = b->heat + f.heat_offset[0];
-                        J.Ky = Ky; J.Kx = Kx; J.loy = loy; J.lox = lox;
-                        J.H = f.height; J.W = f.width; J.h = h; J.w = w; J.kwy = p.kwy[0]; J.kwx = p.kwx[0];
-                        J.frame = f0 + i;
-                        J.tiles_x = (f.width + kScrTW - 1) / kScrTW;
-                        J.tiles = J.tiles_x * ((f.height + kScrTH - 1) / kScrTH);
-                        max_tiles = std::max(max_tiles, J.tiles);
-                        nr = std::max(nr, p.nrows_b[0]); nc = std::max(nc, p.ncols_b[0]); kwx_max = std::max(kwx_max, p.kwx[0]);
-                        m++;
                     } else {
                         table(AxisJob{f.height, h, p.kwy[sI], h * b->stride - f.pad_down[sI], b->stride,
                                       1.0f / (float)f.n_scales, nullptr, nullptr}, Ky, loy);
                         table(AxisJob{f.width, w, p.kwx[sI], w * b->stride - f.pad_right[sI], b->stride, 1.0f, nullptr, nullptr},
                               Kx, lox);
-                        mj.sc[sI] = MsScale{b->heat + f.heat_offset[sI], Ky, Kx, loy, lox, h, w, p.kwy[sI], p.kwx[sI]};
                     }
+                    mj.sc[sI] = MsScale{b->heat + f.heat_offset[sI], Ky, Kx, loy, lox, h, w, p.kwy[sI], p.kwx[sI]};
                 }
-                if (p.multi) {
-                    mj.H = f.height; mj.W = f.width; mj.n_scales = f.n_scales; mj.frame = f0 + i;
-                    mj.tiles_x = (f.width + kScrTW - 1) / kScrTW;
-                    mj.tiles = mj.tiles_x * ((f.height + kScrTH - 1) / kScrTH);
-                    ms_smem = std::max(ms_smem, p.smem);
-                    msj.push_back(mj);
-                }
+                mj.H = f.height; mj.W = f.width; mj.n_scales = f.n_scales; mj.frame = f0 + i;
+                mj.tiles_x = (f.width + kScrTW - 1) / kScrTW;
+                mj.tiles = mj.tiles_x * ((f.height + kScrTH - 1) / kScrTH);
+                if (p.multi) { jobsM.j[nM++] = mj; tM = std::max(tM, mj.tiles); smM = std::max(smM, p.smem); }
+                else if (p.kwx[0] <= 10) { jobs1.j[n1++] = mj; t1 = std::max(t1, mj.tiles); sm1 = std::max(sm1, p.smem); }
+                else { jobs2.j[n2++] = mj; t2 = std::max(t2, mj.tiles); sm2 = std::max(sm2, p.smem); }
             }
             flush_tables();
-            if (m) {
-                ProfScope ps("k_heat_screen", st);
-                const size_t smem = screen_smem_bytes(nr, nc);
-                if (kwx_max <= 10)
-                    k_heat_screen<10><<<dim3(max_tiles, m), kScrThreads, smem, st>>>(sj, (float)b->thre1, cand_cap, cand_key,
-                                                                                  cand_fp, cand_count, tab_err, b->status);
-                else
-                    k_heat_screen<kScrMaxKW><<<dim3(max_tiles, m), kScrThreads, smem, st>>>(
-                        sj, (float)b->thre1, cand_cap, cand_key, cand_fp, cand_count, tab_err, b->status);
-                count_launch();
-            }
-            for (size_t q0 = 0; q0 < msj.size(); q0 += kMsJobsPerLaunch) {
-                MsJobs mjs{};
-                int mm = 0, mt = 0;
-                for (size_t q = q0; q < msj.size() && mm < kMsJobsPerLaunch; q++) { mjs.j[mm++] = msj[q]; mt = std::max(mt, msj[q].tiles); }
-                ProfScope ps("k_heat_screen_ms", st);
-                k_heat_screen_ms<<<dim3(mt, mm), kScrThreads, ms_smem, st>>>(mjs, (float)b->thre1, cand_cap, cand_key, cand_fp,
-                                                                          cand_count, tab_err, b->status);
-                count_launch();
-            }
+            // plan (which (tile, part) pairs can hold a peak) + pairs (screen them), per kernel variant
+            const int sms = tables().sm_count;
+            auto screen = [&](const MsJobs &jobs, int nj, int mt, size_t smem, int variant, int slot) -> int {
+                if (!nj) return RMPE_OK;
+                int32_t *cnt = cand_count + 1 + slot;      // this variant's work-item counter (zeroed with cand_count)
+                ActEntry *lst = act + (size_t)slot * act_cap;
+                float *lstA = act_A + (size_t)slot * act_cap * kParts;
+                // parts per work item: single-scale items are cheap to set up (balance first), multi-scale items
+                // stage the operators of four scales (amortise them over all active parts of the tile)
+                const int group = (variant == 2) ? kParts : 2;
+                {
+                    ProfScope ps("k_screen_plan", st);
+                    k_screen_plan<<<dim3(mt, nj), kPlanThreads, 0, st>>>(jobs, (float)b->thre1, act_cap, group, lst, lstA, cnt, tab_err,
+                                                                       b->status);
+                }
+                {
+                    ProfScope ps("k_screen_pairs", st);
+                    const int per_sm = std::max(1, std::min(6, (int)((200 * 1024) / std::max<size_t>(smem, 1))));
+                    const int grid = sms * per_sm;
+                    if (variant == 0)
+                        k_screen_pairs<10, kScrMaxSrcRows><<<grid, kScrThreads, smem, st>>>(
+                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, cand_cap, cand_key, cand_fp, cand_count, b->status);
+                    else if (variant == 1)
+                        k_screen_pairs<kScrMaxKW, kScrMaxSrcRows><<<grid, kScrThreads, smem, st>>>(
+                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, cand_cap, cand_key, cand_fp, cand_count, b->status);
+                    else
+                        k_screen_pairs<kMsKW, kMsMaxRows><<<grid, kScrThreads, smem, st>>>(
+                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, cand_cap, cand_key, cand_fp, cand_count, b->status);
+                }
+                count_launch(2);
+                return RMPE_OK;
+            };
+            screen(jobs1, n1, t1, sm1, 0, 0);
+            screen(jobs2, n2, t2, sm2, 1, 1);
+            screen(jobsM, nM, tM, smM, 2, 2);
             {
                 ProfScope ps("k_peak_verify", st);
-                const int grid = std::min(cand_cap, 8 * tables().sm_count);
+                const int grid = std::min(cand_cap, 8 * sms);
                 k_peak_verify<<<grid, kVerThreads, 0, st>>>(b->frames, b->heat, b->stride, b->thre1, cand_cap, cand_key, cand_fp,
                                                            cand_count, MP, raw_key, raw_score, raw_count, b->status);
                 count_launch();
