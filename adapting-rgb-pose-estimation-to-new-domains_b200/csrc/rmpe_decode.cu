@@ -905,6 +905,8 @@ __global__ void __launch_bounds__(256) k_peaks_finalize(const __grid_constant__ 
 // (bitonic on (score desc, generation index asc)), greedy one-to-one pick.
 // ------------------------------------------------------------------------------------------
 constexpr int kLimbThreads = 256;
+constexpr int kLimbPairs = 12;     // pairs per pass: 12 x 10 sample points x 2 channels = 240 threads
+constexpr int kLimbFineMax = 96;   // above this many pairs per limb a thread per pair hides the latency by itself
 
 __global__ void __launch_bounds__(kLimbThreads) k_limbs(const RmpeFrameDesc *__restrict__ frames, int first_frame,
                                                         const float *__restrict__ paf, int stride, double thre2,
@@ -929,7 +931,6 @@ __global__ void __launch_bounds__(kLimbThreads) k_limbs(const RmpeFrameDesc *__r
     // candidate rows (i, j, score, score + sA + sB) in generation order
     double *cand = (limb_cand ? limb_cand : ws_cand) + ((size_t)frame * kLimbs + k) * max_cand * 4;
 
-    __shared__ int s_warp_cnt[kLimbThreads / 32];
     __shared__ int s_total;
     extern __shared__ __align__(16) uint8_t sm_raw[];
     double *s_score = reinterpret_cast<double *>(sm_raw);          // [npow]
@@ -939,8 +940,82 @@ __global__ void __launch_bounds__(kLimbThreads) k_limbs(const RmpeFrameDesc *__r
     if (tid == 0) s_total = 0;
     __syncthreads();
 
+    // Pairs in (i-major, j-minor) order, kLimbPairs at a time.  Phase 1 spreads the 10 sample points x 2 PAF
+    // channels of every pair over the CTA (the PAF value of a point is a chain of dependent global loads: with one
+    // thread per pair a frame with 3 persons kept 9 threads busy); phase 2 sums them per pair in the reference's
+    // order, applies the criteria and compacts in order.
     const int total = nA * nB;
     const double halfH = __dmul_rn(0.5, (double)f.height);
+    __shared__ double s_val[kLimbPairs][10][2];
+    __shared__ int s_warp_cnt[kLimbThreads / 32];
+    if (total <= kLimbFineMax) {
+    for (int base = 0; base < total; base += kLimbPairs) {
+        if (tid < kLimbPairs * 20) {
+            const int p = tid / 20, rem = tid - p * 20, I = rem >> 1, ch = rem & 1;
+            const int idx = base + p;
+            if (idx < total) {
+                const int i = idx / nB, j = idx - i * nB;
+                const int ax = pk_x[tA + i], ay = pk_y[tA + i], bx = pk_x[tB + j], by = pk_y[tB + j];
+                const int vx = bx - ax, vy = by - ay;
+                double v = 0.0;
+                if (vx != 0 || vy != 0) {
+                    // np.linspace(a, b, 10): step = (b-a)/9; p_I = I*step + a, p_9 = b
+                    const double stepx = __ddiv_rn((double)vx, 9.0), stepy = __ddiv_rn((double)vy, 9.0);
+                    const double px = (I == 9) ? (double)bx : __dadd_rn(__dmul_rn((double)I, stepx), (double)ax);
+                    const double py = (I == 9) ? (double)by : __dadd_rn(__dmul_rn((double)I, stepy), (double)ay);
+                    const int xi = __double2int_rn(px), yi = __double2int_rn(py);   // round half to even
+                    v = paf_point(f, paf, stride, pc + ch, yi, xi);
+                }
+                s_val[p][I][ch] = v;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const int idx = base + lane;
+            bool pass = false;
+            double score = 0.0, score2 = 0.0;
+            int i = 0, j = 0;
+            if (lane < kLimbPairs && idx < total) {
+                i = idx / nB; j = idx - i * nB;
+                const int ax = pk_x[tA + i], ay = pk_y[tA + i], bx = pk_x[tB + j], by = pk_y[tB + j];
+                const int vx = bx - ax, vy = by - ay;
+                const double norm = __dsqrt_rn((double)(vx * vx + vy * vy));
+                if (norm != 0.0) {
+                    const double ux = __ddiv_rn((double)vx, norm), uy = __ddiv_rn((double)vy, norm);
+                    double sum = 0.0;
+                    int nok = 0;
+#pragma unroll 1
+                    for (int I = 0; I < 10; I++) {
+                        const double sI = __dadd_rn(__dmul_rn(s_val[lane][I][0], ux), __dmul_rn(s_val[lane][I][1], uy));
+                        sum = __dadd_rn(sum, sI);
+                        nok += (sI > thre2) ? 1 : 0;
+                    }
+                    double prior = __dsub_rn(__ddiv_rn(halfH, norm), 1.0);
+                    prior = prior < 0.0 ? prior : 0.0;
+                    score = __dadd_rn(__ddiv_rn(sum, 10.0), prior);
+                    pass = (nok > 8) && (score > 0.0);
+                    score2 = __dadd_rn(__dadd_rn(score, pk_s[tA + i]), pk_s[tB + j]);
+                }
+            }
+            // ordered compaction
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            const int off = s_total;
+            if (pass) {
+                const int slot = off + __popc(bal & ((1u << lane) - 1));
+                if (slot < max_cand) {
+                    double *row = cand + (size_t)slot * 4;
+                    row[0] = (double)i; row[1] = (double)j; row[2] = score; row[3] = score2;
+                } else {
+                    atomicOr(status + frame, RMPE_ST_CAND_OVERFLOW);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) s_total = off + __popc(bal);
+        }
+        __syncthreads();
+    }
+    } else {
+    // many pairs (crowded scenes): one thread per pair, 256 pairs per pass -- enough independent chains per warp
     for (int base = 0; base < total; base += kLimbThreads) {
         int idx = base + tid;
         bool pass = false;
@@ -997,6 +1072,7 @@ __global__ void __launch_bounds__(kLimbThreads) k_limbs(const RmpeFrameDesc *__r
             s_total = t;
         }
         __syncthreads();
+    }
     }
     const int nc = min(s_total, max_cand);
     if (tid == 0 && n_limb_cand) n_limb_cand[frame * kLimbs + k] = nc;
