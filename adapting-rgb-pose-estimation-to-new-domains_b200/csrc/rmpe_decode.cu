@@ -345,6 +345,8 @@ constexpr int kScrMaxSrcRows = 16;   // single scale: staged blob rows per tile 
 constexpr int kScrMaxKW = 12;        // single scale: non-zeros per row of Kx (a 10-wide variant covers stride 8)
 constexpr int kMsKW = 12;            // multi scale: non-zeros per row of Kx_s
 constexpr int kMsMaxRows = 24;       // multi scale: staged blob rows per scale and tile
+constexpr int kMsKWBig = 16;         // small frames (scale 2 of a 240-row image is up-sampled by only 2.6): wider variant
+constexpr int kMsMaxRowsBig = 32;
 
 struct AxisJob {
     int dst, src, kw;
@@ -754,6 +756,7 @@ __global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_const
 // one CTA per screened pixel: exact S at the pixel and its four neighbours
 constexpr int kVerThreads = 128;
 constexpr int kVerN = 2 * kSR + 3;   // 27: the pixel +-1, +-12
+constexpr int kVerI1Cap = 64 * 64;   // cached x-stride rectangle (floats); larger ones are evaluated point by point
 
 // heat value of the (scale-averaged) up-sampled map at an integer point, the reference's arithmetic
 __device__ inline double heat_point(const RmpeFrameDesc &f, const float *__restrict__ heat, int stride, int c, int y,
@@ -783,6 +786,10 @@ __global__ void __launch_bounds__(kVerThreads) k_peak_verify(const RmpeFrameDesc
     __shared__ double sU[kVerN][kVerN + 1];
     __shared__ double sA[3][kVerN + 1];
     __shared__ double sS5[5];
+    __shared__ float sI1[kVerI1Cap];               // multi scale: rectangle of the x-stride map under the neighbourhood
+    __shared__ int s_tap0[2][kVerN];               // first tap of the second resize per row / column
+    __shared__ float s_tapc[2][kVerN][4];          // its coefficients
+    __shared__ int s_box[4];
     const int total = min(*cand_count, cand_cap);
     const int tid = threadIdx.x;
     for (int ci = blockIdx.x; ci < total; ci += gridDim.x) {
@@ -793,9 +800,72 @@ __global__ void __launch_bounds__(kVerThreads) k_peak_verify(const RmpeFrameDesc
         const int y = key / W, x = key - y * W;
         const bool f32map = f.n_scales == 1;
         // U on the 27x27 reflected neighbourhood
-        for (int i = tid; i < kVerN * kVerN; i += kVerThreads) {
-            const int a = i / kVerN, b = i - a * kVerN;
-            sU[a][b] = heat_point(f, heat, stride, part, reflect_idx(y - kSR - 1 + a, H), reflect_idx(x - kSR - 1 + b, W));
+        if (f32map) {
+            for (int i = tid; i < kVerN * kVerN; i += kVerThreads) {
+                const int a = i / kVerN, b = i - a * kVerN;
+                sU[a][b] = heat_point(f, heat, stride, part, reflect_idx(y - kSR - 1 + a, H), reflect_idx(x - kSR - 1 + b, W));
+            }
+        } else {
+            // multi scale: U = sum_s f64(chain_s / n).  The 729 points of one scale share the x-stride map they are
+            // resized from: its needed rectangle is evaluated once into shared memory (same operations as
+            // resize_chain_point, each intermediate value computed once instead of up to 16 times).
+            for (int i = tid; i < kVerN * kVerN; i += kVerThreads) sU[i / kVerN][i % kVerN] = 0.0;
+            for (int sI = 0; sI < f.n_scales; sI++) {
+                const int hs = f.grid_h[sI], ws = f.grid_w[sI];
+                const int Hc = hs * stride - f.pad_down[sI], Wc = ws * stride - f.pad_right[sI];
+                const float *blob = heat + f.heat_offset[sI];
+                __syncthreads();
+                if (tid < 2 * kVerN) {          // second-resize taps of the 27 rows / 27 columns
+                    const bool isrow = tid < kVerN;
+                    const int a = isrow ? tid : tid - kVerN;
+                    float co[4];
+                    const int g = isrow ? reflect_idx(y - kSR - 1 + a, H) : reflect_idx(x - kSR - 1 + a, W);
+                    const int s0 = isrow ? resize_axis(g, resize_scale(H, Hc, 0.0), co) : resize_axis(g, resize_scale(W, Wc, 0.0), co);
+                    s_tap0[isrow ? 0 : 1][a] = s0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) s_tapc[isrow ? 0 : 1][a][k] = co[k];
+                }
+                if (tid == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MIN; s_box[2] = INT_MAX; s_box[3] = INT_MIN; }
+                __syncthreads();
+                if (tid < 2 * kVerN) {
+                    const bool isrow = tid < kVerN;
+                    const int a = isrow ? tid : tid - kVerN, lim = (isrow ? Hc : Wc) - 1;
+                    const int s0 = s_tap0[isrow ? 0 : 1][a];
+                    atomicMin(&s_box[isrow ? 0 : 2], clampi(s0 - 1, 0, lim));
+                    atomicMax(&s_box[isrow ? 1 : 3], clampi(s0 + 2, 0, lim));
+                }
+                __syncthreads();
+                const int r0 = s_box[0], q0 = s_box[2];
+                const int nr = s_box[1] - r0 + 1, nq = s_box[3] - q0 + 1;
+                const bool cached = nr * nq <= kVerI1Cap;
+                if (cached)
+                    for (int i = tid; i < nr * nq; i += kVerThreads) {
+                        const int r = i / nq, q = i - r * nq;
+                        sI1[i] = resize_point_blob(blob, hs, ws, kHeatC, part, r0 + r, q0 + q, hs * stride, ws * stride, (double)stride);
+                    }
+                __syncthreads();
+                for (int i = tid; i < kVerN * kVerN; i += kVerThreads) {
+                    const int a = i / kVerN, b = i - a * kVerN;
+                    float v;
+                    if (cached) {
+                        const int sy = s_tap0[0][a], sx = s_tap0[1][b];
+                        float hp[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float *row = sI1 + (clampi(sy - 1 + j, 0, Hc - 1) - r0) * nq - q0;
+                            hp[j] = tap_ltr(row[clampi(sx - 1, 0, Wc - 1)], row[clampi(sx, 0, Wc - 1)], row[clampi(sx + 1, 0, Wc - 1)],
+                                            row[clampi(sx + 2, 0, Wc - 1)], s_tapc[1][b]);
+                        }
+                        const int xg = reflect_idx(x - kSR - 1 + b, W);
+                        v = in_row_tail(xg, part, W, kHeatC) ? tap_ltr(hp[0], hp[1], hp[2], hp[3], s_tapc[0][a])
+                                                             : tap_rtl(hp[0], hp[1], hp[2], hp[3], s_tapc[0][a]);
+                    } else {
+                        v = resize_chain_point(blob, hs, ws, kHeatC, part, reflect_idx(y - kSR - 1 + a, H),
+                                               reflect_idx(x - kSR - 1 + b, W), H, W, Hc, Wc, stride);
+                    }
+                    sU[a][b] = __dadd_rn(sU[a][b], (double)__fdiv_rn(v, (float)f.n_scales));
+                }
+            }
         }
         __syncthreads();
         // axis 0 on rows y-1, y, y+1 (scipy order, f64 accumulate, store in the map dtype)
@@ -1265,6 +1335,7 @@ struct FramePlan {
     bool screen;         // frame decoded through k_heat_screen[_ms] / k_peak_verify
     int kwy[RMPE_MAX_SCALES], kwx[RMPE_MAX_SCALES];          // non-zeros per row of the composite operators
     int nrows_b[RMPE_MAX_SCALES], ncols_b[RMPE_MAX_SCALES];  // bounds on the staged blob region of a screening tile
+    bool big;            // multi scale: needs the wider k_screen_pairs variant
     size_t tab_elems;    // 4-byte elements of the frame's operator tables
     size_t smem;         // dynamic shared memory of its screening kernel
     bool multi;
@@ -1317,10 +1388,13 @@ static FramePlan plan_frame(const RmpeFrameDesc &f, int stride, bool allow_scree
             ok = p.kwy[s] <= 24 && p.kwx[s] <= kScrMaxKW && p.nrows_b[s] <= kScrMaxSrcRows;
             smem += pairs_smem_scale(p.nrows_b[s], p.ncols_b[s], p.kwx[s] <= 10 ? 10 : kScrMaxKW, kScrMaxSrcRows);
         } else {
-            ok = p.kwy[s] <= 24 && p.kwx[s] <= kMsKW && p.nrows_b[s] <= kMsMaxRows;
-            smem += pairs_smem_scale(p.nrows_b[s], p.ncols_b[s], kMsKW, kMsMaxRows);
+            ok = p.kwy[s] <= 24 && p.kwx[s] <= kMsKWBig && p.nrows_b[s] <= kMsMaxRowsBig;
+            if (p.kwx[s] > kMsKW || p.nrows_b[s] > kMsMaxRows) p.big = true;
         }
     }
+    if (p.multi)
+        for (int s = 0; s < f.n_scales && ok; s++)
+            smem += pairs_smem_scale(p.nrows_b[s], p.ncols_b[s], p.big ? kMsKWBig : kMsKW, p.big ? kMsMaxRowsBig : kMsMaxRows);
     p.smem = smem;
     ok = ok && smem <= 160 * 1024;
     p.screen = ok;
@@ -1350,7 +1424,7 @@ static size_t fixed_ws_bytes(int batch, int max_peaks, int max_cand) {
            al256(per_list * 4) * 2 /*pk_x, pk_y*/ + al256(per_list * 8) /*pk_s*/ +
            al256((size_t)batch * kLimbs * max_cand * 4 * 8) /*ws_cand*/ +
            al256(per_list * 2 * 4) * 2 /*cand_key, cand_fp*/ + 256 /*cand_count, tab_err*/ +
-           al256((size_t)3 * kActCap * sizeof(ActEntry)) + al256((size_t)3 * kActCap * kParts * 4) /*work items*/ + 4096;
+           al256((size_t)4 * kActCap * sizeof(ActEntry)) + al256((size_t)4 * kActCap * kParts * 4) /*work items*/ + 4096;
 }
 
 static bool frame_ok(const RmpeFrameDesc &f, int stride) {
@@ -1460,6 +1534,7 @@ static int ensure_smooth_attr() {
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_screen_pairs<10, kScrMaxSrcRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_screen_pairs<kScrMaxKW, kScrMaxSrcRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_screen_pairs<kMsKW, kMsMaxRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    RMPE_CUDA_TRY(cudaFuncSetAttribute(k_screen_pairs<kMsKWBig, kMsMaxRowsBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     done = true;
     return RMPE_OK;
 }
@@ -1513,11 +1588,11 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
     double *ws_cand = (double *)take((size_t)B * kLimbs * MC * 4 * 8);
     int32_t *cand_key = (int32_t *)take(per_list * 2 * 4);
     int32_t *cand_fp = (int32_t *)take(per_list * 2 * 4);
-    int32_t *cand_count = (int32_t *)take(256);      // [0] candidates, [1..3] work items per kernel variant, [8] table error
+    int32_t *cand_count = (int32_t *)take(256);      // [0] candidates, [1..4] work items per kernel variant, [8] table error
     int32_t *tab_err = cand_count + 8;
     const int act_cap = kActCap;
-    ActEntry *act = (ActEntry *)take((size_t)3 * kActCap * sizeof(ActEntry));
-    float *act_A = (float *)take((size_t)3 * kActCap * kParts * sizeof(float));
+    ActEntry *act = (ActEntry *)take((size_t)4 * kActCap * sizeof(ActEntry));
+    float *act_A = (float *)take((size_t)4 * kActCap * kParts * sizeof(float));
     RMPE_REQUIRE(off <= b->workspace_bytes, "workspace too small (see rmpe_decode_workspace_bytes)");
     const size_t frame_ws0 = off;
 
@@ -1557,12 +1632,12 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
         if (any_screen) {
             // ---- screen in float32 straight from the blobs, decide exactly per surviving pixel ----
             AxisJobs aj{};
-            MsJobs jobs1{}, jobs2{}, jobsM{};      // single scale (Kx <= 10 / <= 12 wide), multi scale
-            int n1 = 0, n2 = 0, nM = 0, t1 = 0, t2 = 0, tM = 0;
-            size_t sm1 = 0, sm2 = 0, smM = 0;
+            MsJobs jobs1{}, jobs2{}, jobsM{}, jobsB{};      // single scale (Kx <= 10 / <= 12 wide), multi scale, multi scale wide
+            int n1 = 0, n2 = 0, nM = 0, nB = 0, t1 = 0, t2 = 0, tM = 0, tB = 0;
+            size_t sm1 = 0, sm2 = 0, smM = 0, smB = 0;
             int n_tab = 0, max_len = 0;
             const int cand_cap = (int)std::min<size_t>(per_list * 2, (size_t)n * kParts * MP * 2);
-            if (f0 > 0) RMPE_CUDA_TRY(cudaMemsetAsync(cand_count, 0, 16, st));
+            if (f0 > 0) RMPE_CUDA_TRY(cudaMemsetAsync(cand_count, 0, 20, st));
             const bool reuse_tables = (b->flags & RMPE_DECODE_REUSE_TABLES) != 0;
             auto flush_tables = [&]() {
                 if (!n_tab) return;
@@ -1611,7 +1686,8 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                 mj.H = f.height; mj.W = f.width; mj.n_scales = f.n_scales; mj.frame = f0 + i;
                 mj.tiles_x = (f.width + kScrTW - 1) / kScrTW;
                 mj.tiles = mj.tiles_x * ((f.height + kScrTH - 1) / kScrTH);
-                if (p.multi) { jobsM.j[nM++] = mj; tM = std::max(tM, mj.tiles); smM = std::max(smM, p.smem); }
+                if (p.multi && p.big) { jobsB.j[nB++] = mj; tB = std::max(tB, mj.tiles); smB = std::max(smB, p.smem); }
+                else if (p.multi) { jobsM.j[nM++] = mj; tM = std::max(tM, mj.tiles); smM = std::max(smM, p.smem); }
                 else if (p.kwx[0] <= 10) { jobs1.j[n1++] = mj; t1 = std::max(t1, mj.tiles); sm1 = std::max(sm1, p.smem); }
                 else { jobs2.j[n2++] = mj; t2 = std::max(t2, mj.tiles); sm2 = std::max(sm2, p.smem); }
             }
@@ -1625,7 +1701,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                 float *lstA = act_A + (size_t)slot * act_cap * kParts;
                 // parts per work item: single-scale items are cheap to set up (balance first), multi-scale items
                 // stage the operators of four scales (amortise them over all active parts of the tile)
-                const int group = (variant == 2) ? kParts : 2;
+                const int group = (variant >= 2) ? kParts : 2;
                 {
                     ProfScope ps("k_screen_plan", st);
                     k_screen_plan<<<dim3(mt, nj), kPlanThreads, 0, st>>>(jobs, (float)b->thre1, act_cap, group, lst, lstA, cnt, tab_err,
@@ -1633,7 +1709,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                 }
                 {
                     ProfScope ps("k_screen_pairs", st);
-                    const int per_sm = std::max(1, std::min(6, (int)((200 * 1024) / std::max<size_t>(smem, 1))));
+                    const int per_sm = std::max(1, std::min(6, (int)((224 * 1024) / (std::max<size_t>(smem, 1) + 2048))));   // + static smem / reserve
                     const int grid = sms * per_sm;
                     if (variant == 0)
                         k_screen_pairs<10, kScrMaxSrcRows><<<grid, kScrThreads, smem, st>>>(
@@ -1641,8 +1717,11 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                     else if (variant == 1)
                         k_screen_pairs<kScrMaxKW, kScrMaxSrcRows><<<grid, kScrThreads, smem, st>>>(
                             jobs, (float)b->thre1, act_cap, lst, lstA, cnt, cand_cap, cand_key, cand_fp, cand_count, b->status);
-                    else
+                    else if (variant == 2)
                         k_screen_pairs<kMsKW, kMsMaxRows><<<grid, kScrThreads, smem, st>>>(
+                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, cand_cap, cand_key, cand_fp, cand_count, b->status);
+                    else
+                        k_screen_pairs<kMsKWBig, kMsMaxRowsBig><<<grid, kScrThreads, smem, st>>>(
                             jobs, (float)b->thre1, act_cap, lst, lstA, cnt, cand_cap, cand_key, cand_fp, cand_count, b->status);
                 }
                 count_launch(2);
@@ -1651,6 +1730,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
             screen(jobs1, n1, t1, sm1, 0, 0);
             screen(jobs2, n2, t2, sm2, 1, 1);
             screen(jobsM, nM, tM, smM, 2, 2);
+            screen(jobsB, nB, tB, smB, 3, 3);
             {
                 ProfScope ps("k_peak_verify", st);
                 const int grid = std::min(cand_cap, 8 * sms);
