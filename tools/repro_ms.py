@@ -32,3 +32,15 @@ else:
     dp = rmpe_b200.batch.DecodeDevicePlan(frames)
     dp.run(); torch.cuda.synchronize()
     print("ok", [r["status"] for r in dp.results()])
+import time
+if not one:
+    for _ in range(3):
+        dp.run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        dp.run()
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print("host submit per call %.3f ms, total per call %.3f ms" % ((t1 - t0) / 20 * 1e3, (t2 - t0) / 20 * 1e3))
