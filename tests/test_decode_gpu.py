@@ -203,3 +203,23 @@ def test_mixed_screened_and_materialised_frames(rmpe):
         assert r["status"] == 0
         assert np.array_equal(r["candidate"], o[0]), c[0]
         assert np.array_equal(r["subset"], o[1]), c[0]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_frame_shapes(rmpe, seed):
+    """Odd frame sizes (tiles partly outside the frame, frames smaller than the Gaussian radius of a tile
+    ring, reflect/replicate borders inside the screening operators), single and multi scale, against the oracle."""
+    rng = np.random.RandomState(9000 + seed)
+    H, W = int(rng.randint(40, 420)), int(rng.randint(40, 520))
+    if seed == 0:
+        H, W = 33, 47            # smaller than one screening tile in both directions
+    if seed == 1:
+        H, W = 127, 253          # interior width of a tile + 1
+    P = int(rng.randint(1, 5))
+    multi = bool(seed % 2)
+    case = ("r%d" % seed, H, W, P, 500 + seed, multi)
+    o = _oracle(case, detail=False)
+    r = rmpe.batch.decode_batch_host([frames_of(case)])[0]
+    assert r["status"] == 0
+    assert np.array_equal(r["candidate"], o[0]), "%s: %d vs %d peaks" % (case, len(r["candidate"]), len(o[0]))
+    assert np.array_equal(r["subset"], o[1])
