@@ -223,3 +223,38 @@ def test_random_frame_shapes(rmpe, seed):
     assert r["status"] == 0
     assert np.array_equal(r["candidate"], o[0]), "%s: %d vs %d peaks" % (case, len(r["candidate"]), len(o[0]))
     assert np.array_equal(r["subset"], o[1])
+
+
+def test_full_size_decode_batch_properties(rmpe):
+    """BASELINE config 3 size on one device (64 ski-shaped frames in one call): a few frames equal the oracle,
+    size-independent properties hold for all, and a second run is bit-identical (atomics only feed sorted lists)."""
+    H, W = 674, 712
+    h, w = rmpe.synth.single_scale_grid(H, W)
+    frames = []
+    for i in range(64):
+        paf, heat, _ = rmpe.synth.decode_blobs(4000 + i, (H, W), (h, w), 3 + (i % 3))
+        frames.append(dict(H=H, W=W, scales=[(paf, heat, 0, 0)]))
+    plan = rmpe.batch.DecodeDevicePlan(frames)
+    plan.run()
+    res = plan.results()
+    plan.run()
+    res2 = plan.results()
+    for i, (a, b) in enumerate(zip(res, res2)):
+        assert a["status"] == 0
+        assert np.array_equal(a["candidate"], b["candidate"]) and np.array_equal(a["subset"], b["subset"])
+        c, s = a["candidate"], a["subset"]
+        assert np.array_equal(c[:, 3], np.arange(len(c)))                     # ids consecutive across parts
+        assert int(a["n_peaks"].sum()) == len(c)
+        off = 0
+        for n in a["n_peaks"]:
+            part = c[off:off + n]
+            assert np.array_equal(part, part[np.lexsort((part[:, 0], part[:, 1]))])
+            off += n
+        ids = s[:, :18]
+        assert ((ids == -1) | ((ids >= 0) & (ids < len(c)))).all()
+        assert (s[:, 19] >= (ids >= 0).sum(axis=1)).all()                     # count column (the reference may count a re-assigned part twice)
+        assert len(s) >= 3                                                    # the synthetic persons are found
+    for i in (0, 31, 63):
+        f = frames[i]["scales"][0]
+        cand, sub = do.single_scale(f[0], f[1], H, W)
+        assert np.array_equal(res[i]["candidate"], cand) and np.array_equal(res[i]["subset"], sub)
