@@ -1199,7 +1199,11 @@ __global__ void __launch_bounds__(kLimbThreads) k_limbs(const RmpeFrameDesc *__r
 // k_assemble: one warp per frame; sequential person assembly, merge and prune.
 // ------------------------------------------------------------------------------------------
 constexpr int kAsmConnRows = 1024;   // connection rows of a frame held in shared memory (more: read from global)
+constexpr int kAsmRowCap = kMaxSubsetCap + 1;
 
+// Working copy of `subset` in shared memory, column-major: ids as int32 (they are small exact integers in the
+// reference's float64 rows; -1 = no part), total score and part count as float64 with the reference's addition order.
+// Column-major turns the row search of every connection into conflict-free loads and a row deletion into one pass.
 __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks, int max_persons,
                                                  const double *__restrict__ candidate,
                                                  const double *__restrict__ connections,
@@ -1208,14 +1212,15 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
                                                  int32_t *__restrict__ n_subset, int32_t *__restrict__ status) {
     const int frame = first_frame + blockIdx.x, lane = threadIdx.x;
     extern __shared__ __align__(16) double sm_asm[];
-    double(*s_sub)[20] = reinterpret_cast<double(*)[20]>(sm_asm);                 // [kMaxSubsetCap + 1][20]
-    double *s_conn = sm_asm + (kMaxSubsetCap + 1) * 20;                           // [kAsmConnRows][3]: idA, idB, score
-    double *s_score = s_conn + kAsmConnRows * 3;                                  // [18 * max_peaks] peak scores
+    double *s_sc = sm_asm;                                        // [kAsmRowCap] subset[:, 18]
+    double *s_ct = s_sc + kAsmRowCap;                             // [kAsmRowCap] subset[:, 19]
+    double *s_conn = s_ct + kAsmRowCap;                           // [kAsmConnRows][3]: idA, idB, score
+    double *s_score = s_conn + kAsmConnRows * 3;                  // [18 * max_peaks] peak scores
+    int *s_id = reinterpret_cast<int *>(s_score + kParts * max_peaks);   // [18][kAsmRowCap] subset[:, 0:18]
     __shared__ int s_off[kLimbs + 1];
-    const double *cand = candidate + (size_t)frame * kParts * max_peaks * 4;
-    // ---- one pass over global memory: connection rows and peak scores of the frame ----
-    // counts in one parallel load per lane (a serial loop pays one global round trip per element)
     __shared__ int s_nc[kLimbs];
+    const double *cand = candidate + (size_t)frame * kParts * max_peaks * 4;
+    // ---- one pass over global memory: counts, connection rows and peak scores of the frame ----
     int ntot = (lane < kParts) ? n_peaks[frame * kParts + lane] : 0;
     const int my_nc = (lane < kLimbs) ? n_conn[frame * kLimbs + lane] : 0;
 #pragma unroll
@@ -1230,7 +1235,7 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
     if (lane == kLimbs - 1) s_off[kLimbs] = incl;
     __syncwarp();
     for (int i = lane; i < ntot; i += 32) s_score[i] = cand[(size_t)i * 4 + 2];
-    {   // all limbs' rows in one flat pass (a loop over limbs would pay one global round trip per limb)
+    {
         const int rows_all = min(s_off[kLimbs], kAsmConnRows);
         for (int i = lane; i < rows_all * 3; i += 32) {
             const int row = i / 3, c = i - 3 * row;
@@ -1247,63 +1252,71 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
         const int nc = s_nc[k];
         if (nc < 0) continue;
         const int ia = c_dec_a[k], ib = c_dec_b[k];
+        int *colA = s_id + ia * kAsmRowCap, *colB = s_id + ib * kAsmRowCap;
         const double *conn = connections + ((size_t)frame * kLimbs + k) * max_peaks * 5;
         for (int i = 0; i < nc; i++) {
             const bool in_smem = s_off[k] + i < kAsmConnRows;
             const double *row = in_smem ? s_conn + (s_off[k] + i) * 3 : conn + i * 5;
-            const double pA = row[0], pB = row[1], sc = row[2];
+            const int pA = (int)row[0], pB = (int)row[1];
+            const double sc = row[2];
+            // rows that already hold this A peak or this B peak (eval...:186-195: the first two are recorded)
             int found = 0, j1 = -1, j2 = -1;
             for (int j0 = 0; j0 < nrows; j0 += 32) {
-                int j = j0 + lane;
-                bool hit = (j < nrows) && (s_sub[j][ia] == pA || s_sub[j][ib] == pB);
+                const int j = j0 + lane;
+                const bool hit = (j < nrows) && (colA[j] == pA || colB[j] == pB);
                 unsigned bal = __ballot_sync(0xffffffffu, hit);
-                while (bal) {
-                    int b = __ffs(bal) - 1;
-                    bal &= bal - 1;
-                    if (found == 0) j1 = j0 + b;
-                    else if (found == 1) j2 = j0 + b;
-                    found++;
+                const int n = __popc(bal);
+                if (n) {
+                    if (found == 0) { j1 = j0 + __ffs(bal) - 1; bal &= bal - 1; if (bal) j2 = j0 + __ffs(bal) - 1; }
+                    else if (found == 1) j2 = j0 + __ffs(bal) - 1;
+                    found += n;
                 }
             }
             if (found > 2) { st |= RMPE_ST_FOUND_GT2; found = 2; }
-            __syncwarp();
             if (found == 1) {
-                if (lane == 0 && s_sub[j1][ib] != pB) {
-                    s_sub[j1][ib] = pB;
-                    s_sub[j1][19] = __dadd_rn(s_sub[j1][19], 1.0);
-                    s_sub[j1][18] = __dadd_rn(s_sub[j1][18], __dadd_rn(s_score[(int)pB], sc));
+                if (lane == 0 && colB[j1] != pB) {
+                    colB[j1] = pB;
+                    s_ct[j1] = __dadd_rn(s_ct[j1], 1.0);
+                    s_sc[j1] = __dadd_rn(s_sc[j1], __dadd_rn(s_score[pB], sc));
                 }
             } else if (found == 2) {
-                bool both = (lane < kParts) && (s_sub[j1][lane] >= 0.0) && (s_sub[j2][lane] >= 0.0);
-                unsigned overlap = __ballot_sync(0xffffffffu, both);
+                const bool both = (lane < kParts) && (s_id[lane * kAsmRowCap + j1] >= 0) && (s_id[lane * kAsmRowCap + j2] >= 0);
+                const unsigned overlap = __ballot_sync(0xffffffffu, both);
                 if (overlap == 0) {
-                    if (lane < kParts) s_sub[j1][lane] = __dadd_rn(s_sub[j1][lane], __dadd_rn(s_sub[j2][lane], 1.0));
-                    if (lane == 18) s_sub[j1][18] = __dadd_rn(__dadd_rn(s_sub[j1][18], s_sub[j2][18]), sc);
-                    if (lane == 19) s_sub[j1][19] = __dadd_rn(s_sub[j1][19], s_sub[j2][19]);
+                    // merge (eval...:203-207): r1[:18] += r2[:18] + 1; r1[18:] += r2[18:]; r1[18] += score; delete r2
+                    if (lane < kParts) s_id[lane * kAsmRowCap + j1] += s_id[lane * kAsmRowCap + j2] + 1;
+                    if (lane == 18) s_sc[j1] = __dadd_rn(__dadd_rn(s_sc[j1], s_sc[j2]), sc);
+                    if (lane == 19) s_ct[j1] = __dadd_rn(s_ct[j1], s_ct[j2]);
                     __syncwarp();
-                    for (int r = j2; r < nrows - 1; r++) {   // np.delete(subset, j2, 0)
-                        double v = (lane < 20) ? s_sub[r + 1][lane] : 0.0;
+                    for (int r0 = j2; r0 < nrows - 1; r0 += 32) {          // np.delete(subset, j2, 0): shift up by one
+                        const int r = r0 + lane;
+                        const bool on = r < nrows - 1;
+                        int idv[kParts];
+#pragma unroll
+                        for (int c = 0; c < kParts; c++) idv[c] = on ? s_id[c * kAsmRowCap + r + 1] : 0;
+                        const double scv = on ? s_sc[r + 1] : 0.0, ctv = on ? s_ct[r + 1] : 0.0;
                         __syncwarp();
-                        if (lane < 20) s_sub[r][lane] = v;
+                        if (on) {
+#pragma unroll
+                            for (int c = 0; c < kParts; c++) s_id[c * kAsmRowCap + r] = idv[c];
+                            s_sc[r] = scv; s_ct[r] = ctv;
+                        }
                         __syncwarp();
                     }
                     nrows--;
                 } else if (lane == 0) {
-                    s_sub[j1][ib] = pB;
-                    s_sub[j1][19] = __dadd_rn(s_sub[j1][19], 1.0);
-                    s_sub[j1][18] = __dadd_rn(s_sub[j1][18], __dadd_rn(s_score[(int)pB], sc));
+                    colB[j1] = pB;
+                    s_ct[j1] = __dadd_rn(s_ct[j1], 1.0);
+                    s_sc[j1] = __dadd_rn(s_sc[j1], __dadd_rn(s_score[pB], sc));
                 }
             } else if (found == 0 && k < 17) {
                 if (nrows < max_persons && nrows < kMaxSubsetCap) {
-                    if (lane < 20) s_sub[nrows][lane] = -1.0;
-                    __syncwarp();
-                    if (lane == 0) {
-                        s_sub[nrows][ia] = pA;
-                        s_sub[nrows][ib] = pB;
-                        s_sub[nrows][19] = 2.0;
-                        double s2 = __dadd_rn(__dadd_rn(0.0, s_score[(int)pA]), s_score[(int)pB]);
-                        s_sub[nrows][18] = __dadd_rn(s2, sc);
+                    if (lane < kParts) s_id[lane * kAsmRowCap + nrows] = (lane == ia) ? pA : ((lane == ib) ? pB : -1);
+                    if (lane == 18) {
+                        const double s2 = __dadd_rn(__dadd_rn(0.0, s_score[pA]), s_score[pB]);
+                        s_sc[nrows] = __dadd_rn(s2, sc);
                     }
+                    if (lane == 19) s_ct[nrows] = 2.0;
                     nrows++;
                 } else {
                     st |= RMPE_ST_PERSON_OVERFLOW;
@@ -1312,15 +1325,20 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
             __syncwarp();
         }
     }
-    // prune: fewer than 4 parts or mean score < 0.4
+    // prune: fewer than 4 parts or mean score < 0.4 (eval...:411-415); rows leave as float64
     int nout = 0;
     double *out = subset + (size_t)frame * max_persons * 20;
-    for (int r = 0; r < nrows; r++) {
-        bool drop = (s_sub[r][19] < 4.0) || (__ddiv_rn(s_sub[r][18], s_sub[r][19]) < 0.4);
-        if (!drop) {
-            if (lane < 20) out[(size_t)nout * 20 + lane] = s_sub[r][lane];
-            nout++;
+    for (int r0 = 0; r0 < nrows; r0 += 32) {
+        const int r = r0 + lane;
+        const bool keep = (r < nrows) && !((s_ct[r] < 4.0) || (__ddiv_rn(s_sc[r], s_ct[r]) < 0.4));
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            double *o = out + (size_t)(nout + __popc(bal & ((1u << lane) - 1))) * 20;
+#pragma unroll
+            for (int c = 0; c < kParts; c++) o[c] = (double)s_id[c * kAsmRowCap + r];
+            o[18] = s_sc[r]; o[19] = s_ct[r];
         }
+        nout += __popc(bal);
     }
     if (lane == 0) {
         n_subset[frame] = nout;
@@ -1530,7 +1548,7 @@ static int ensure_smooth_attr() {
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_limbs, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kMaxCandCap * 12 + 2 * kMaxPeaksCap));
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(((kMaxSubsetCap + 1) * 20 + kAsmConnRows * 3 + kParts * kMaxPeaksCap) * 8)));
+                                       (int)((kAsmRowCap * 2 + kAsmConnRows * 3 + kParts * kMaxPeaksCap) * 8 + kParts * kAsmRowCap * 4)));
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_screen_pairs<10, kScrMaxSrcRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_screen_pairs<kScrMaxKW, kScrMaxSrcRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_screen_pairs<kMsKW, kMsMaxRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -1790,7 +1808,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
         }
         {
             ProfScope ps("k_assemble", st);
-            const size_t asm_smem = ((size_t)(kMaxSubsetCap + 1) * 20 + (size_t)kAsmConnRows * 3 + (size_t)kParts * MP) * 8;
+            const size_t asm_smem = ((size_t)kAsmRowCap * 2 + (size_t)kAsmConnRows * 3 + (size_t)kParts * MP) * 8 + (size_t)kParts * kAsmRowCap * 4;
             k_assemble<<<B, 32, asm_smem, st>>>(0, MP, b->max_persons, b->candidate, b->connections, b->n_conn, b->n_peaks,
                                                 b->subset, b->n_subset, b->status);
         }
