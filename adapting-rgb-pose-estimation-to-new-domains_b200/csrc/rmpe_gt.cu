@@ -188,6 +188,60 @@ __device__ __forceinline__ void bicubic_bgrm(const uint32_t *__restrict__ p, int
     oM = kMask ? min(255, max(0, (hM * 256 + lM) >> 15)) : 0;
 }
 
+// "Wide" footprint layout: one 16-byte entry per source position x = the four taps x..x+3 of every channel already
+// packed for dp4a -- (B x4, G x4, R x4, mask x4).  A tap row is then ONE LDS.128 and no byte shuffling at all
+// (the 32-bit (B,G,R,mask) layout needs 4 LDS.32 + 8 PRMT per tap row).  p -> entry of tap row 0; pitch in entries.
+template <bool kMask>
+__device__ __forceinline__ unsigned bicubic_wide(const uint4 *__restrict__ p, int wpitch, const uint32_t *__restrict__ wt) {
+    const uint4 wa = *reinterpret_cast<const uint4 *>(wt);
+    const uint4 wb = *reinterpret_cast<const uint4 *>(wt + kTabBytes / 8);
+    const unsigned whi[4] = {wa.x, wa.y, wa.z, wa.w};
+    const unsigned wlo[4] = {wb.x, wb.y, wb.z, wb.w};
+    int hB = 0, hG = 0, hR = 0, hM = 0;
+    int lB = 16384, lG = 16384, lR = 16384, lM = 16384;   // rounding term of the >>15
+#pragma unroll
+    for (int ky = 0; ky < 4; ky++) {
+        const uint4 e = p[ky * wpitch];
+        hB = dp4a_us(e.x, whi[ky], hB); lB = dp4a_uu(e.x, wlo[ky], lB);
+        hG = dp4a_us(e.y, whi[ky], hG); lG = dp4a_uu(e.y, wlo[ky], lG);
+        hR = dp4a_us(e.z, whi[ky], hR); lR = dp4a_uu(e.z, wlo[ky], lR);
+        if (kMask) { hM = dp4a_us(e.w, whi[ky], hM); lM = dp4a_uu(e.w, wlo[ky], lM); }
+    }
+    const unsigned oB = (unsigned)min(255, max(0, (hB * 256 + lB) >> 15));
+    const unsigned oG = (unsigned)min(255, max(0, (hG * 256 + lG) >> 15));
+    const unsigned oR = (unsigned)min(255, max(0, (hR * 256 + lR) >> 15));
+    const unsigned oM = kMask ? (unsigned)min(255, max(0, (hM * 256 + lM) >> 15)) : 0u;
+    return oB | (oG << 8) | (oR << 16) | (oM << 24);
+}
+
+// planes of 8 consecutive pixels (lo = pixels 0..3, hi = 4..7) -> the 4 sliding entries c..c+3 of one footprint row.
+// Store k of a thread writes entry c + ((k + rot) & 3), rot = (unit index >> 1): the eight lanes of a quarter-warp then
+// hit eight different 16-byte bank groups (entries of one thread are 64 contiguous bytes); the rotation costs nothing,
+// it only makes the funnel-shift amount a register.
+__device__ __forceinline__ void wide_store4(uint4 *__restrict__ row, int c, int rot, unsigned Blo, unsigned Bhi,
+                                            unsigned Glo, unsigned Ghi, unsigned Rlo, unsigned Rhi, unsigned Mlo,
+                                            unsigned Mhi) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int e = (k + rot) & 3;
+        const unsigned sh = 8u * e;
+        row[c + e] = make_uint4(__funnelshift_r(Blo, Bhi, sh), __funnelshift_r(Glo, Ghi, sh), __funnelshift_r(Rlo, Rhi, sh),
+                                __funnelshift_r(Mlo, Mhi, sh));
+    }
+}
+
+// 24 interleaved image bytes (q0..q5 = pixels 0..7) -> B, G, R planes
+__device__ __forceinline__ void wide_planes(unsigned q0, unsigned q1, unsigned q2, unsigned q3, unsigned q4, unsigned q5,
+                                            unsigned &Blo, unsigned &Bhi, unsigned &Glo, unsigned &Ghi, unsigned &Rlo,
+                                            unsigned &Rhi) {
+    Blo = __byte_perm(__byte_perm(q0, q1, 0x0630), q2, 0x5210);
+    Glo = __byte_perm(__byte_perm(q0, q1, 0x0741), q2, 0x6210);
+    Rlo = __byte_perm(__byte_perm(q0, q1, 0x0052), q2, 0x7410);
+    Bhi = __byte_perm(__byte_perm(q3, q4, 0x0630), q5, 0x5210);
+    Ghi = __byte_perm(__byte_perm(q3, q4, 0x0741), q5, 0x6210);
+    Rhi = __byte_perm(__byte_perm(q3, q4, 0x0052), q5, 0x7410);
+}
+
 // (B,G,R,mask) word of one source pixel with cv2's per-tap constant border
 __device__ __forceinline__ unsigned bgrm_pixel(const uint8_t *__restrict__ img, const uint8_t *__restrict__ msk,
                                                int H, int W, int ipitch, int mpitch, int yy, int xx) {
@@ -249,47 +303,84 @@ struct TileCtx {
     const uint32_t *foot;
     const uint32_t *tab;
     const int *gX0, *gY0;
-    int adx, bdx, fpitch, bx0, by0;
-    int mode;   // 0 = staged, 1 = all border, 2 = generic
+    int adx, bdx, fpitch, bx0, by0;   // fpitch: words (mode 0) or 16-byte entries (mode 3)
     const uint8_t *img, *msk;
     int H, W, ipitch, mpitch;
     const int16_t *tab16;
 };
 
 // one destination row of the warp: returns packed B | G<<8 | R<<16 | mask<<24
-template <bool kMask>
-__device__ __forceinline__ unsigned fused_row(const TileCtx &c, int ly, bool lane_on) {
-    if (c.mode == 1 || !lane_on) return kBorderWord;
+// kMode: 0 = staged (B,G,R,mask) words, 1 = all border, 2 = generic (taps from global memory), 3 = staged wide entries
+template <int kMode, bool kMask>
+__device__ __forceinline__ unsigned fused_row(const TileCtx &c, int ly) {
+    if (kMode == 1) return kBorderWord;
     const int X = (c.gX0[ly] + c.adx) >> 5;
     const int Y = (c.gY0[ly] + c.bdx) >> 5;
-    if (c.mode == 0) {
+    const uint32_t *wt = c.tab + (((Y & 31) * 32 + (X & 31)) << 2);
+    if (kMode == 3) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(c.foot) + ((Y >> 5) - 1 - c.by0) * c.fpitch + ((X >> 5) - 1 - c.bx0);
+        return bicubic_wide<kMask>(p, c.fpitch, wt);
+    }
+    if (kMode == 0) {
         int oB, oG, oR, oM;
         const uint32_t *p = c.foot + ((Y >> 5) - 1 - c.by0) * c.fpitch + ((X >> 5) - 1 - c.bx0);
-        const uint32_t *wt = c.tab + (((Y & 31) * 32 + (X & 31)) << 2);
         bicubic_bgrm<kMask>(p, c.fpitch, wt, oB, oG, oR, oM);
         return (unsigned)oB | ((unsigned)oG << 8) | ((unsigned)oR << 16) | ((unsigned)oM << 24);
     }
     return generic_bgrm(c.img, c.msk, c.H, c.W, c.ipitch, c.mpitch, X, Y, c.tab16, kMask);
 }
 
-// store one 32-pixel destination row held one pixel per lane
-__device__ __forceinline__ void store_row(uint8_t *__restrict__ out_sample, int chw, int y, int x0, int tw, int lane,
-                                          unsigned bgr, int pk_lane, unsigned pk_sel) {
-    if (!chw) {
+// per-warp constants of the row stores: HWC packs B,G,R of 32 neighbouring pixels into 24 words with two shuffles
+struct RowStore {
+    uint8_t *op;        // HWC: word `lane` of the first row of the warp; CHW: pixel `lane` of plane 0
+    int pk_lane;
+    unsigned pk_sel;
+    bool on;
+    int chw;
+};
+
+// store destination row j (0..7) of the warp, one pixel per lane
+__device__ __forceinline__ void store_row(const RowStore &rs, int j, unsigned bgr) {
+    if (!rs.chw) {
         // 24 words of the 96-byte row: word w = bytes 4w..4w+3 = pixels floor(4w/3), +1
-        const unsigned a = __shfl_sync(0xffffffffu, bgr, pk_lane);
-        const unsigned b = __shfl_sync(0xffffffffu, bgr, pk_lane + 1);
-        if (4 * lane < 3 * tw)
-            reinterpret_cast<uint32_t *>(out_sample + ((size_t)y * kOutW + x0) * 3)[lane] = __byte_perm(a, b, pk_sel);
-    } else if (lane < tw) {
-        uint8_t *o = out_sample + (size_t)y * kOutW + x0 + lane;
+        const unsigned a = __shfl_sync(0xffffffffu, bgr, rs.pk_lane);
+        const unsigned b = __shfl_sync(0xffffffffu, bgr, rs.pk_lane + 1);
+        if (rs.on) *reinterpret_cast<uint32_t *>(rs.op + j * (kOutW * 3)) = __byte_perm(a, b, rs.pk_sel);
+    } else if (rs.on) {
+        uint8_t *o = rs.op + j * kOutW;
         o[0] = (uint8_t)bgr;
         o[kOutW * kOutH] = (uint8_t)(bgr >> 8);
         o[2 * kOutW * kOutH] = (uint8_t)(bgr >> 16);
     }
 }
 
-template <int NG, bool kWantMask>
+// the 8 destination rows (one cell row) of a warp: taps, stores, and the 8x8 -> 1 mask reduction of cv2.resize
+// returns the cell's float32 accumulator (valid in every lane of the cell's 8-lane group)
+template <int kMode, bool kWantMask>
+__device__ __forceinline__ float cell_rows(const TileCtx &c, const RowStore &rs, int r0, int mw, float b0, float b1) {
+#pragma unroll
+    for (int j = 0; j < 2; j++) store_row(rs, j, fused_row<kMode, false>(c, r0 + j));
+    float macc = 0.f;   // cv2.resize vertical pass, float32 FMA chain S3*b0 -> S2*b1 -> S1*b1 -> S0*b0
+#pragma unroll
+    for (int j = 5; j >= 2; j--) {
+        const unsigned v4 = fused_row<kMode, kWantMask>(c, r0 + j);
+        store_row(rs, j, v4);
+        if (kWantMask) {
+            // cv2.resize horizontal pass: exact int32 sum of (-192,1216,1216,-192) x cols 8c+2..8c+5
+            int v = (int)(v4 >> 24) * mw;
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            const float Sj = (float)v;
+            macc = (j == 5) ? Sj * b0 : fmaf(Sj, (j == 2) ? b0 : b1, macc);
+        }
+    }
+#pragma unroll
+    for (int j = 6; j < 8; j++) store_row(rs, j, fused_row<kMode, false>(c, r0 + j));
+    return macc;
+}
+
+template <int NG, bool kWantMask, bool kWide>
 __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a, int n_items) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem_raw);
@@ -358,6 +449,15 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
     }
     __syncthreads();   // weight table + first two geometries
 
+    // bounding box of the current tile: computed once (for the L2 prefetch, one tile ahead) and carried over
+    int mnx = 0, mxx = 0, mny = 0, mxy = 0;
+    bool sane = false;
+    if (item < n_items) {
+        const int tt = item % kTilesPerSample;
+        const int ty = tt / kTilesX, tx = tt - ty * kTilesX;
+        sane = bbox(geo, min(kTile, kOutW - tx * kTile), min(kTile, kOutH - ty * kTile), mnx, mxx, mny, mxy);
+    }
+
     for (int k = 0; item < n_items; item += stride, k++) {
         const int sample = item / kTilesPerSample;
         const int tt = item - sample * kTilesPerSample;
@@ -369,8 +469,6 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
         const uint8_t *msk = a.src_mask + d.mask_offset;
         const int *gX0 = geo + (k % 3) * kGeoInts, *gY0 = gX0 + kTile, *gad = gY0 + kTile, *gbd = gad + kTile;
 
-        int mnx, mxx, mny, mxy;
-        const bool sane = bbox(gX0, tw, th, mnx, mxx, mny, mxy);
         // 4-byte aligned sources are read with plain 32-bit loads; the footprint then starts on a multiple of 4
         const bool al4 = ((((size_t)img | (size_t)msk) & 3) == 0) && (((d.img_pitch | d.mask_pitch) & 3) == 0);
         const int bx0 = al4 ? (mnx & ~3) : mnx, by0 = mny;
@@ -379,7 +477,66 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
         int fpitch = (fwa + 31) & ~31;     // = 0 (mod 32): the bank of a tap is its column, whatever its row
         if ((long long)fpitch * fh > a.foot_cap) fpitch = fwa;
         const bool outside = sane && (mxx < 0 || mnx >= d.width || mxy < 0 || mny >= d.height);
-        const bool staged = sane && !outside && (long long)fpitch * fh <= a.foot_cap;
+        // wide entries (16 bytes per source position, taps pre-packed): columns bx0 .. mxx-3; the pitch is a multiple
+        // of 8 entries, so the 16-byte bank group of an entry is its column whatever its row
+        const int upr = fw >> 2;                      // units (4 entries) per footprint row = ceil((fw - 3) / 4)
+        const int wpitch = (4 * upr + 7) & ~7;
+        const bool wide = kWide && sane && !outside && al4 && upr >= 1 && upr <= 64 && (long long)wpitch * fh * 4 <= a.foot_cap;
+        const bool staged = !wide && sane && !outside && (long long)fpitch * fh <= a.foot_cap;
+
+        if (kWide && wide) {
+            // ---- one thread = 4 entries of one footprint row = 7 source pixels (read as 8) -> four 16-byte stores;
+            //      units are numbered row-major over the footprint, two units (u, u + 128) in flight per thread ----
+            uint4 *wfoot = reinterpret_cast<uint4 *>(foot);
+            const int n_units = fh * upr;
+            const unsigned inv = (65536u + upr - 1) / upr;          // u / upr == (u * inv) >> 16 for u < 2^13
+            for (int u0 = t; u0 < n_units; u0 += 2 * kGroupThreads) {
+                int rr[2], cc[2], kind[2];                            // kind: 0 = interior, 1 = row outside, 2 = edge
+                unsigned q[2][6], m[2][2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int u = u0 + h * kGroupThreads;
+                    const int r = (int)(((unsigned)u * inv) >> 16);
+                    rr[h] = r; cc[h] = (u - r * upr) << 2;
+                    const int xx = bx0 + cc[h], yy = by0 + r;
+                    kind[h] = (u >= n_units) ? 3 : ((unsigned)yy >= (unsigned)d.height ? 1 : ((xx >= 0 && xx + 7 < d.width) ? 0 : 2));
+                    if (kind[h] == 0) {
+                        const uint32_t *ip = reinterpret_cast<const uint32_t *>(img + (size_t)yy * d.img_pitch + 3 * xx);
+                        const uint32_t *mp = reinterpret_cast<const uint32_t *>(msk + (size_t)yy * d.mask_pitch + xx);
+#pragma unroll
+                        for (int i = 0; i < 6; i++) q[h][i] = __ldg(ip + i);
+                        m[h][0] = __ldg(mp); m[h][1] = __ldg(mp + 1);
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    if (kind[h] == 3) break;
+                    unsigned Blo, Bhi, Glo, Ghi, Rlo, Rhi, Mlo, Mhi;
+                    if (kind[h] == 0) {
+                        wide_planes(q[h][0], q[h][1], q[h][2], q[h][3], q[h][4], q[h][5], Blo, Bhi, Glo, Ghi, Rlo, Rhi);
+                        Mlo = m[h][0]; Mhi = m[h][1];
+                    } else if (kind[h] == 1) {
+                        Blo = Bhi = Glo = Ghi = Rlo = Rhi = 0x7F7F7F7Fu; Mlo = Mhi = 0xFFFFFFFFu;
+                    } else {
+                        // a unit that straddles the left/right image edge: per-pixel border test, then 4x4 byte transposes
+                        unsigned w[8];
+#pragma unroll
+                        for (int i = 0; i < 7; i++)
+                            w[i] = bgrm_pixel(img, msk, d.height, d.width, d.img_pitch, d.mask_pitch, by0 + rr[h], bx0 + cc[h] + i);
+                        w[7] = w[6];
+                        const unsigned t0 = __byte_perm(w[0], w[1], 0x5140), t1 = __byte_perm(w[2], w[3], 0x5140);
+                        const unsigned t2 = __byte_perm(w[0], w[1], 0x7362), t3 = __byte_perm(w[2], w[3], 0x7362);
+                        const unsigned u0_ = __byte_perm(w[4], w[5], 0x5140), u1 = __byte_perm(w[6], w[7], 0x5140);
+                        const unsigned u2 = __byte_perm(w[4], w[5], 0x7362), u3 = __byte_perm(w[6], w[7], 0x7362);
+                        Blo = __byte_perm(t0, t1, 0x5410); Glo = __byte_perm(t0, t1, 0x7632);
+                        Rlo = __byte_perm(t2, t3, 0x5410); Mlo = __byte_perm(t2, t3, 0x7632);
+                        Bhi = __byte_perm(u0_, u1, 0x5410); Ghi = __byte_perm(u0_, u1, 0x7632);
+                        Rhi = __byte_perm(u2, u3, 0x5410); Mhi = __byte_perm(u2, u3, 0x7632);
+                    }
+                    wide_store4(wfoot + rr[h] * wpitch, cc[h], (cc[h] >> 3) & 3, Blo, Bhi, Glo, Ghi, Rlo, Rhi, Mlo, Mhi);
+                }
+            }
+        }
 
         // ---- stage the footprint as (B,G,R,mask) words: one thread = 4 pixels = one 16-byte store ----
         if (staged) {
@@ -414,18 +571,21 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
         }
         group_bar(group);     // footprint visible
 
-        // two tiles ahead: geometry; one tile ahead: pull the footprint's lines into L2 -- both overlap this tile's taps
+        // two tiles ahead: geometry; one tile ahead: bounding box (kept for the next pass) and its lines pulled into L2
+        // -- all of it overlaps this tile's taps
         if (item + 2 * stride < n_items && t < 2 * kTile) geometry(item + 2 * stride, (k + 2) % 3);
+        int nmnx = 0, nmxx = 0, nmny = 0, nmxy = 0;
+        bool nsane = false;
         if (item + stride < n_items) {
             const int ni = item + stride;
             const int ns = ni / kTilesPerSample, ntt = ni - ns * kTilesPerSample;
             const int nty = ntt / kTilesX, ntx = ntt - nty * kTilesX;
-            int pnx, pxx, pny, pxy;
-            if (bbox(geo + ((k + 1) % 3) * kGeoInts, min(kTile, kOutW - ntx * kTile), min(kTile, kOutH - nty * kTile), pnx,
-                     pxx, pny, pxy)) {
+            nsane = bbox(geo + ((k + 1) % 3) * kGeoInts, min(kTile, kOutW - ntx * kTile), min(kTile, kOutH - nty * kTile),
+                         nmnx, nmxx, nmny, nmxy);
+            if (nsane) {
                 const RmpeSrcDesc nd = a.desc[ns];
-                pnx = max(pnx, 0); pxx = min(pxx, nd.width - 1);
-                pny = max(pny, 0); pxy = min(pxy, nd.height - 1);
+                const int pnx = max(nmnx, 0), pxx = min(nmxx, nd.width - 1);
+                const int pny = max(nmny, 0), pxy = min(nmxy, nd.height - 1);
                 const int rows = pxy - pny + 1;
                 if (pxx >= pnx && rows > 0 && rows <= 256) {
                     // per row: up to 3 image lines + 1 mask line of 128 bytes (wider footprints: first 384 bytes)
@@ -450,35 +610,24 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
         // ---- taps, mask reduction, stores: warp = cell row ----
         if (8 * warp < th) {
             TileCtx c;
+            const int gl = min(lane, tw - 1);     // lanes beyond the tile edge repeat its last pixel (never stored)
             c.foot = foot; c.tab = s_tab; c.gX0 = gX0; c.gY0 = gY0;
-            c.adx = gad[lane]; c.bdx = gbd[lane]; c.fpitch = fpitch; c.bx0 = bx0; c.by0 = by0;
-            c.mode = staged ? 0 : (outside ? 1 : 2);
+            c.adx = gad[gl]; c.bdx = gbd[gl]; c.fpitch = wide ? wpitch : fpitch; c.bx0 = bx0; c.by0 = by0;
             c.img = img; c.msk = msk; c.H = d.height; c.W = d.width; c.ipitch = d.img_pitch; c.mpitch = d.mask_pitch;
             c.tab16 = a.tab;
             const bool lane_on = lane < tw;
-            uint8_t *out_sample = a.out_img + (size_t)sample * (3 * kOutW * kOutH);
             const int r0 = 8 * warp;
-#pragma unroll
-            for (int j = 0; j < 2; j++)
-                store_row(out_sample, a.chw, y0 + r0 + j, x0, tw, lane, fused_row<false>(c, r0 + j, lane_on), pk_lane, pk_sel);
-            float macc = 0.f;   // cv2.resize vertical pass, float32 FMA chain S3*b0 -> S2*b1 -> S1*b1 -> S0*b0
-#pragma unroll
-            for (int j = 5; j >= 2; j--) {
-                const unsigned v4 = kWantMask ? fused_row<true>(c, r0 + j, lane_on) : fused_row<false>(c, r0 + j, lane_on);
-                store_row(out_sample, a.chw, y0 + r0 + j, x0, tw, lane, v4, pk_lane, pk_sel);
-                if (kWantMask) {
-                    // cv2.resize horizontal pass: exact int32 sum of (-192,1216,1216,-192) x cols 8c+2..8c+5
-                    int v = (int)(v4 >> 24) * mw;
-                    v += __shfl_xor_sync(0xffffffffu, v, 1);
-                    v += __shfl_xor_sync(0xffffffffu, v, 2);
-                    v += __shfl_xor_sync(0xffffffffu, v, 4);
-                    const float Sj = (float)v;
-                    macc = (j == 5) ? Sj * b0 : fmaf(Sj, (j == 2) ? b0 : b1, macc);
-                }
-            }
-#pragma unroll
-            for (int j = 6; j < 8; j++)
-                store_row(out_sample, a.chw, y0 + r0 + j, x0, tw, lane, fused_row<false>(c, r0 + j, lane_on), pk_lane, pk_sel);
+            uint8_t *out_sample = a.out_img + (size_t)sample * (3 * kOutW * kOutH);
+            RowStore rs;
+            rs.chw = a.chw; rs.pk_lane = pk_lane; rs.pk_sel = pk_sel;
+            rs.op = a.chw ? out_sample + (size_t)(y0 + r0) * kOutW + x0 + lane
+                          : out_sample + ((size_t)(y0 + r0) * kOutW + x0) * 3 + 4 * lane;
+            rs.on = a.chw ? lane_on : (4 * lane < 3 * tw);
+            float macc;
+            if (kWide && wide) macc = cell_rows<3, kWantMask>(c, rs, r0, mw, b0, b1);
+            else if (staged) macc = cell_rows<0, kWantMask>(c, rs, r0, mw, b0, b1);
+            else if (outside) macc = cell_rows<1, kWantMask>(c, rs, r0, mw, b0, b1);
+            else macc = cell_rows<2, kWantMask>(c, rs, r0, mw, b0, b1);
             if (kWantMask && l7 == 0 && lane_on) {
                 // rint, saturate; then /255.  (py_rmpe_transformer.py:92,95)
                 const int iv = min(255, max(0, __float2int_rn(macc)));
@@ -488,6 +637,7 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
                 else reinterpret_cast<float *>(a.out_mask)[o] = (float)m;
             }
         }
+        mnx = nmnx; mxx = nmxx; mny = nmny; mxy = nmxy; sane = nsane;
         group_bar(group);     // footprint free, next geometry visible
     }
 }
@@ -789,22 +939,35 @@ __global__ void __launch_bounds__(kRasterThreads) k_raster(RasterArgs a) {
 
 // ==========================================================================================
 // k_raster_small: the same rasteriser for the common case of <= 4 persons per sample (COCO crops).
-// grid = (pixel slices, batch), one slice by default (measured best: the per-CTA tables are built once
-// per sample); a thread owns ONE float4 run of pixels and writes it for all 57 planes.  Everything the planes need is built once per CTA -- transformed joints, the separable
-// exp tables of all 18 parts x persons, the limb records of all 19 limbs x persons -- so the plane
-// loop has no barrier and every store is an independent coalesced 128-bit write.
+// grid = (plane groups, batch); a thread owns ONE float4 run of pixels and writes it for all planes of its group.
+// Everything the planes need is built once per CTA -- transformed joints, the separable exp tables of the group's
+// parts x persons, the limb records of the group's limbs x persons -- so the plane loop has no barrier and every
+// store is an independent coalesced 128-bit write.  One group (all 57 planes) is the default: splitting a sample over
+// 2 or 4 CTAs (heat | PAF; parts 0-8 | parts 9-17 + background | limbs 0-9 | limbs 10-18, RMPE_RASTER_GROUPS) evens out
+// the 256 CTAs over 148 SMs but repeats the per-CTA load/table latency chain: measured 46 / 49 / 57 us per 256 samples.
 // ==========================================================================================
 constexpr int kRsMaxP = 4;
-constexpr int kRsSlices = 1;         // default pixel slices per sample (gridDim.x); blockDim.x = runs per slice, rounded to warps
+constexpr int kRsGroups = 1;         // default plane groups per sample (gridDim.x): 1, 2 or 4
 
 template <typename T>
 __global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
     const int b = blockIdx.y;
-    const int slice = blockIdx.x;
+    const int grp = blockIdx.x, n_grp = gridDim.x;
     const int tid = threadIdx.x;
     const int kRsThreads = blockDim.x;
-    const int kRsRuns = (kCellVec + gridDim.x - 1) / gridDim.x;
     const int P = min(a.n_persons[b], kRsMaxP);
+    // planes of this group: parts [part_lo, part_hi) are stored, the background needs the max over all 18 parts
+    int part_lo = 0, part_hi = kParts, limb_lo = 0, limb_hi = kLimbs;
+    bool want_bkg = true;
+    if (n_grp == 2) {
+        if (grp == 0) { limb_hi = 0; } else { part_hi = 0; want_bkg = false; }
+    } else if (n_grp == 4) {
+        if (grp == 0) { part_hi = 9; want_bkg = false; limb_hi = 0; }
+        else if (grp == 1) { part_lo = 9; limb_hi = 0; }
+        else if (grp == 2) { part_hi = 0; want_bkg = false; limb_hi = 10; }
+        else { part_hi = 0; want_bkg = false; limb_lo = 10; }
+    }
+    const int tab_lo = want_bkg ? 0 : part_lo, tab_hi = want_bkg ? kParts : part_hi;
 
     // dynamic shared memory sized for the launch's max_persons (raster_small_smem): 24 KB at 3 persons
     extern __shared__ __align__(16) uint8_t rs_smem[];
@@ -830,7 +993,7 @@ __global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
             oy = __dadd_rn(__fma_rn(M[4], y, __dmul_rn(M[3], x)), M[5]);
         }
         s_j[i * 3 + 0] = ox; s_j[i * 3 + 1] = oy; s_j[i * 3 + 2] = ov;
-        if (slice == 0 && a.out_joints) {
+        if (grp == 0 && a.out_joints) {
             double *jo = a.out_joints + ((size_t)b * a.max_persons + p) * (kParts * 3) + part * 3;
             jo[0] = ox; jo[1] = oy; jo[2] = ov;
         }
@@ -839,7 +1002,7 @@ __global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
 
     // ---- H1/H2 tables: ex/ey[part][person][cell], cell centres 8i + 3.5 (py_rmpe_heatmapper.py:22-23, 51-57) ----
     const float inv2s2 = (float)(1.0 / (2.0 * a.sigma * a.sigma));
-    for (int i = tid; i < kParts * P * kGrid; i += kRsThreads) {
+    for (int i = tab_lo * P * kGrid + tid; i < tab_hi * P * kGrid; i += kRsThreads) {
         const int cidx = i % kGrid, pp = i / kGrid;           // pp = part * P + p
         const int part = pp / P, p = pp - part * P;
         const double *j = s_j + (p * kParts + part) * 3;
@@ -851,7 +1014,7 @@ __global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
     }
     // ---- H4 limb records: [limb][person] ----
     const double thre = a.thre;
-    for (int i = tid; i < kLimbs * P; i += kRsThreads) {
+    for (int i = limb_lo * P + tid; i < limb_hi * P; i += kRsThreads) {
         const int k = i / P, p = i - k * P;
         const double *jf = s_j + (p * kParts + c_limb_from[k]) * 3, *jt = s_j + (p * kParts + c_limb_to[k]) * 3;
         LimbRec r;
@@ -863,7 +1026,7 @@ __global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
         r.ux = r.uy = 0.f;
         if (jf[2] < 2.0 && jt[2] < 2.0) {
             if (r.norm2 == 0.0) {
-                if (slice == 0) atomicOr(a.status + b, RMPE_ST_ZERO_LIMB);
+                atomicOr(a.status + b, RMPE_ST_ZERO_LIMB);
             } else {
                 r.ux = (float)__ddiv_rn(r.xD, r.norm2);
                 r.uy = (float)__ddiv_rn(r.yD, r.norm2);
@@ -884,8 +1047,8 @@ __global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
     }
     __syncthreads();
 
-    const int run = slice * kRsRuns + tid;
-    if (tid >= kRsRuns || run >= kCellVec) return;
+    const int run = tid;
+    if (run >= kCellVec) return;
     const int pix = 4 * run;
     int y[4], x[4];
 #pragma unroll
@@ -901,7 +1064,7 @@ __global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
     // ---- H2/H3: Gaussian part maps with max merge, background = 1 - max ----
     float bk[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 2
-    for (int part = 0; part < kParts; part++) {
+    for (int part = tab_lo; part < tab_hi; part++) {
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         for (int p = 0; p < P; p++) {
             const float *ex = s_ex + (part * P + p) * kGrid, *ey = s_ey + (part * P + p) * kGrid;
@@ -910,13 +1073,13 @@ __global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) bk[q] = fmaxf(bk[q], v[q]);
-        store4<T>(lab + (size_t)(38 + part) * kCells, v[0], v[1], v[2], v[3], m);
+        if (part >= part_lo) store4<T>(lab + (size_t)(38 + part) * kCells, v[0], v[1], v[2], v[3], m);
     }
-    store4<T>(lab + (size_t)56 * kCells, 1.f - bk[0], 1.f - bk[1], 1.f - bk[2], 1.f - bk[3], m);
+    if (want_bkg) store4<T>(lab + (size_t)56 * kCells, 1.f - bk[0], 1.f - bk[1], 1.f - bk[2], 1.f - bk[3], m);
 
     // ---- H4: part-affinity fields ----
     const int ymin = y[0], ymax = y[3];
-    for (int k = 0; k < kLimbs; k++) {
+    for (int k = limb_lo; k < limb_hi; k++) {
         float vx[4] = {0.f, 0.f, 0.f, 0.f}, vy[4] = {0.f, 0.f, 0.f, 0.f};
         int cnt[4] = {0, 0, 0, 0};
         for (int p = 0; p < P; p++) {
@@ -988,20 +1151,20 @@ static int fused_foot_cap(int ng) {
 }
 static size_t fused_smem_bytes(int ng) { return (size_t)kTabBytes + (size_t)ng * ((size_t)fused_foot_cap(ng) * 4 + kGroupFixedBytes); }
 
-template <int NG>
+template <int NG, bool kWide>
 static int launch_fused(const FusedArgs &fa_, bool want_mask, int n_items, int sm_count, cudaStream_t st) {
     FusedArgs fa = fa_;
     fa.foot_cap = fused_foot_cap(NG);
     const size_t smem = fused_smem_bytes(NG);
     static bool attr_set = false;
     if (!attr_set) {
-        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, true, kWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, false, kWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const int grid = min((n_items + NG - 1) / NG, sm_count);
-    if (want_mask) k_warp_fused<NG, true><<<grid, NG * kGroupThreads, smem, st>>>(fa, n_items);
-    else k_warp_fused<NG, false><<<grid, NG * kGroupThreads, smem, st>>>(fa, n_items);
+    if (want_mask) k_warp_fused<NG, true, kWide><<<grid, NG * kGroupThreads, smem, st>>>(fa, n_items);
+    else k_warp_fused<NG, false, kWide><<<grid, NG * kGroupThreads, smem, st>>>(fa, n_items);
     return RMPE_OK;
 }
 
@@ -1052,15 +1215,28 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
             fa.mask_f64 = (b->flags & RMPE_GT_LABELS_F64) ? 1 : 0;
             fa.foot_cap = 0;
             const int n_items = b->batch * kTilesPerSample;
+            // default: 32-bit (B,G,R,mask) footprint words, 8 tile groups (1024 threads) per SM.  RMPE_WARP_GROUPS = 4 | 6 | 8
+            // and RMPE_WARP_WIDE=1 (16-byte pre-packed footprint entries, 4 | 5 | 6 groups) are kept for A/B tests:
+            // measured on B200 (GT batch 256): words 8 groups 0.354 ms, 6 groups 0.365 ms; wide 5 groups 0.393 ms --
+            // the wide layout halves the issued instructions of the taps but pays for it in staging wavefronts, and
+            // both are bound by the shared-memory/L1 data pipe (profiles/r01r).
+            static const bool wide = [] {
+                const char *e = getenv("RMPE_WARP_WIDE");
+                return e ? atoi(e) != 0 : false;
+            }();
             static const int ng = [] {
                 const char *e = getenv("RMPE_WARP_GROUPS");
-                int v = e ? atoi(e) : 6;
-                return (v == 4 || v == 8) ? v : 6;
+                int v = e ? atoi(e) : 0;
+                return (v == 4 || v == 5 || v == 6 || v == 8) ? v : 0;
             }();
             ProfScope ps("k_warp_fused", st);
-            int rc = ng == 4 ? launch_fused<4>(fa, want_mask, n_items, T.sm_count, st)
-                   : ng == 8 ? launch_fused<8>(fa, want_mask, n_items, T.sm_count, st)
-                             : launch_fused<6>(fa, want_mask, n_items, T.sm_count, st);
+            int rc;
+            if (wide) rc = ng == 4 ? launch_fused<4, true>(fa, want_mask, n_items, T.sm_count, st)
+                         : ng == 6 ? launch_fused<6, true>(fa, want_mask, n_items, T.sm_count, st)
+                                   : launch_fused<5, true>(fa, want_mask, n_items, T.sm_count, st);
+            else rc = ng == 4 ? launch_fused<4, false>(fa, want_mask, n_items, T.sm_count, st)
+                    : ng == 6 ? launch_fused<6, false>(fa, want_mask, n_items, T.sm_count, st)
+                              : launch_fused<8, false>(fa, want_mask, n_items, T.sm_count, st);
             if (rc != RMPE_OK) return rc;
             mask_done = want_mask;
         }
@@ -1084,13 +1260,13 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
         ra.sigma = 7.0; ra.thre = 8.0;
         ProfScope ps("k_raster", st);
         if (b->max_persons <= kRsMaxP && !simple) {
-            static const int slices = [] {
-                const char *e = getenv("RMPE_RASTER_SLICES");
-                int v = e ? atoi(e) : kRsSlices;
-                return (v >= 1 && v <= 8) ? v : kRsSlices;
+            static const int groups = [] {
+                const char *e = getenv("RMPE_RASTER_GROUPS");
+                int v = e ? atoi(e) : kRsGroups;
+                return (v == 1 || v == 2 || v == 4) ? v : kRsGroups;
             }();
-            dim3 grid(slices, b->batch);
-            const int kRsThreads = (((kCellVec + slices - 1) / slices) + 31) & ~31;
+            dim3 grid(groups, b->batch);
+            const int kRsThreads = (kCellVec + 31) & ~31;
             const int pm = b->max_persons;
             const size_t smem = (size_t)kLimbs * pm * sizeof(LimbRec) + (size_t)pm * kParts * 3 * 8 + 2 * (size_t)kParts * pm * kGrid * 4;
             if (ra.f64) k_raster_small<double><<<grid, kRsThreads, smem, st>>>(ra);
