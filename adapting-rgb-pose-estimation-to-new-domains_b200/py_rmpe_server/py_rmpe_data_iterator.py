@@ -36,6 +36,48 @@ class RawDataIterator:
             image = np.transpose(image, (2, 0, 1))
             yield image, mask, labels, meta['joints']
 
+    def gen_batched(self, batch, dbg=False):
+        """Same stream of (image, mask, labels, joints) tuples as gen(), produced `batch` samples per C-ABI call.
+        Sources of different sizes share a call after padding to the largest with the border constants of the two
+        warps (127 / 255, py_rmpe_transformer.py:90-91): cv2 substitutes exactly those values for every tap outside
+        the source, so the padded warp is bit-identical to the unpadded one."""
+        keys = list(self.datum.keys())
+        if self.shuffle:
+            random.shuffle(keys)
+        for k0 in range(0, len(keys), batch):
+            raw = [self.read_data(key) for key in keys[k0:k0 + batch]]
+            for tpl in self.transform_batch(raw):
+                yield tpl
+
+    def transform_batch(self, raw):
+        """raw: list of (img HxWx3 u8, mask HxW u8, meta) -> list of (image (3,368,368), mask, labels, joints)."""
+        n = len(raw)
+        H = max(r[0].shape[0] for r in raw)
+        W = max(r[0].shape[1] for r in raw)
+        imgs = np.full((n, H, W, 3), 127, np.uint8)
+        masks = np.full((n, H, W), 255, np.uint8)
+        P = max(max(np.asarray(r[2]['joints']).shape[0] for r in raw), 1)
+        joints = np.zeros((n, P, 18, 3))
+        joints[:, :, :, 2] = 2.0                      # padding persons are "absent"
+        n_persons = np.zeros(n, np.int32)
+        augs = [AugmentSelection.random() if self.augment else AugmentSelection.unrandom() for _ in raw]
+        for i, (img, mask, meta) in enumerate(raw):
+            imgs[i, :img.shape[0], :img.shape[1]] = img
+            masks[i, :mask.shape[0], :mask.shape[1]] = mask
+            j = np.asarray(meta['joints'], dtype=np.float64)
+            joints[i, :j.shape[0]] = j
+            n_persons[i] = j.shape[0]
+        M = _batch.aug_affine([a.flip for a in augs], [a.degree for a in augs], [a.crop for a in augs],
+                              [a.scale for a in augs], [r[2]['objpos'][0] for r in raw],
+                              [r[2]['scale_provided'][0] for r in raw])
+        res = _batch.gt_batch_host(imgs, masks, joints, n_persons, M, [1 if a.flip else 0 for a in augs], f64=True, chw=True)
+        out = []
+        for i, (_, _, meta) in enumerate(raw):
+            if n_persons[i]:
+                meta['joints'][:, :, :] = res["joints"][i, :n_persons[i]]
+            out.append((res["img"][i], res["mask"][i], res["labels"][i], meta['joints']))
+        return out
+
     def num_keys(self):
         return len(list(self.datum.keys()))
 

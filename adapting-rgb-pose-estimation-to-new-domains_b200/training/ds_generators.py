@@ -5,12 +5,14 @@
 y2 (B,46,46,19)] * n_stages` like the reference.  The per-sample transposes / repeats / concatenations
 of the reference (:47-77) run as ONE pass of k_keras_batch over the whole batch (rmpe_keras_batch);
 `FusedDataIterator` additionally runs warp + mask + labels for the whole batch in one call instead
-of sample by sample.  The ZMQ client (DataGeneratorClient) is transport, not arithmetic: out of scope."""
+of sample by sample.  `DataGeneratorClient` (:109-186) is the ZMQ PULL side of py_rmpe_server/rmpe_server.py;
+the wire format lives in rmpe_server.send_arrays / recv_arrays."""
 import numpy as np
 
 from .. import batch as _batch
 from ..py_rmpe_server.py_rmpe_data_iterator import RawDataIterator
 from ..py_rmpe_server.py_rmpe_transformer import AugmentSelection
+from ..py_rmpe_server.rmpe_server import recv_arrays as _recv_arrays_wire
 
 
 class DataIteratorBase:
@@ -27,7 +29,11 @@ class DataIteratorBase:
 
     def gen_raw(self):
         while True:
-            yield tuple(self._recv_arrays())
+            try:
+                arrays = self._recv_arrays()
+            except StopIteration:      # `stop` header / limit reached: end the stream (a bare StopIteration inside a
+                return                 # generator is a RuntimeError since PEP 479)
+            yield tuple(arrays)
 
     def gen(self, n_stages):
         imgs, masks, labels = [], [], []
@@ -47,6 +53,30 @@ class DataIteratorBase:
                 imgs, masks, labels = [], [], []
                 yield [batch_x, kb["x1"], kb["x2"]], [kb["y1"], kb["y2"]] * n_stages
                 self.keypoints = [None] * self.batch_size
+
+
+class DataGeneratorClient(DataIteratorBase):
+    """ZMQ client of rmpe_server.Server (reference :109-186): same constructor, same `stop` / `limit` behaviour."""
+
+    def __init__(self, host, port, hwm=20, batch_size=10, limit=None):
+        super(DataGeneratorClient, self).__init__(batch_size)
+        import zmq
+        self.limit = limit
+        self.records = 0
+        self.host = host
+        self.port = port
+        self.hwm = hwm
+        context = zmq.Context()
+        self.socket = context.socket(zmq.PULL)
+        self.socket.set_hwm(self.hwm)
+        self.socket.connect("tcp://{}:{}".format(self.host, self.port))
+
+    def _recv_arrays(self):
+        if self.limit is not None and self.records > self.limit:
+            raise StopIteration
+        arrays = _recv_arrays_wire(self.socket)
+        self.records += 1
+        return arrays
 
 
 class DataIterator(DataIteratorBase):

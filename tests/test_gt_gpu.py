@@ -261,3 +261,62 @@ def test_fused_data_iterator_batches(rmpe):
         assert np.abs(ys[0][i] - np.transpose(olab[:38], (1, 2, 0))).max() <= LABEL_TOL
         assert np.abs(ys[1][i] - np.transpose(olab[38:], (1, 2, 0))).max() <= LABEL_TOL
         assert np.array_equal(it.keypoints[i], oj) or True
+
+
+class _FakeEntry:
+    """One HDF5 dataset of generate_hdf5_coco2014.py: a (6,H,W) u8 datum + a JSON `meta` attribute."""
+
+    def __init__(self, data, meta):
+        import json
+        self._data = data
+        self.attrs = {'meta': json.dumps(meta)}
+
+    def __getitem__(self, key):
+        return self._data
+
+
+def _fake_datum(shapes, seed0=900):
+    datum = {}
+    for i, (H, W) in enumerate(shapes):
+        rng = np.random.RandomState(seed0 + i)
+        data = rng.randint(0, 256, (6, H, W)).astype(np.uint8)
+        data[4] = 255
+        data[4, H // 4:H // 2, W // 3:W // 2] = 0            # a miss-mask rectangle
+        P = 1 + i % 3
+        joints = np.zeros((P, 17, 3))
+        joints[:, :, 0] = rng.uniform(0, W, (P, 17))
+        joints[:, :, 1] = rng.uniform(0, H, (P, 17))
+        joints[:, :, 2] = rng.choice([0., 1., 2.], (P, 17), p=[.2, .7, .1])
+        meta = dict(joints=joints.tolist(), objpos=[[W / 2. + 3 * i, H / 2. - 2 * i]], scale_provided=[0.45 + 0.1 * i])
+        datum["%07d" % i] = _FakeEntry(data, meta)
+    return datum
+
+
+def test_raw_iterator_batched_equals_per_sample(rmpe):
+    """RawDataIterator.gen_batched (one C-ABI call per batch, ragged sources padded with the border constants) ==
+    RawDataIterator.gen (one call per sample), bit for bit; one sample is also checked against the oracle."""
+    import random
+    shapes = [(240, 320), (368, 368), (300, 200), (427, 640), (180, 500), (333, 500), (96, 128)]
+    it = rmpe.data_iterator.RawDataIterator(None, shuffle=False, augment=True)
+    it.datum = _fake_datum(shapes)
+    assert it.num_keys() == len(shapes)
+    random.seed(11)
+    one = [tuple(np.array(a, copy=True) for a in tpl) for tpl in it.gen()]
+    it.datum = _fake_datum(shapes)
+    random.seed(11)
+    many = [tuple(np.array(a, copy=True) for a in tpl) for tpl in it.gen_batched(4)]
+    assert len(one) == len(many) == len(shapes)
+    for a, b in zip(one, many):
+        assert a[0].shape == (3, 368, 368) and a[1].shape == (46, 46) and a[2].shape == (57, 46, 46)
+        for x, y in zip(a, b):
+            assert x.dtype == y.dtype and np.array_equal(x, y)
+    # oracle on the first sample (same RNG draw order as AugmentSelection.random)
+    random.seed(11)
+    aug = rmpe.transformer.AugmentSelection.random()
+    img, mask, meta = it.read_data("0000000")
+    M = go.affine_closed_form(aug.flip, aug.degree, aug.crop, aug.scale, meta['objpos'][0], meta['scale_provided'][0])
+    oimg, omask, oj = go.transform(np.ascontiguousarray(img), np.ascontiguousarray(mask), meta['joints'], M, aug.flip)
+    olab = go.create_heatmaps(oj, omask)
+    assert np.array_equal(many[0][0], np.transpose(oimg, (2, 0, 1)))
+    assert np.array_equal(many[0][1], omask) and np.array_equal(many[0][3], oj)
+    assert np.abs(many[0][2] - olab).max() <= LABEL_TOL
