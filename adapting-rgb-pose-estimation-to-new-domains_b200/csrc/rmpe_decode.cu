@@ -1196,7 +1196,8 @@ __global__ void __launch_bounds__(kLimbThreads) k_limbs(const RmpeFrameDesc *__r
 }
 
 // ------------------------------------------------------------------------------------------
-// k_assemble: one warp per frame; sequential person assembly, merge and prune.
+// k_assemble: one warp per frame; person assembly limb by limb (the connections of a limb side by side where that
+// cannot change the result, in the reference's order otherwise), merge and prune.
 // ------------------------------------------------------------------------------------------
 constexpr int kAsmConnRows = 1024;   // connection rows of a frame held in shared memory (more: read from global)
 constexpr int kAsmRowCap = kMaxSubsetCap + 1;
@@ -1254,7 +1255,51 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
         const int ia = c_dec_a[k], ib = c_dec_b[k];
         int *colA = s_id + ia * kAsmRowCap, *colB = s_id + ib * kAsmRowCap;
         const double *conn = connections + ((size_t)frame * kLimbs + k) * max_peaks * 5;
-        for (int i = 0; i < nc; i++) {
+        for (int i0 = 0; i0 < nc; i0 += 32) {
+        const int n_chunk = min(32, nc - i0);
+        {
+            // ---- the connections of a limb side by side, one per lane.  The greedy pick gives every connection of a
+            // limb its own A peak and its own B peak, so a connection that extends one row (found == 1) or opens a new
+            // one (found == 0) cannot change what the other connections of the limb find -- unless two of them meet in
+            // the same row or one of them joins two rows (found == 2): those chunks take the reference's order below.
+            int pA = -1, pB = -1;
+            double sc = 0.0;
+            if (lane < n_chunk) {
+                const int i = i0 + lane;
+                const double *row = (s_off[k] + i < kAsmConnRows) ? s_conn + (s_off[k] + i) * 3 : conn + i * 5;
+                pA = (int)row[0]; pB = (int)row[1]; sc = row[2];
+            }
+            int found = 0, j1 = -1;
+            for (int j = 0; j < nrows; j++) {
+                const bool hit = (lane < n_chunk) && (colA[j] == pA || colB[j] == pB);
+                if (hit) { if (found == 0) j1 = j; found++; }
+            }
+            bool bad = found >= 2;
+            const unsigned one_m = __ballot_sync(0xffffffffu, found == 1);
+            if (found == 1) bad = __popc(__match_any_sync(one_m, j1)) > 1;
+            const unsigned new_m = __ballot_sync(0xffffffffu, lane < n_chunk && found == 0 && k < 17);
+            const int n_new = __popc(new_m);
+            bad = bad || (nrows + n_new > min(max_persons, kMaxSubsetCap));   // overflow bits are set in order below
+            if (!__any_sync(0xffffffffu, bad)) {
+                if (found == 1) {
+                    if (colB[j1] != pB) {
+                        colB[j1] = pB;
+                        s_ct[j1] = __dadd_rn(s_ct[j1], 1.0);
+                        s_sc[j1] = __dadd_rn(s_sc[j1], __dadd_rn(s_score[pB], sc));
+                    }
+                } else if ((new_m >> lane) & 1u) {
+                    const int r = nrows + __popc(new_m & ((1u << lane) - 1));
+#pragma unroll
+                    for (int c = 0; c < kParts; c++) s_id[c * kAsmRowCap + r] = (c == ia) ? pA : ((c == ib) ? pB : -1);
+                    s_sc[r] = __dadd_rn(__dadd_rn(__dadd_rn(0.0, s_score[pA]), s_score[pB]), sc);
+                    s_ct[r] = 2.0;
+                }
+                nrows += n_new;
+                __syncwarp();
+                continue;
+            }
+        }
+        for (int i = i0; i < i0 + n_chunk; i++) {
             const bool in_smem = s_off[k] + i < kAsmConnRows;
             const double *row = in_smem ? s_conn + (s_off[k] + i) * 3 : conn + i * 5;
             const int pA = (int)row[0], pB = (int)row[1];
@@ -1323,6 +1368,7 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
                 }
             }
             __syncwarp();
+        }
         }
     }
     // prune: fewer than 4 parts or mean score < 0.4 (eval...:411-415); rows leave as float64
