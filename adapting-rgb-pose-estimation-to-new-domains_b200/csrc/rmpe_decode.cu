@@ -434,6 +434,7 @@ __global__ void __launch_bounds__(128) k_axis_tables(const __grid_constant__ Axi
 constexpr int kMsJobsPerLaunch = kChunkFrames;
 constexpr float kScreenDelta = 1.2e-5f;
 constexpr int kPlanThreads = 256;
+constexpr int kPlanStride = 13 * kHeatC;     // 247 of the 256 threads scan the blob: thread t stays on channel t % 19
 
 struct MsScale {
     const float *heat;
@@ -506,14 +507,32 @@ __global__ void __launch_bounds__(kPlanThreads) k_screen_plan(const __grid_const
         const MsScale &S = J.sc[sc];
         const int r0 = s_rng[sc][0], c0 = s_rng[sc][2];
         const int nrows = s_rng[sc][1] - r0 + 1, rowlen = (s_rng[sc][3] - c0 + 1) * kHeatC;
-        // coalesced row segments of the NHWC blob; element e of a segment belongs to channel e % 19
-        for (int r = 0; r < nrows; r++) {
-            const float *row = S.heat + ((size_t)(r0 + r) * S.w + c0) * kHeatC;
-            for (int e = tid; e < rowlen; e += kPlanThreads) {
-                const float v = row[e];
-                int *dst = (v > 0.f) ? &s_bpos[sc][0] : &s_bneg[sc][0];       // one atomic per element, no divergence
-                atomicMax(dst + e % kHeatC, __float_as_int(fabsf(v)));
+        // coalesced row segments of the NHWC blob; element e of a segment belongs to channel e % 19.  13 x 19 = 247
+        // threads walk a segment with stride 247, so a thread stays on ONE channel and keeps its maxima in registers;
+        // the 13 threads of a channel meet in shared memory once per scale.
+        float vpos = 0.f, vneg = 0.f;
+        if (tid < kPlanStride) {
+            const float *base = S.heat + ((size_t)r0 * S.w + c0) * kHeatC;
+            const size_t rstride = (size_t)S.w * kHeatC;
+            int r = 0;
+            for (; r + 1 < nrows; r += 2) {                       // two rows in flight
+                const float *row0 = base + (size_t)r * rstride, *row1 = row0 + rstride;
+                for (int e = tid; e < rowlen; e += kPlanStride) {
+                    const float v0 = row0[e], v1 = row1[e];
+                    vpos = fmaxf(vpos, fmaxf(v0, v1));
+                    vneg = fmaxf(vneg, fmaxf(-v0, -v1));
+                }
             }
+            if (r < nrows) {
+                const float *row0 = base + (size_t)r * rstride;
+                for (int e = tid; e < rowlen; e += kPlanStride) {
+                    const float v0 = row0[e];
+                    vpos = fmaxf(vpos, v0);
+                    vneg = fmaxf(vneg, -v0);
+                }
+            }
+            if (vpos > 0.f) atomicMax(&s_bpos[sc][tid % kHeatC], __float_as_int(vpos));
+            if (vneg > 0.f) atomicMax(&s_bneg[sc][tid % kHeatC], __float_as_int(vneg));
         }
     }
     __syncthreads();

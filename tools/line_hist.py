@@ -36,10 +36,12 @@ for r in rows:
         continue
     key = (fname, int(r[0]))
     a = agg[key]
+    def num(x):
+        return int(x) if x.isdigit() else 0
     a[0] += e
-    a[1] += int(r[isamp] or 0)
-    a[2] += int(r[iw] or 0)
-    a[3] += int(r[iwi] or 0)
+    a[1] += num(r[isamp])
+    a[2] += num(r[iw])
+    a[3] += num(r[iwi])
     a[4] = r[1]
 tot = sum(a[0] for a in agg.values())
 tots = sum(a[1] for a in agg.values())
