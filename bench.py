@@ -335,6 +335,11 @@ def main():
         traffic_db = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:  # noqa: BLE001
         pass
+    limiters = {}
+    try:
+        limiters = json.load(open(os.path.join(ROOT, "profiles", "limiters.json")))
+    except Exception:  # noqa: BLE001
+        pass
     roofline = None
     if kernels:
         top = max(kernels, key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches"])
@@ -345,7 +350,9 @@ def main():
                     "peak_source": peak_src, "kernel_ms": kt["ms_per_launch"],
                     "kernel_share_of_step": kt["ms_per_launch"] * kt["launches"] / tot if tot else None,
                     "step_achieved": per["step"] * BATCH / (ms * 1e-3) / 1e9,
-                    "step_frac": per["step"] * BATCH / (ms * 1e-3) / 1e9 / peak}
+                    "step_frac": per["step"] * BATCH / (ms * 1e-3) / 1e9 / peak,
+                    # what ncu says holds the kernel below the HBM roofline (from the committed capture, not live)
+                    "limiter": limiters.get(top)}
 
     # ---- e2e: host (pinned) buffers in, host buffers out, through rmpe_gt_batch_host ----
     e2e = None
