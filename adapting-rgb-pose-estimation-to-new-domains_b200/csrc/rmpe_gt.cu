@@ -1215,9 +1215,10 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
             fa.mask_f64 = (b->flags & RMPE_GT_LABELS_F64) ? 1 : 0;
             fa.foot_cap = 0;
             const int n_items = b->batch * kTilesPerSample;
-            // default: 32-bit (B,G,R,mask) footprint words, 8 tile groups (1024 threads) per SM.  RMPE_WARP_GROUPS = 4 | 6 | 8
-            // and RMPE_WARP_WIDE=1 (16-byte pre-packed footprint entries, 4 | 5 | 6 groups) are kept for A/B tests:
-            // measured on B200 (GT batch 256): words 8 groups 0.354 ms, 6 groups 0.365 ms; wide 5 groups 0.393 ms --
+            // default: 32-bit (B,G,R,mask) footprint words, 7 tile groups (896 threads, 72 registers, no spills) per SM.
+            // RMPE_WARP_GROUPS = 4 | 6 | 7 | 8 and RMPE_WARP_WIDE=1 (16-byte pre-packed footprint entries, 4 | 5 | 6
+            // groups) are kept for A/B tests; measured on B200 (GT batch 256): words 7 or 8 groups 0.354 ms (8 groups
+            // spill and leave a smaller footprint buffer), 6 groups 0.365 ms, 4 groups 0.404 ms; wide 5 groups 0.393 ms --
             // the wide layout halves the issued instructions of the taps but pays for it in staging wavefronts, and
             // both are bound by the shared-memory/L1 data pipe (profiles/r01r).
             static const bool wide = [] {
@@ -1227,7 +1228,7 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
             static const int ng = [] {
                 const char *e = getenv("RMPE_WARP_GROUPS");
                 int v = e ? atoi(e) : 0;
-                return (v == 4 || v == 5 || v == 6 || v == 8) ? v : 0;
+                return (v == 4 || v == 5 || v == 6 || v == 7 || v == 8) ? v : 0;
             }();
             ProfScope ps("k_warp_fused", st);
             int rc;
@@ -1236,7 +1237,8 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
                                    : launch_fused<5, true>(fa, want_mask, n_items, T.sm_count, st);
             else rc = ng == 4 ? launch_fused<4, false>(fa, want_mask, n_items, T.sm_count, st)
                     : ng == 6 ? launch_fused<6, false>(fa, want_mask, n_items, T.sm_count, st)
-                              : launch_fused<8, false>(fa, want_mask, n_items, T.sm_count, st);
+                    : ng == 8 ? launch_fused<8, false>(fa, want_mask, n_items, T.sm_count, st)
+                              : launch_fused<7, false>(fa, want_mask, n_items, T.sm_count, st);
             if (rc != RMPE_OK) return rc;
             mask_done = want_mask;
         }
