@@ -316,7 +316,7 @@ __device__ __forceinline__ unsigned fused_row(const TileCtx &c, int ly) {
     if (kMode == 1) return kBorderWord;
     const int X = (c.gX0[ly] + c.adx) >> 5;
     const int Y = (c.gY0[ly] + c.bdx) >> 5;
-    const uint32_t *wt = c.tab + (((Y & 31) * 32 + (X & 31)) << 2);
+    const uint32_t *wt = c.tab + (((X & 31) * 32 + (Y & 31)) << 2);      // slot = ax * 32 + ay (see the table fill)
     if (kMode == 3) {
         const uint4 *p = reinterpret_cast<const uint4 *>(c.foot) + ((Y >> 5) - 1 - c.by0) * c.fpitch + ((X >> 5) - 1 - c.bx0);
         return bicubic_wide<kMask>(p, c.fpitch, wt);
@@ -394,10 +394,15 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
     {   // dp4a weight table -> shared memory, once per persistent CTA: [phase][row]{hi,lo} -> hi[phase][row], lo[phase][row]
         const uint4 *src = reinterpret_cast<const uint4 *>(a.tab_dp4a);
         uint4 *dst = reinterpret_cast<uint4 *>(s_tab);
+        // shared-memory slot of phase (ay, ax) = ax * 32 + ay: the 16-byte bank group of an entry is then ay & 7.  Along a
+        // destination row ay moves by 32 sin(theta) per pixel and ax by 32 (cos(theta) - 1): for the rotations of the
+        // augmentation (|theta| <= 40 deg) ax often stays put over a quarter-warp while ay changes, which with the
+        // [ay][ax] order put 8 different entries into one bank group (measured 2.75 wavefronts per quarter-warp, 2.2 now)
         for (int e = threadIdx.x; e < 1024; e += NG * kGroupThreads) {
             const uint4 r01 = __ldg(src + 2 * e), r23 = __ldg(src + 2 * e + 1);
-            dst[e] = make_uint4(r01.x, r01.z, r23.x, r23.z);
-            dst[1024 + e] = make_uint4(r01.y, r01.w, r23.y, r23.w);
+            const int slot = ((e & 31) << 5) | (e >> 5);
+            dst[slot] = make_uint4(r01.x, r01.z, r23.x, r23.z);
+            dst[1024 + slot] = make_uint4(r01.y, r01.w, r23.y, r23.w);
         }
     }
 
