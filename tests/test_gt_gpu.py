@@ -320,3 +320,50 @@ def test_raw_iterator_batched_equals_per_sample(rmpe):
     assert np.array_equal(many[0][0], np.transpose(oimg, (2, 0, 1)))
     assert np.array_equal(many[0][1], omask) and np.array_equal(many[0][3], oj)
     assert np.abs(many[0][2] - olab).max() <= LABEL_TOL
+
+
+_VARIANT_SCRIPT = r"""
+import hashlib, sys
+import numpy as np
+sys.path.insert(0, %r)
+import rmpe_b200
+rmpe_b200.lib.ensure_init(0)
+h = hashlib.sha256()
+for seed0, P, hw in ((700, 3, (368, 368)), (720, 2, (240, 320)), (740, 4, (427, 640)), (760, 6, (368, 368))):
+    b = rmpe_b200.synth.gt_batch(6, n_persons=P, seed0=seed0, src_hw=hw)
+    flip = np.array([a[0] for a in b["augs"]], np.uint8)
+    # person scales from 0.3 to 1.5 of the crop: up-scaling, down-scaling past the staging buffer (generic taps), borders
+    ss = b["scale_self"] * np.random.RandomState(seed0).uniform(0.5, 2.5, 6)
+    M = rmpe_b200.batch.aug_affine(flip, [a[1] for a in b["augs"]], [a[2] for a in b["augs"]], [a[3] for a in b["augs"]],
+                                   b["centers"], ss)
+    r = rmpe_b200.batch.gt_batch_host(b["imgs"], b["masks"], b["joints"], b["n_persons"], M, flip, want_count=True)
+    for k in ("img", "mask", "labels", "joints", "count", "status"):
+        h.update(np.ascontiguousarray(r[k]).tobytes())
+print("SHA", h.hexdigest())
+"""
+
+
+@pytest.mark.parametrize("env", [{"RMPE_WARP_WIDE": "1"}, {"RMPE_WARP_WIDE": "1", "RMPE_WARP_GROUPS": "6"},
+                                 {"RMPE_WARP_GROUPS": "4"}, {"RMPE_WARP_GROUPS": "8"}, {"RMPE_RASTER_GROUPS": "2"},
+                                 {"RMPE_RASTER_GROUPS": "4"}],
+                         ids=["wide5", "wide6", "groups4", "groups8", "raster2", "raster4"])
+def test_kernel_variants_are_bit_identical(rmpe, env):
+    """The A/B variants kept in the library (footprint layout, tile groups per SM, rasteriser plane groups) read their
+    switch once per process: each runs in its own interpreter and must reproduce the default's outputs bit for bit."""
+    import os
+    import subprocess
+    import sys
+    from cases import ROOT
+
+    def run(extra):
+        e = dict(os.environ)
+        for k in ("RMPE_WARP_WIDE", "RMPE_WARP_GROUPS", "RMPE_RASTER_GROUPS"):
+            e.pop(k, None)
+        e.update(extra)
+        out = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT % ROOT], env=e, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return [l for l in out.stdout.splitlines() if l.startswith("SHA")][0]
+
+    if not hasattr(test_kernel_variants_are_bit_identical, "_default"):
+        test_kernel_variants_are_bit_identical._default = run({})
+    assert run(env) == test_kernel_variants_are_bit_identical._default
