@@ -355,7 +355,7 @@ __device__ __forceinline__ void store_row(const RowStore &rs, int j, unsigned bg
 }
 
 // the 8 destination rows (one cell row) of a warp: taps, stores, and the 8x8 -> 1 mask reduction of cv2.resize
-// returns the cell's float32 accumulator (valid in every lane of the cell's 8-lane group)
+// returns the cell's float32 accumulator (valid in lanes 3 and 4 of the cell's 8-lane group)
 template <int kMode, bool kWantMask>
 __device__ __forceinline__ float cell_rows(const TileCtx &c, const RowStore &rs, int r0, int mw, float b0, float b1) {
 #pragma unroll
@@ -367,10 +367,11 @@ __device__ __forceinline__ float cell_rows(const TileCtx &c, const RowStore &rs,
         store_row(rs, j, v4);
         if (kWantMask) {
             // cv2.resize horizontal pass: exact int32 sum of (-192,1216,1216,-192) x cols 8c+2..8c+5
+            // (only lanes 2..5 of a cell carry a weight: 2+3 and 4+5 meet with xor 1, lanes 3 and 4 swap sums with xor 7;
+            // the total is valid in lanes 3 and 4 of the cell)
             int v = (int)(v4 >> 24) * mw;
             v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 7);
             const float Sj = (float)v;
             macc = (j == 5) ? Sj * b0 : fmaf(Sj, (j == 2) ? b0 : b1, macc);
         }
@@ -633,7 +634,7 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
             else if (staged) macc = cell_rows<0, kWantMask>(c, rs, r0, mw, b0, b1);
             else if (outside) macc = cell_rows<1, kWantMask>(c, rs, r0, mw, b0, b1);
             else macc = cell_rows<2, kWantMask>(c, rs, r0, mw, b0, b1);
-            if (kWantMask && l7 == 0 && lane_on) {
+            if (kWantMask && l7 == 3 && lane_on) {
                 // rint, saturate; then /255.  (py_rmpe_transformer.py:92,95)
                 const int iv = min(255, max(0, __float2int_rn(macc)));
                 const double m = __ddiv_rn((double)iv, 255.0);
