@@ -7,6 +7,8 @@
 //   py_rmpe_server/py_rmpe_heatmapper.py:32-138    Heatmapper.create_heatmaps -> k_raster
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "rmpe_common.cuh"
 
 namespace rmpe {
@@ -145,6 +147,7 @@ struct FusedArgs {
     int chw;
     int mask_f64;
     int foot_cap;   // footprint capacity of one group, in pixels (32-bit words)
+    int32_t *counter;   // next tile to hand out (zero at launch): tile groups take tiles as they finish theirs
 };
 
 __device__ __forceinline__ void group_bar(int group) {
@@ -447,24 +450,33 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
         return sane;
     };
 
-    const int stride = gridDim.x * NG;
-    int item = blockIdx.x * NG + group;
+    // Tiles are handed out dynamically (border tiles are cheap, strongly rotated ones expensive): q[k & 3] is the tile of
+    // pass k; thread 0 of the group draws the tile of pass k+3 while pass k runs, so geometry (two passes ahead) and the
+    // L2 prefetch (one ahead) still know their tiles, and the atomic's latency is never waited for.
+    int *q = geo + 3 * kGeoInts;
+    if (t == 0) {
+        q[0] = atomicAdd(a.counter, 1); q[1] = atomicAdd(a.counter, 1); q[2] = atomicAdd(a.counter, 1);
+    }
+    group_bar(group);
     if (t < 2 * kTile) {
-        if (item < n_items) geometry(item, 0);
-        if (item + stride < n_items) geometry(item + stride, 1);
+        if (q[0] < n_items) geometry(q[0], 0);
+        if (q[1] < n_items) geometry(q[1], 1);
     }
     __syncthreads();   // weight table + first two geometries
 
     // bounding box of the current tile: computed once (for the L2 prefetch, one tile ahead) and carried over
     int mnx = 0, mxx = 0, mny = 0, mxy = 0;
     bool sane = false;
-    if (item < n_items) {
-        const int tt = item % kTilesPerSample;
+    if (q[0] < n_items) {
+        const int tt = q[0] % kTilesPerSample;
         const int ty = tt / kTilesX, tx = tt - ty * kTilesX;
         sane = bbox(geo, min(kTile, kOutW - tx * kTile), min(kTile, kOutH - ty * kTile), mnx, mxx, mny, mxy);
     }
 
-    for (int k = 0; item < n_items; item += stride, k++) {
+    for (int k = 0;; k++) {
+        const int item = q[k & 3];
+        if (item >= n_items) break;
+        const int item1 = q[(k + 1) & 3], item2 = q[(k + 2) & 3];
         const int sample = item / kTilesPerSample;
         const int tt = item - sample * kTilesPerSample;
         const int ty = tt / kTilesX, tx = tt - ty * kTilesX;
@@ -579,11 +591,12 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
 
         // two tiles ahead: geometry; one tile ahead: bounding box (kept for the next pass) and its lines pulled into L2
         // -- all of it overlaps this tile's taps
-        if (item + 2 * stride < n_items && t < 2 * kTile) geometry(item + 2 * stride, (k + 2) % 3);
+        if (t == 0) q[(k + 3) & 3] = atomicAdd(a.counter, 1);    // slot of pass k-1: free since its closing barrier
+        if (item2 < n_items && t < 2 * kTile) geometry(item2, (k + 2) % 3);
         int nmnx = 0, nmxx = 0, nmny = 0, nmxy = 0;
         bool nsane = false;
-        if (item + stride < n_items) {
-            const int ni = item + stride;
+        if (item1 < n_items) {
+            const int ni = item1;
             const int ns = ni / kTilesPerSample, ntt = ni - ns * kTilesPerSample;
             const int nty = ntt / kTilesX, ntx = ntt - nty * kTilesX;
             nsane = bbox(geo + ((k + 1) % 3) * kGeoInts, min(kTile, kOutW - ntx * kTile), min(kTile, kOutH - nty * kTile),
@@ -1161,6 +1174,9 @@ template <int NG, bool kWide>
 static int launch_fused(const FusedArgs &fa_, bool want_mask, int n_items, int sm_count, cudaStream_t st) {
     FusedArgs fa = fa_;
     fa.foot_cap = fused_foot_cap(NG);
+    static std::atomic<unsigned> ring{0};
+    fa.counter = tables().counters + (size_t)(ring.fetch_add(1) % kCounterRing) * kCounterStride;
+    RMPE_CUDA_TRY(cudaMemsetAsync(fa.counter, 0, sizeof(int32_t), st));
     const size_t smem = fused_smem_bytes(NG);
     static bool attr_set = false;
     if (!attr_set) {

@@ -215,6 +215,7 @@ extern "C" int rmpe_init(int device) {
     g.tab.bicubic_i16 = (const int16_t *)g.tab_mem;
     g.tab.bicubic_dp4a = (const uint32_t *)((uint8_t *)g.tab_mem + b16);
     g.tab.sm_count = prop.multiProcessorCount;
+    RMPE_CUDA_TRY(cudaMalloc(&g.tab.counters, (size_t)kCounterRing * kCounterStride * sizeof(int32_t)));
     RMPE_CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     for (int i = 0; i < 3; i++) RMPE_CUDA_TRY(cudaStreamCreateWithFlags(&g.pipe[i], cudaStreamNonBlocking));
     g.device = device;
@@ -228,6 +229,7 @@ extern "C" void rmpe_shutdown(void) {
     cudaSetDevice(g.device);
     cudaDeviceSynchronize();
     if (g.tab_mem) cudaFree(g.tab_mem);
+    if (g.tab.counters) cudaFree(g.tab.counters);
     if (g.arena.dev) cudaFree(g.arena.dev);
     if (g.stream) cudaStreamDestroy(g.stream);
     for (int i = 0; i < 3; i++) { if (g.pipe[i]) cudaStreamDestroy(g.pipe[i]); g.pipe[i] = nullptr; }
