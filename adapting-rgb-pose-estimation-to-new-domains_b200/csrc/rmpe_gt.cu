@@ -333,10 +333,9 @@ __device__ __forceinline__ unsigned fused_row(const TileCtx &c, int ly) {
     return generic_bgrm(c.img, c.msk, c.H, c.W, c.ipitch, c.mpitch, X, Y, c.tab16, kMask);
 }
 
-// per-warp constants of the row stores: HWC packs B,G,R of 32 neighbouring pixels into 24 words with two shuffles
+// per-warp constants of the row stores: HWC packs B,G,R of 32 neighbouring pixels into 24 words with one shuffle
 struct RowStore {
-    uint8_t *op;        // HWC: word `lane` of the first row of the warp; CHW: pixel `lane` of plane 0
-    int pk_lane;
+    uint8_t *op;        // HWC: this lane's word of the first row of the warp; CHW: pixel `lane` of plane 0
     unsigned pk_sel;
     bool on;
     int chw;
@@ -345,10 +344,10 @@ struct RowStore {
 // store destination row j (0..7) of the warp, one pixel per lane
 __device__ __forceinline__ void store_row(const RowStore &rs, int j, unsigned bgr) {
     if (!rs.chw) {
-        // 24 words of the 96-byte row: word w = bytes 4w..4w+3 = pixels floor(4w/3), +1
-        const unsigned a = __shfl_sync(0xffffffffu, bgr, rs.pk_lane);
-        const unsigned b = __shfl_sync(0xffffffffu, bgr, rs.pk_lane + 1);
-        if (rs.on) *reinterpret_cast<uint32_t *>(rs.op + j * (kOutW * 3)) = __byte_perm(a, b, rs.pk_sel);
+        // 24 words of the 96-byte row.  Pixel l starts at byte 3l, so lane l = 4k + m (m = 0, 1, 2) holds, together with
+        // its right neighbour's pixel, exactly the aligned word 3k + m (bytes 12k + 4m ..): ONE shuffle per row.
+        const unsigned nb = __shfl_down_sync(0xffffffffu, bgr, 1);
+        if (rs.on) *reinterpret_cast<uint32_t *>(rs.op + j * (kOutW * 3)) = __byte_perm(bgr, nb, rs.pk_sel);
     } else if (rs.on) {
         uint8_t *o = rs.op + j * kOutW;
         o[0] = (uint8_t)bgr;
@@ -412,8 +411,8 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
 
     const int l7 = lane & 7;
     const int mw = (l7 == 3 || l7 == 4) ? 1216 : ((l7 == 2 || l7 == 5) ? -192 : 0);
-    const int pk_lane = (4 * lane) / 3;                       // HWC row packing (store_row)
-    const unsigned pk_sel = (4 * lane) % 3 == 0 ? 0x4210u : ((4 * lane) % 3 == 1 ? 0x5421u : 0x6542u);
+    const int pk_word = 3 * (lane >> 2) + (lane & 3);         // HWC row packing (store_row): lanes 4k+3 store nothing
+    const unsigned pk_sel = (lane & 3) == 0 ? 0x4210u : ((lane & 3) == 1 ? 0x5421u : 0x6542u);
     const float sc = 1.0f / 4194304.0f;                       // 2^-22
     const float b0 = -192.0f * sc, b1 = 1216.0f * sc;
 
@@ -638,10 +637,10 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
             const int r0 = 8 * warp;
             uint8_t *out_sample = a.out_img + (size_t)sample * (3 * kOutW * kOutH);
             RowStore rs;
-            rs.chw = a.chw; rs.pk_lane = pk_lane; rs.pk_sel = pk_sel;
+            rs.chw = a.chw; rs.pk_sel = pk_sel;
             rs.op = a.chw ? out_sample + (size_t)(y0 + r0) * kOutW + x0 + lane
-                          : out_sample + ((size_t)(y0 + r0) * kOutW + x0) * 3 + 4 * lane;
-            rs.on = a.chw ? lane_on : (4 * lane < 3 * tw);
+                          : out_sample + ((size_t)(y0 + r0) * kOutW + x0) * 3 + 4 * pk_word;
+            rs.on = a.chw ? lane_on : ((lane & 3) != 3 && 4 * pk_word < 3 * tw);
             float macc;
             if (kWide && wide) macc = cell_rows<3, kWantMask>(c, rs, r0, mw, b0, b1);
             else if (staged) macc = cell_rows<0, kWantMask>(c, rs, r0, mw, b0, b1);
