@@ -305,7 +305,7 @@ __device__ __noinline__ unsigned generic_bgrm(const uint8_t *__restrict__ img, c
 struct TileCtx {
     const uint32_t *foot;
     const uint32_t *tab;
-    const int *gX0, *gY0;
+    const int2 *gXY;                   // {X0[y], Y0[y]} of the tile's rows
     int adx, bdx, fpitch, bx0, by0;   // fpitch: words (mode 0) or 16-byte entries (mode 3)
     const uint8_t *img, *msk;
     int H, W, ipitch, mpitch;
@@ -317,8 +317,9 @@ struct TileCtx {
 template <int kMode, bool kMask>
 __device__ __forceinline__ unsigned fused_row(const TileCtx &c, int ly) {
     if (kMode == 1) return kBorderWord;
-    const int X = (c.gX0[ly] + c.adx) >> 5;
-    const int Y = (c.gY0[ly] + c.bdx) >> 5;
+    const int2 xy0 = c.gXY[ly];        // one 64-bit broadcast load per row
+    const int X = (xy0.x + c.adx) >> 5;
+    const int Y = (xy0.y + c.bdx) >> 5;
     const uint32_t *wt = c.tab + (((X & 31) * 32 + (Y & 31)) << 2);      // slot = ax * 32 + ay (see the table fill)
     if (kMode == 3) {
         const uint4 *p = reinterpret_cast<const uint4 *>(c.foot) + ((Y >> 5) - 1 - c.by0) * c.fpitch + ((X >> 5) - 1 - c.bx0);
@@ -425,11 +426,11 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
         double iM[6];
         const bool ok = invert_affine(a.M + 6 * sample, iM);
         if (t < kTile) {
-            g[t] = warp_row_term(iM[1], iM[2], ty * kTile + t);
-            g[kTile + t] = warp_row_term(iM[4], iM[5], ty * kTile + t);
+            g[2 * t] = warp_row_term(iM[1], iM[2], ty * kTile + t);
+            g[2 * t + 1] = warp_row_term(iM[4], iM[5], ty * kTile + t);
         } else {
-            g[2 * kTile + t - kTile] = warp_col_term(iM[0], tx * kTile + t - kTile);
-            g[3 * kTile + t - kTile] = warp_col_term(iM[3], tx * kTile + t - kTile);
+            g[2 * kTile + 2 * (t - kTile)] = warp_col_term(iM[0], tx * kTile + t - kTile);
+            g[2 * kTile + 2 * (t - kTile) + 1] = warp_col_term(iM[3], tx * kTile + t - kTile);
         }
         if (t == 0 && !ok && tt == 0) atomicOr(a.status + sample, RMPE_ST_SINGULAR);
     };
@@ -441,7 +442,7 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             const int cx = (c & 1) ? tw - 1 : 0, cy = (c & 2) ? th - 1 : 0;
-            const int qx = (g[cy] + g[2 * kTile + cx]) >> 10, qy = (g[kTile + cy] + g[3 * kTile + cx]) >> 10;
+            const int qx = (g[2 * cy] + g[2 * kTile + 2 * cx]) >> 10, qy = (g[2 * cy + 1] + g[2 * kTile + 2 * cx + 1]) >> 10;
             sane = sane && qx > -30000 && qx < 30000 && qy > -30000 && qy < 30000;  // no short saturation
             mnx = min(mnx, qx - 1); mxx = max(mxx, qx + 2);
             mny = min(mny, qy - 1); mxy = max(mxy, qy + 2);
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
         const RmpeSrcDesc d = a.desc[sample];
         const uint8_t *img = a.src_img + d.img_offset;
         const uint8_t *msk = a.src_mask + d.mask_offset;
-        const int *gX0 = geo + (k % 3) * kGeoInts, *gY0 = gX0 + kTile, *gad = gY0 + kTile, *gbd = gad + kTile;
+        const int *gcur = geo + (k % 3) * kGeoInts;      // {X0,Y0}[32] then {ad,bd}[32], interleaved
 
         // 4-byte aligned sources are read with plain 32-bit loads; the footprint then starts on a multiple of 4
         const bool al4 = ((((size_t)img | (size_t)msk) & 3) == 0) && (((d.img_pitch | d.mask_pitch) & 3) == 0);
@@ -629,8 +630,9 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
         if (8 * warp < th) {
             TileCtx c;
             const int gl = min(lane, tw - 1);     // lanes beyond the tile edge repeat its last pixel (never stored)
-            c.foot = foot; c.tab = s_tab; c.gX0 = gX0; c.gY0 = gY0;
-            c.adx = gad[gl]; c.bdx = gbd[gl]; c.fpitch = wide ? wpitch : fpitch; c.bx0 = bx0; c.by0 = by0;
+            c.foot = foot; c.tab = s_tab; c.gXY = reinterpret_cast<const int2 *>(gcur);
+            const int2 abd = reinterpret_cast<const int2 *>(gcur + 2 * kTile)[gl];
+            c.adx = abd.x; c.bdx = abd.y; c.fpitch = wide ? wpitch : fpitch; c.bx0 = bx0; c.by0 = by0;
             c.img = img; c.msk = msk; c.H = d.height; c.W = d.width; c.ipitch = d.img_pitch; c.mpitch = d.mask_pitch;
             c.tab16 = a.tab;
             const bool lane_on = lane < tw;
