@@ -489,9 +489,11 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
 
         // 4-byte aligned sources are read with plain 32-bit loads; the footprint then starts on a multiple of 4
         const bool al4 = ((((size_t)img | (size_t)msk) & 3) == 0) && (((d.img_pitch | d.mask_pitch) & 3) == 0);
-        const int bx0 = al4 ? (mnx & ~3) : mnx, by0 = mny;
+        // 8-byte aligned sources (the 32-bit word layout only): 64-bit loads, 8 pixels per thread, footprint on a multiple of 8
+        const bool al8 = !kWide && ((((size_t)img | (size_t)msk) & 7) == 0) && (((d.img_pitch | d.mask_pitch) & 7) == 0);
+        const int bx0 = al8 ? (mnx & ~7) : (al4 ? (mnx & ~3) : mnx), by0 = mny;
         const int fw = mxx - bx0 + 1, fh = mxy - mny + 1;
-        const int fwa = (fw + 3) & ~3;
+        const int fwa = al8 ? ((fw + 7) & ~7) : ((fw + 3) & ~3);
         int fpitch = (fwa + 31) & ~31;     // = 0 (mod 32): the bank of a tap is its column, whatever its row
         if ((long long)fpitch * fh > a.foot_cap) fpitch = fwa;
         const bool outside = sane && (mxx < 0 || mnx >= d.width || mxy < 0 || mny >= d.height);
@@ -557,7 +559,43 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
         }
 
         // ---- stage the footprint as (B,G,R,mask) words: one thread = 4 pixels = one 16-byte store ----
-        if (staged) {
+        if (staged && al8) {
+            // 8 threads x 8 pixels per footprint row (three 64-bit image loads + one 64-bit mask load, two 16-byte stores);
+            // two rows (r, r+16) in flight per thread and pass
+            for (int r = t >> 3; r < fh; r += 2 * (kGroupThreads / 8))
+            for (int c = (t & 7) << 3; c < fwa; c += 64) {
+                const int xx = bx0 + c;
+                const int r1 = r + kGroupThreads / 8;
+                const int ya = by0 + r, yb = by0 + r1;
+                const bool xin = xx >= 0 && xx + 7 < d.width;
+                const bool fa = xin && (unsigned)ya < (unsigned)d.height;
+                const bool fb = xin && (unsigned)yb < (unsigned)d.height && r1 < fh;
+                uint2 qa0, qa1, qa2, qam, qb0, qb1, qb2, qbm;
+                qa0 = qa1 = qa2 = qam = qb0 = qb1 = qb2 = qbm = make_uint2(0u, 0u);
+                if (fa) {
+                    const uint2 *ip = reinterpret_cast<const uint2 *>(img + (size_t)ya * d.img_pitch + 3 * xx);
+                    qa0 = __ldg(ip); qa1 = __ldg(ip + 1); qa2 = __ldg(ip + 2);
+                    qam = __ldg(reinterpret_cast<const uint2 *>(msk + (size_t)ya * d.mask_pitch + xx));
+                }
+                if (fb) {
+                    const uint2 *ip = reinterpret_cast<const uint2 *>(img + (size_t)yb * d.img_pitch + 3 * xx);
+                    qb0 = __ldg(ip); qb1 = __ldg(ip + 1); qb2 = __ldg(ip + 2);
+                    qbm = __ldg(reinterpret_cast<const uint2 *>(msk + (size_t)yb * d.mask_pitch + xx));
+                }
+                uint4 *dst = reinterpret_cast<uint4 *>(foot + r * fpitch + c);
+                dst[0] = fa ? bgrm_pack4(qa0.x, qa0.y, qa1.x, qam.x)
+                            : bgrm_load4(img, msk, d.height, d.width, d.img_pitch, d.mask_pitch, ya, xx);
+                dst[1] = fa ? bgrm_pack4(qa1.y, qa2.x, qa2.y, qam.y)
+                            : bgrm_load4(img, msk, d.height, d.width, d.img_pitch, d.mask_pitch, ya, xx + 4);
+                if (r1 < fh) {
+                    dst = reinterpret_cast<uint4 *>(foot + r1 * fpitch + c);
+                    dst[0] = fb ? bgrm_pack4(qb0.x, qb0.y, qb1.x, qbm.x)
+                                : bgrm_load4(img, msk, d.height, d.width, d.img_pitch, d.mask_pitch, yb, xx);
+                    dst[1] = fb ? bgrm_pack4(qb1.y, qb2.x, qb2.y, qbm.y)
+                                : bgrm_load4(img, msk, d.height, d.width, d.img_pitch, d.mask_pitch, yb, xx + 4);
+                }
+            }
+        } else if (staged) {
             // 16 threads x 4 pixels per footprint row; two rows (r, r+8) in flight per thread and pass
             for (int r = t >> 4; r < fh; r += 2 * (kGroupThreads / 16))
             for (int c = (t & 15) << 2; c < fwa; c += 64) {
