@@ -5,6 +5,7 @@
 //   py_rmpe_server/py_rmpe_transformer.py:83-114  Transformer.transform      -> k_warp_fused / k_warp_simple,
 //                                                                               k_mask46, joints in k_raster
 //   py_rmpe_server/py_rmpe_heatmapper.py:32-138    Heatmapper.create_heatmaps -> k_raster
+#include <stddef.h>
 #include <stdlib.h>
 
 #include <atomic>
@@ -784,9 +785,28 @@ struct RasterArgs {
 
 struct LimbRec {
     double x1, y1, xD, yD, norm2;
+    double tn, en;               // thre * norm2 and its half-ulp allowance (band_on); en = 0: use the division
     float ux, uy;
-    int minx, maxx, miny, maxy;  // cell box, max exclusive; valid iff maxx > minx
+    int minx, maxx, miny, maxy;  // cell box, max exclusive; valid iff maxx > minx  (16-byte aligned: one 128-bit load)
 };
+static_assert(sizeof(LimbRec) == 80 && offsetof(LimbRec, minx) == 64, "LimbRec layout");
+
+// thre * norm2 and the allowance of band_on for a power-of-two thre (8.0 in the reference); 0 otherwise
+__device__ __forceinline__ void band_prepare(LimbRec &r, double thre) {
+    const bool pow2 = thre > 0.0 && (__double2hiint(thre) & 0x000FFFFF) == 0 && __double2loint(thre) == 0;
+    r.tn = __dmul_rn(thre, r.norm2);                 // exact for a power of two
+    r.en = pow2 ? __dmul_rn(r.tn, 1.1102230246251565e-16) : 0.0;   // * 2^-53: half an ulp of thre, times norm2 (exact)
+    if (!(r.tn < 1e300) || !(r.en > 1e-300)) r.en = 0.0;
+}
+
+// py_rmpe_heatmapper.py:116-118: abs(dd / norm) <= thre with dd / norm rounded to f64.  RN(q) <= thre  <=>  q <= thre (1 +
+// 2^-53) (the midpoint above a power of two ties to even, i.e. down)  <=>  |dd| - thre*norm <= thre*norm*2^-53.  Both products
+// are exact for a power-of-two thre and the subtraction is exact wherever the answer is in doubt (|dd| within a factor 2 of
+// thre*norm, Sterbenz), so the test needs no division; any other thre takes the division.
+__device__ __forceinline__ bool band_on(const LimbRec &r, double dd, double thre) {
+    if (r.en > 0.0) return __dsub_rn(fabs(dd), r.tn) <= r.en;
+    return fabs(__ddiv_rn(dd, r.norm2)) <= thre;
+}
 
 constexpr int kRasterThreads = 288;
 constexpr int kRasterChunks = 2;  // 2 * 288 >= 529
@@ -933,12 +953,14 @@ __global__ void __launch_bounds__(kRasterThreads) k_raster(RasterArgs a) {
             // distances(): sqrt(xD**2 + yD**2); put_vector_maps: sqrt(dx*dx + dy*dy) -- same value
             r.norm2 = __dsqrt_rn(__dadd_rn(__dmul_rn(r.xD, r.xD), __dmul_rn(r.yD, r.yD)));
             r.ux = r.uy = 0.f;
+            r.tn = r.en = 0.0;
             if (jf[2] < 2.0 && jt[2] < 2.0) {
                 if (r.norm2 == 0.0) {
                     atomicOr(a.status + b, RMPE_ST_ZERO_LIMB);
                 } else {
                     r.ux = (float)__ddiv_rn(r.xD, r.norm2);
                     r.uy = (float)__ddiv_rn(r.yD, r.norm2);
+                    band_prepare(r, thre);
                     double mnx = r.x1 < x2 ? r.x1 : x2, mxx = r.x1 < x2 ? x2 : r.x1;
                     double mny = r.y1 < y2 ? r.y1 : y2, mxy = r.y1 < y2 ? y2 : r.y1;
                     int a0 = py_round(__ddiv_rn(__dsub_rn(mnx, thre), 8.0));
@@ -975,10 +997,9 @@ __global__ void __launch_bounds__(kRasterThreads) k_raster(RasterArgs a) {
                     for (int q = 0; q < 4; q++) {
                         if (x[q] >= r.minx && x[q] < r.maxx && y[q] >= r.miny && y[q] < r.maxy) {
                             double X = (double)(8 * x[q]), Y = (double)(8 * y[q]);
-                            double dd = __dsub_rn(__dmul_rn(r.xD, __dsub_rn(r.y1, Y)),
-                                                  __dmul_rn(__dsub_rn(r.x1, X), r.yD));
-                            dd = __ddiv_rn(dd, r.norm2);
-                            if (fabs(dd) <= thre) { vx[q] = r.ux; vy[q] = r.uy; cnt[q]++; }
+                            const double dd = __dsub_rn(__dmul_rn(r.xD, __dsub_rn(r.y1, Y)),
+                                                        __dmul_rn(__dsub_rn(r.x1, X), r.yD));
+                            if (band_on(r, dd, thre)) { vx[q] = r.ux; vy[q] = r.uy; cnt[q]++; }
                         }
                     }
                 }
@@ -1082,12 +1103,14 @@ __global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
         r.xD = __dsub_rn(x2, r.x1); r.yD = __dsub_rn(y2, r.y1);
         r.norm2 = __dsqrt_rn(__dadd_rn(__dmul_rn(r.xD, r.xD), __dmul_rn(r.yD, r.yD)));
         r.ux = r.uy = 0.f;
+        r.tn = r.en = 0.0;
         if (jf[2] < 2.0 && jt[2] < 2.0) {
             if (r.norm2 == 0.0) {
                 atomicOr(a.status + b, RMPE_ST_ZERO_LIMB);
             } else {
                 r.ux = (float)__ddiv_rn(r.xD, r.norm2);
                 r.uy = (float)__ddiv_rn(r.yD, r.norm2);
+                band_prepare(r, thre);
                 const double mnx = r.x1 < x2 ? r.x1 : x2, mxx = r.x1 < x2 ? x2 : r.x1;
                 const double mny = r.y1 < y2 ? r.y1 : y2, mxy = r.y1 < y2 ? y2 : r.y1;
                 const int a0 = py_round(__ddiv_rn(__dsub_rn(mnx, thre), 8.0));
@@ -1125,9 +1148,14 @@ __global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
     for (int part = tab_lo; part < tab_hi; part++) {
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         for (int p = 0; p < P; p++) {
+            // a run starts on an even column: its four cells are two aligned pairs (the second one on the next grid row
+            // when the run wraps at column 44), each pair sharing its row's ey
             const float *ex = s_ex + (part * P + p) * kGrid, *ey = s_ey + (part * P + p) * kGrid;
-#pragma unroll
-            for (int q = 0; q < 4; q++) v[q] = fmaxf(v[q], ey[y[q]] * ex[x[q]]);
+            const float2 ea = *reinterpret_cast<const float2 *>(ex + x[0]);
+            const float2 eb = *reinterpret_cast<const float2 *>(ex + x[2]);
+            const float ya = ey[y[0]], yb = ey[y[2]];
+            v[0] = fmaxf(v[0], ya * ea.x); v[1] = fmaxf(v[1], ya * ea.y);
+            v[2] = fmaxf(v[2], yb * eb.x); v[3] = fmaxf(v[3], yb * eb.y);
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) bk[q] = fmaxf(bk[q], v[q]);
@@ -1142,14 +1170,14 @@ __global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
         int cnt[4] = {0, 0, 0, 0};
         for (int p = 0; p < P; p++) {
             const LimbRec &r = s_rec[k * P + p];
-            if (r.maxx <= r.minx || r.maxy <= ymin || r.miny > ymax) continue;
+            const int4 box = *reinterpret_cast<const int4 *>(&r.minx);      // minx, maxx, miny, maxy
+            if (box.y <= box.x || box.w <= ymin || box.z > ymax) continue;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                if (x[q] >= r.minx && x[q] < r.maxx && y[q] >= r.miny && y[q] < r.maxy) {
+                if (x[q] >= box.x && x[q] < box.y && y[q] >= box.z && y[q] < box.w) {
                     const double X = (double)(8 * x[q]), Y = (double)(8 * y[q]);
-                    double dd = __dsub_rn(__dmul_rn(r.xD, __dsub_rn(r.y1, Y)), __dmul_rn(__dsub_rn(r.x1, X), r.yD));
-                    dd = __ddiv_rn(dd, r.norm2);
-                    if (fabs(dd) <= thre) { vx[q] = r.ux; vy[q] = r.uy; cnt[q]++; }
+                    const double dd = __dsub_rn(__dmul_rn(r.xD, __dsub_rn(r.y1, Y)), __dmul_rn(__dsub_rn(r.x1, X), r.yD));
+                    if (band_on(r, dd, thre)) { vx[q] = r.ux; vy[q] = r.uy; cnt[q]++; }
                 }
             }
         }
@@ -1209,12 +1237,13 @@ static int fused_foot_cap(int ng) {
 }
 static size_t fused_smem_bytes(int ng) { return (size_t)kTabBytes + (size_t)ng * ((size_t)fused_foot_cap(ng) * 4 + kGroupFixedBytes); }
 
+static std::atomic<unsigned> g_counter_ring{0};   // next work counter of DeviceTables::counters (all launches share the ring)
+
 template <int NG, bool kWide>
 static int launch_fused(const FusedArgs &fa_, bool want_mask, int n_items, int sm_count, cudaStream_t st) {
     FusedArgs fa = fa_;
     fa.foot_cap = fused_foot_cap(NG);
-    static std::atomic<unsigned> ring{0};
-    fa.counter = tables().counters + (size_t)(ring.fetch_add(1) % kCounterRing) * kCounterStride;
+    fa.counter = tables().counters + (size_t)(g_counter_ring.fetch_add(1) % kCounterRing) * kCounterStride;
     RMPE_CUDA_TRY(cudaMemsetAsync(fa.counter, 0, sizeof(int32_t), st));
     const size_t smem = fused_smem_bytes(NG);
     static bool attr_set = false;

@@ -194,3 +194,28 @@ def test_write_json_matches_reference(built_lib, decode_golden, tmp_path):
         with um.patch.object(ref.json, "dump", lambda o, f: real_dump(o, f, default=lambda v: v.item())):
             ref.write_json(cands, subs, ids, open(p_ref, "w"))
         assert json.load(open(p_ref)) == got
+
+
+def test_band_test_without_division_is_exact():
+    """k_raster's limb band test (csrc/rmpe_gt.cu band_on) replaces abs(dd / norm) <= 8.0 (py_rmpe_heatmapper.py:116-118,
+    f64 division rounded to nearest) by |dd| - 8 norm <= 8 norm 2^-53.  Checked here in NumPy float64 on adversarial
+    inputs: |dd| within a few ulps of 8 norm, of the rounding midpoint above it, and far away."""
+    rng = np.random.RandomState(0)
+    n = np.concatenate([rng.uniform(1e-3, 1e3, 20000), np.ldexp(1.0, rng.randint(-8, 9, 2000)),
+                        rng.randint(1, 4000, 4000).astype(np.float64) / 8.0])
+    t = 8.0 * n
+    dd = []
+    for k in range(-6, 7):                       # ulps around 8 norm
+        x = t.copy()
+        for _ in range(abs(k)):
+            x = np.nextafter(x, np.inf if k > 0 else -np.inf)
+        dd.append(x)
+    dd += [t * (1 + 2.0 ** -53), t * (1 + 2.0 ** -52), t * 0.3, t * 0.5, t * 2.0, t * 7.0, np.zeros_like(t)]
+    dd = np.stack(dd)
+    nn = np.broadcast_to(n, dd.shape)
+    ref = np.abs(dd / nn) <= 8.0
+    new = (np.abs(dd) - 8.0 * nn) <= (8.0 * nn) * 2.0 ** -53
+    assert np.array_equal(ref, new)
+    assert ref.any() and (~ref).any()
+    ref2 = np.abs(-dd / nn) <= 8.0
+    assert np.array_equal(ref2, new)
