@@ -149,6 +149,7 @@ struct FusedArgs {
     int mask_f64;
     int foot_cap;   // footprint capacity of one group, in pixels (32-bit words)
     int32_t *counter;   // next tile to hand out (zero at launch): tile groups take tiles as they finish theirs
+    int prefetch;       // pull the next tile's source lines into L2 during the taps
 };
 
 __device__ __forceinline__ void group_bar(int group) {
@@ -645,7 +646,7 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
                 const int pnx = max(nmnx, 0), pxx = min(nmxx, nd.width - 1);
                 const int pny = max(nmny, 0), pxy = min(nmxy, nd.height - 1);
                 const int rows = pxy - pny + 1;
-                if (pxx >= pnx && rows > 0 && rows <= 256) {
+                if (a.prefetch && pxx >= pnx && rows > 0 && rows <= 256) {
                     // per row: up to 3 image lines + 1 mask line of 128 bytes (wider footprints: first 384 bytes)
                     for (int i = t; i < rows * 4; i += kGroupThreads) {
                         const int row = pny + (i >> 2), seg = i & 3;
@@ -1243,6 +1244,13 @@ template <int NG, bool kWide>
 static int launch_fused(const FusedArgs &fa_, bool want_mask, int n_items, int sm_count, cudaStream_t st) {
     FusedArgs fa = fa_;
     fa.foot_cap = fused_foot_cap(NG);
+    static const int prefetch = [] {
+        // off by default: with tiles handed out dynamically, neighbouring tiles of a sample are staged at about the same
+        // time by other groups and their halos bring the lines into L2 anyway (measured 0.3015 ms with, 0.2952 ms without)
+        const char *e = getenv("RMPE_WARP_PREFETCH");
+        return e ? atoi(e) : 0;
+    }();
+    fa.prefetch = prefetch;
     fa.counter = tables().counters + (size_t)(g_counter_ring.fetch_add(1) % kCounterRing) * kCounterStride;
     RMPE_CUDA_TRY(cudaMemsetAsync(fa.counter, 0, sizeof(int32_t), st));
     const size_t smem = fused_smem_bytes(NG);
