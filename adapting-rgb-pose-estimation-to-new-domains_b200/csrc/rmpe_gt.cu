@@ -7,6 +7,7 @@
 //   py_rmpe_server/py_rmpe_heatmapper.py:32-138    Heatmapper.create_heatmaps -> k_raster
 #include <stddef.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -390,6 +391,9 @@ template <int NG, bool kWantMask, bool kWide>
 __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a, int n_items) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem_raw);
+    // the rasteriser that follows on the stream may be scheduled as soon as an SM is free (it waits for this grid's
+    // completion itself before it touches the mask)
+    asm volatile("griddepcontrol.launch_dependents;");
     const int group = threadIdx.x / kGroupThreads;
     const int t = threadIdx.x - group * kGroupThreads;
     const int warp = t >> 5, lane = t & 31;
@@ -1135,6 +1139,9 @@ __global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
     int y[4], x[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) { y[q] = (pix + q) / kGrid; x[q] = (pix + q) - y[q] * kGrid; }
+    // Launched with programmatic stream serialization behind k_warp_fused: everything above (joints, tables, limb records)
+    // reads only the caller's inputs and overlaps the tail of the warp kernel; the 46x46 mask is its output, so wait here.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     T m[4];
     {
         const T *mk = reinterpret_cast<const T *>(a.mask) + (size_t)b * kCells + pix;
@@ -1369,8 +1376,15 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
             const int kRsThreads = (kCellVec + 31) & ~31;
             const int pm = b->max_persons;
             const size_t smem = (size_t)kLimbs * pm * sizeof(LimbRec) + (size_t)pm * kParts * 3 * 8 + 2 * (size_t)kParts * pm * kGrid * 4;
-            if (ra.f64) k_raster_small<double><<<grid, kRsThreads, smem, st>>>(ra);
-            else k_raster_small<float><<<grid, kRsThreads, smem, st>>>(ra);
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = grid; cfg.blockDim = dim3(kRsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute pdl;
+            pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            pdl.val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = &pdl; cfg.numAttrs = 1;
+            if (ra.f64) RMPE_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_raster_small<double>, ra));
+            else RMPE_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_raster_small<float>, ra));
         } else {
             dim3 grid(3, b->batch);
             if (ra.f64) k_raster<double><<<grid, kRasterThreads, 0, st>>>(ra);
