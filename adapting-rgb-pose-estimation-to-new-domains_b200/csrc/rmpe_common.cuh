@@ -64,6 +64,22 @@ struct DeviceTables {
 };
 constexpr int kCounterRing = 64;      // launches that may be in flight at once (each takes the next counter of the ring)
 constexpr int kCounterStride = 32;    // int32 per counter line
+// Programmatic dependent launch: a kernel launched with launch_pdl may be scheduled while its predecessor on the stream
+// still runs (once every CTA of the predecessor has called pdl_trigger or exited); it must call pdl_wait before it reads
+// anything the predecessor wrote.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 bool is_initialised();
 const DeviceTables &tables();
 

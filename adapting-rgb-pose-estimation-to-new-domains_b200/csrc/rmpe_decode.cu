@@ -488,6 +488,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_screen_plan(const __grid_const
                                                               float *__restrict__ act_A, int32_t *__restrict__ act_count,
                                                               const int32_t *__restrict__ tab_err,
                                                               int32_t *__restrict__ status) {
+    pdl_trigger();
     const MsJob &J = jobs.j[blockIdx.y];
     if ((int)blockIdx.x >= J.tiles) return;
     if (*tab_err) {   // an operator row did not fit its table (cannot happen with plan_frame's bound): never screen on it
@@ -613,6 +614,8 @@ __global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_const
                                                               int32_t *__restrict__ cand_fp,
                                                               int32_t *__restrict__ cand_count,
                                                               int32_t *__restrict__ status) {
+    pdl_wait();
+    pdl_trigger();
     const int tid = threadIdx.x, lane = tid & 31;
     const int col = tid & (kScrCols - 1), half = tid >> 7;   // 128 columns x 2 row halves
     extern __shared__ __align__(16) uint8_t sm_raw[];
@@ -800,6 +803,8 @@ __global__ void __launch_bounds__(kVerThreads) k_peak_verify(const RmpeFrameDesc
                                                             const int32_t *__restrict__ cand_count, int max_peaks,
                                                             int32_t *__restrict__ raw_key, double *__restrict__ raw_score,
                                                             int32_t *__restrict__ raw_count, int32_t *__restrict__ status) {
+    pdl_wait();
+    pdl_trigger();
     // doubles hold both map dtypes: float32 maps (single scale) are rounded to float32 where the
     // reference stores float32, and comparing float32 values as doubles is the float32 comparison
     __shared__ double sU[kVerN][kVerN + 1];
@@ -947,6 +952,8 @@ __global__ void __launch_bounds__(256) k_peaks_finalize(const __grid_constant__ 
                                                         double *__restrict__ candidate, int32_t *__restrict__ n_peaks,
                                                         int32_t *__restrict__ pk_x, int32_t *__restrict__ pk_y,
                                                         double *__restrict__ pk_s) {
+    pdl_wait();
+    pdl_trigger();
     const int part = blockIdx.x, frame = first_frame + blockIdx.y;
     const int W = fj.W[blockIdx.y];
     __shared__ int s_key[kMaxPeaksCap];
@@ -1007,6 +1014,8 @@ __global__ void __launch_bounds__(kLimbThreads) k_limbs(const RmpeFrameDesc *__r
                                                         double *__restrict__ limb_cand, int32_t *__restrict__ n_limb_cand,
                                                         double *__restrict__ connections, int32_t *__restrict__ n_conn,
                                                         double *__restrict__ ws_cand, int32_t *__restrict__ status) {
+    pdl_wait();
+    pdl_trigger();
     const int k = blockIdx.x, frame = first_frame + blockIdx.y;
     const RmpeFrameDesc f = frames[frame];
     const int pa = c_dec_a[k], pb = c_dec_b[k], pc = c_dec_paf[k];
@@ -1230,6 +1239,7 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
                                                  const int32_t *__restrict__ n_conn, const int32_t *__restrict__ n_peaks,
                                                  double *__restrict__ subset,
                                                  int32_t *__restrict__ n_subset, int32_t *__restrict__ status) {
+    pdl_wait();
     const int frame = first_frame + blockIdx.x, lane = threadIdx.x;
     extern __shared__ __align__(16) double sm_asm[];
     double *s_sc = sm_asm;                                        // [kAsmRowCap] subset[:, 18]
@@ -1795,17 +1805,17 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                     const int per_sm = std::max(1, std::min(6, (int)((224 * 1024) / (std::max<size_t>(smem, 1) + 2048))));   // + static smem / reserve
                     const int grid = sms * per_sm;
                     if (variant == 0)
-                        k_screen_pairs<10, kScrMaxSrcRows><<<grid, kScrThreads, smem, st>>>(
-                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, cand_cap, cand_key, cand_fp, cand_count, b->status);
+                        RMPE_CUDA_TRY(launch_pdl(k_screen_pairs<10, kScrMaxSrcRows>, dim3(grid), dim3(kScrThreads), smem, st,
+                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, cand_cap, cand_key, cand_fp, cand_count, b->status));
                     else if (variant == 1)
-                        k_screen_pairs<kScrMaxKW, kScrMaxSrcRows><<<grid, kScrThreads, smem, st>>>(
-                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, cand_cap, cand_key, cand_fp, cand_count, b->status);
+                        RMPE_CUDA_TRY(launch_pdl(k_screen_pairs<kScrMaxKW, kScrMaxSrcRows>, dim3(grid), dim3(kScrThreads), smem, st,
+                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, cand_cap, cand_key, cand_fp, cand_count, b->status));
                     else if (variant == 2)
-                        k_screen_pairs<kMsKW, kMsMaxRows><<<grid, kScrThreads, smem, st>>>(
-                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, cand_cap, cand_key, cand_fp, cand_count, b->status);
+                        RMPE_CUDA_TRY(launch_pdl(k_screen_pairs<kMsKW, kMsMaxRows>, dim3(grid), dim3(kScrThreads), smem, st,
+                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, cand_cap, cand_key, cand_fp, cand_count, b->status));
                     else
-                        k_screen_pairs<kMsKWBig, kMsMaxRowsBig><<<grid, kScrThreads, smem, st>>>(
-                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, cand_cap, cand_key, cand_fp, cand_count, b->status);
+                        RMPE_CUDA_TRY(launch_pdl(k_screen_pairs<kMsKWBig, kMsMaxRowsBig>, dim3(grid), dim3(kScrThreads), smem, st,
+                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, cand_cap, cand_key, cand_fp, cand_count, b->status));
                 }
                 count_launch(2);
                 return RMPE_OK;
@@ -1817,8 +1827,8 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
             {
                 ProfScope ps("k_peak_verify", st);
                 const int grid = std::min(cand_cap, 8 * sms);
-                k_peak_verify<<<grid, kVerThreads, 0, st>>>(b->frames, b->heat, b->stride, b->thre1, cand_cap, cand_key, cand_fp,
-                                                           cand_count, MP, raw_key, raw_score, raw_count, b->status);
+                RMPE_CUDA_TRY(launch_pdl(k_peak_verify, dim3(grid), dim3(kVerThreads), 0, st, b->frames, b->heat, b->stride, b->thre1,
+                                         cand_cap, cand_key, cand_fp, cand_count, MP, raw_key, raw_score, raw_count, b->status));
                 count_launch();
             }
         }
@@ -1855,8 +1865,8 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
             FinalizeJobs fj{};
             for (int i = 0; i < n; i++) fj.W[i] = fr[i].width;
             ProfScope ps("k_peaks_finalize", st);
-            k_peaks_finalize<<<dim3(kParts, n), 256, 0, st>>>(fj, f0, MP, raw_key, raw_score, raw_count, b->candidate,
-                                                             b->n_peaks, pk_x, pk_y, pk_s);
+            RMPE_CUDA_TRY(launch_pdl(k_peaks_finalize, dim3(kParts, n), dim3(256), 0, st, fj, f0, MP, raw_key, raw_score, raw_count,
+                                     b->candidate, b->n_peaks, pk_x, pk_y, pk_s));
             count_launch();
         }
         f0 += n;
@@ -1866,16 +1876,15 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
         size_t smem = (size_t)MC * 12 + 2 * kMaxPeaksCap;
         {
             ProfScope ps("k_limbs", st);
-            k_limbs<<<dim3(kLimbs, B), kLimbThreads, smem, st>>>(b->frames, 0, b->paf, b->stride, b->thre2, MP, MC,
-                                                                b->n_peaks, pk_x, pk_y, pk_s, b->limb_cand,
-                                                                b->n_limb_cand, b->connections, b->n_conn, ws_cand,
-                                                                b->status);
+            RMPE_CUDA_TRY(launch_pdl(k_limbs, dim3(kLimbs, B), dim3(kLimbThreads), smem, st, b->frames, 0, b->paf, b->stride,
+                                     b->thre2, MP, MC, b->n_peaks, pk_x, pk_y, pk_s, b->limb_cand, b->n_limb_cand,
+                                     b->connections, b->n_conn, ws_cand, b->status));
         }
         {
             ProfScope ps("k_assemble", st);
             const size_t asm_smem = ((size_t)kAsmRowCap * 2 + (size_t)kAsmConnRows * 3 + (size_t)kParts * MP) * 8 + (size_t)kParts * kAsmRowCap * 4;
-            k_assemble<<<B, 32, asm_smem, st>>>(0, MP, b->max_persons, b->candidate, b->connections, b->n_conn, b->n_peaks,
-                                                b->subset, b->n_subset, b->status);
+            RMPE_CUDA_TRY(launch_pdl(k_assemble, dim3(B), dim3(32), asm_smem, st, 0, MP, b->max_persons, b->candidate,
+                                     b->connections, b->n_conn, b->n_peaks, b->subset, b->n_subset, b->status));
         }
         count_launch(2);
     }
