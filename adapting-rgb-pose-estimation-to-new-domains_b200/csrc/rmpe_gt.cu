@@ -108,31 +108,34 @@ __global__ void __launch_bounds__(256) k_warp_simple(WarpArgs a) {
 // resize in ONE pass over the destination.
 //
 // A persistent CTA (one per SM) holds the 32 KB dp4a weight table once and runs NG independent
-// groups of 128 threads; each group walks 32x32 destination tiles, warp w owning the cell row
-// (destination rows 8w..8w+7) so every warp does identical work.  Per tile the group
-//   1. (one tile ahead, overlapped with the taps) builds the fixed-point row/column terms of
-//      cv::WarpAffineInvoker in f64,
+// groups of 128 threads; each group draws 32x32 destination tiles from a global counter (three
+// passes ahead), warp w owning the cell row (destination rows 8w..8w+7) so every warp does
+// identical work.  Per tile the group
+//   1. (two tiles ahead, overlapped with the taps) builds the fixed-point row/column terms of
+//      cv::WarpAffineInvoker in f64; (one tile ahead) the footprint bounding box,
 //   2. stages the UNCLIPPED source footprint of the tile into shared memory as one 32-bit word
 //      per source pixel (B,G,R,mask), out-of-image pixels already replaced by the border
-//      constants (127,127,127,255) -- the 16-tap loop needs no bounds test at all; sources whose
-//      rows are 16-byte aligned are read with 128-bit loads, 16 pixels per thread,
+//      constants (127,127,127,255) -- the 16-tap loop needs no bounds test at all; 8-byte aligned
+//      sources are read with 64-bit loads, 8 pixels per thread (4-byte aligned: 32-bit, 4 pixels),
 //   3. evaluates the 16 taps of the channels with dp4a over hi/lo byte-split int16 weights
 //      (exact: identical to OpenCV's int32 accumulation): 4 LDS.32 + 8 PRMT + 8 IDP per tap row
 //      on the four rows that feed the mask, 4 + 7 + 6 on the others,
 //   4. reduces the warped mask to the 46x46 grid in registers/shuffles (cells are 8x8 destination
 //      pixels of which rows/cols 2..5 feed cv2.resize),
-//   5. packs B,G,R of 32 neighbouring pixels into 24 words with two shuffles and stores the row
+//   5. packs B,G,R of 32 neighbouring pixels into 24 words with one shuffle and stores the row
 //      as one coalesced 96-byte segment (planar rows for CHW).
-// The shared-memory row pitch is kept = 16 (mod 32) words so that a warp walking a rotated line
-// through the footprint spreads over the banks.
+// The kernel is bound by the L1/shared-memory data pipe (wavefronts of the tap and weight gathers),
+// so the layouts are chosen for bank behaviour: the footprint pitch is 0 (mod 32) words (the bank
+// of a tap is its column, whatever its row) and the weight table is stored transposed (the 16-byte
+// bank group of an entry is ay & 7); DESIGN.md 4.1 has the measured wavefront budget.
 // ==========================================================================================
 constexpr int kTile = 32;
 constexpr int kTilesX = (kOutW + kTile - 1) / kTile;  // 12
 constexpr int kTilesPerSample = kTilesX * kTilesX;    // 144
 constexpr int kTabBytes = 32 * 32 * 8 * 4;            // dp4a table
 constexpr int kGroupThreads = 128;
-constexpr int kGeoInts = 4 * kTile;                   // X0, Y0, ad, bd
-constexpr int kGroupFixedBytes = 4 * kGeoInts * 4;    // geometry ring (3 used): tile k, k+1 (prefetch), k+2 (being built)
+constexpr int kGeoInts = 4 * kTile;                   // {X0,Y0}[32] then {ad,bd}[32], interleaved
+constexpr int kGroupFixedBytes = 4 * kGeoInts * 4;    // geometry ring: tile k, k+1 (bounding box), k+2 (being built); 4th slot: tile queue
 constexpr unsigned kBorderWord = 0xFF7F7F7Fu;         // (B,G,R,mask) = (127,127,127,255)
 
 struct FusedArgs {
