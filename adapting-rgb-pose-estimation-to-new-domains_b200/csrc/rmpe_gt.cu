@@ -160,6 +160,15 @@ __device__ __forceinline__ void group_bar(int group) {
     asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kGroupThreads) : "memory");
 }
 
+// saturate four int32 to u8 and pack them as B | G<<8 | R<<16 | M<<24: two I2IP (cvt.pack.sat.u8.s32) instead of eight
+// min/max and three shift-ors
+__device__ __forceinline__ unsigned pack_sat_u8x4(int vB, int vG, int vR, int vM) {
+    unsigned t, w;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(vM), "r"(vR), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(vG), "r"(vB), "r"(t));
+    return w;
+}
+
 // 16 taps x {B,G,R[,mask]} from a staged (B,G,R,mask) footprint.  p -> tap (0,0).
 template <bool kMask>
 __device__ __forceinline__ void bicubic_bgrm(const uint32_t *__restrict__ p, int fpitch,
@@ -191,10 +200,11 @@ __device__ __forceinline__ void bicubic_bgrm(const uint32_t *__restrict__ p, int
             hM = dp4a_us(pm, whi[ky], hM); lM = dp4a_uu(pm, wlo[ky], lM);
         }
     }
-    oB = min(255, max(0, (hB * 256 + lB) >> 15));
-    oG = min(255, max(0, (hG * 256 + lG) >> 15));
-    oR = min(255, max(0, (hR * 256 + lR) >> 15));
-    oM = kMask ? min(255, max(0, (hM * 256 + lM) >> 15)) : 0;
+    // unclamped; the caller saturates and packs (pack_sat_u8x4)
+    oB = (hB * 256 + lB) >> 15;
+    oG = (hG * 256 + lG) >> 15;
+    oR = (hR * 256 + lR) >> 15;
+    oM = kMask ? (hM * 256 + lM) >> 15 : 0;
 }
 
 // "Wide" footprint layout: one 16-byte entry per source position x = the four taps x..x+3 of every channel already
@@ -216,11 +226,8 @@ __device__ __forceinline__ unsigned bicubic_wide(const uint4 *__restrict__ p, in
         hR = dp4a_us(e.z, whi[ky], hR); lR = dp4a_uu(e.z, wlo[ky], lR);
         if (kMask) { hM = dp4a_us(e.w, whi[ky], hM); lM = dp4a_uu(e.w, wlo[ky], lM); }
     }
-    const unsigned oB = (unsigned)min(255, max(0, (hB * 256 + lB) >> 15));
-    const unsigned oG = (unsigned)min(255, max(0, (hG * 256 + lG) >> 15));
-    const unsigned oR = (unsigned)min(255, max(0, (hR * 256 + lR) >> 15));
-    const unsigned oM = kMask ? (unsigned)min(255, max(0, (hM * 256 + lM) >> 15)) : 0u;
-    return oB | (oG << 8) | (oR << 16) | (oM << 24);
+    return pack_sat_u8x4((hB * 256 + lB) >> 15, (hG * 256 + lG) >> 15, (hR * 256 + lR) >> 15,
+                         kMask ? (hM * 256 + lM) >> 15 : 0);
 }
 
 // planes of 8 consecutive pixels (lo = pixels 0..3, hi = 4..7) -> the 4 sliding entries c..c+3 of one footprint row.
@@ -335,7 +342,7 @@ __device__ __forceinline__ unsigned fused_row(const TileCtx &c, int ly) {
         int oB, oG, oR, oM;
         const uint32_t *p = c.foot + ((Y >> 5) - 1 - c.by0) * c.fpitch + ((X >> 5) - 1 - c.bx0);
         bicubic_bgrm<kMask>(p, c.fpitch, wt, oB, oG, oR, oM);
-        return (unsigned)oB | ((unsigned)oG << 8) | ((unsigned)oR << 16) | ((unsigned)oM << 24);
+        return pack_sat_u8x4(oB, oG, oR, oM);
     }
     return generic_bgrm(c.img, c.msk, c.H, c.W, c.ipitch, c.mpitch, X, Y, c.tab16, kMask);
 }
