@@ -148,6 +148,17 @@ __device__ inline int dp4a_us(unsigned a_u8x4, unsigned b_s8x4, int c) {
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
     return d;
 }
+// two-way dot product of signed 16-bit weights with the low (.lo) / high (.hi) two unsigned bytes of b: exact int32
+__device__ inline int dp2a_lo_su(unsigned a_s16x2, unsigned b_u8x4, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_s16x2), "r"(b_u8x4), "r"(c));
+    return d;
+}
+__device__ inline int dp2a_hi_su(unsigned a_s16x2, unsigned b_u8x4, int c) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_s16x2), "r"(b_u8x4), "r"(c));
+    return d;
+}
 __device__ inline int dp4a_uu(unsigned a_u8x4, unsigned b_u8x4, int c) {
     unsigned d;
     asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_u8x4), "r"(c));

@@ -173,89 +173,31 @@ __device__ __forceinline__ unsigned pack_sat_u8x4(int vB, int vG, int vR, int vM
 template <bool kMask>
 __device__ __forceinline__ void bicubic_bgrm(const uint32_t *__restrict__ p, int fpitch,
                                              const uint32_t *__restrict__ wt, int &oB, int &oG, int &oR, int &oM) {
-    // hi bytes (s8 x4 per tap row) and lo bytes (u8 x4) of the 16 int16 weights of this phase live in
-    // two tables of 16-byte entries: a quarter-warp's LDS.128 then spreads over all 8 bank groups
+    // the 16 int16 weights of this phase, [ky][kx] as in OpenCV's table: tap rows 0-1 in one table of 16-byte entries,
+    // rows 2-3 in a second one (a quarter-warp's LDS.128 then spreads over all 8 bank groups)
     const uint4 wa = *reinterpret_cast<const uint4 *>(wt);
     const uint4 wb = *reinterpret_cast<const uint4 *>(wt + kTabBytes / 8);
-    const unsigned whi[4] = {wa.x, wa.y, wa.z, wa.w};
-    const unsigned wlo[4] = {wb.x, wb.y, wb.z, wb.w};
-    int hB = 0, hG = 0, hR = 0, hM = 0;
-    int lB = 16384, lG = 16384, lR = 16384, lM = 16384;   // rounding term of the >>15
+    const unsigned w01[4] = {wa.x, wa.z, wb.x, wb.z};    // (w[ky][0], w[ky][1]) as s16 x2
+    const unsigned w23[4] = {wa.y, wa.w, wb.y, wb.w};    // (w[ky][2], w[ky][3])
+    int vB = 16384, vG = 16384, vR = 16384, vM = 16384;  // rounding term of the >>15
 #pragma unroll
     for (int ky = 0; ky < 4; ky++) {
         const unsigned p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3];
         p += fpitch;
+        // half a 4x4 byte transpose is enough for dp2a: it multiplies the two s16 weights of a pair with the low or the
+        // high two bytes of its second operand
         const unsigned t0 = __byte_perm(p0, p1, 0x5140);   // B0 B1 G0 G1
         const unsigned t1 = __byte_perm(p2, p3, 0x5140);   // B2 B3 G2 G3
-        const unsigned pb = __byte_perm(t0, t1, 0x5410);
-        const unsigned pg = __byte_perm(t0, t1, 0x7632);
         const unsigned t2 = __byte_perm(p0, p1, 0x7362);   // R0 R1 M0 M1
         const unsigned t3 = __byte_perm(p2, p3, 0x7362);   // R2 R3 M2 M3
-        const unsigned pr = __byte_perm(t2, t3, 0x5410);
-        hB = dp4a_us(pb, whi[ky], hB); lB = dp4a_uu(pb, wlo[ky], lB);
-        hG = dp4a_us(pg, whi[ky], hG); lG = dp4a_uu(pg, wlo[ky], lG);
-        hR = dp4a_us(pr, whi[ky], hR); lR = dp4a_uu(pr, wlo[ky], lR);
-        if (kMask) {
-            const unsigned pm = __byte_perm(t2, t3, 0x7632);
-            hM = dp4a_us(pm, whi[ky], hM); lM = dp4a_uu(pm, wlo[ky], lM);
-        }
+        vB = dp2a_lo_su(w01[ky], t0, vB); vB = dp2a_lo_su(w23[ky], t1, vB);
+        vG = dp2a_hi_su(w01[ky], t0, vG); vG = dp2a_hi_su(w23[ky], t1, vG);
+        vR = dp2a_lo_su(w01[ky], t2, vR); vR = dp2a_lo_su(w23[ky], t3, vR);
+        if (kMask) { vM = dp2a_hi_su(w01[ky], t2, vM); vM = dp2a_hi_su(w23[ky], t3, vM); }
     }
     // unclamped; the caller saturates and packs (pack_sat_u8x4)
-    oB = (hB * 256 + lB) >> 15;
-    oG = (hG * 256 + lG) >> 15;
-    oR = (hR * 256 + lR) >> 15;
-    oM = kMask ? (hM * 256 + lM) >> 15 : 0;
-}
-
-// "Wide" footprint layout: one 16-byte entry per source position x = the four taps x..x+3 of every channel already
-// packed for dp4a -- (B x4, G x4, R x4, mask x4).  A tap row is then ONE LDS.128 and no byte shuffling at all
-// (the 32-bit (B,G,R,mask) layout needs 4 LDS.32 + 8 PRMT per tap row).  p -> entry of tap row 0; pitch in entries.
-template <bool kMask>
-__device__ __forceinline__ unsigned bicubic_wide(const uint4 *__restrict__ p, int wpitch, const uint32_t *__restrict__ wt) {
-    const uint4 wa = *reinterpret_cast<const uint4 *>(wt);
-    const uint4 wb = *reinterpret_cast<const uint4 *>(wt + kTabBytes / 8);
-    const unsigned whi[4] = {wa.x, wa.y, wa.z, wa.w};
-    const unsigned wlo[4] = {wb.x, wb.y, wb.z, wb.w};
-    int hB = 0, hG = 0, hR = 0, hM = 0;
-    int lB = 16384, lG = 16384, lR = 16384, lM = 16384;   // rounding term of the >>15
-#pragma unroll
-    for (int ky = 0; ky < 4; ky++) {
-        const uint4 e = p[ky * wpitch];
-        hB = dp4a_us(e.x, whi[ky], hB); lB = dp4a_uu(e.x, wlo[ky], lB);
-        hG = dp4a_us(e.y, whi[ky], hG); lG = dp4a_uu(e.y, wlo[ky], lG);
-        hR = dp4a_us(e.z, whi[ky], hR); lR = dp4a_uu(e.z, wlo[ky], lR);
-        if (kMask) { hM = dp4a_us(e.w, whi[ky], hM); lM = dp4a_uu(e.w, wlo[ky], lM); }
-    }
-    return pack_sat_u8x4((hB * 256 + lB) >> 15, (hG * 256 + lG) >> 15, (hR * 256 + lR) >> 15,
-                         kMask ? (hM * 256 + lM) >> 15 : 0);
-}
-
-// planes of 8 consecutive pixels (lo = pixels 0..3, hi = 4..7) -> the 4 sliding entries c..c+3 of one footprint row.
-// Store k of a thread writes entry c + ((k + rot) & 3), rot = (unit index >> 1): the eight lanes of a quarter-warp then
-// hit eight different 16-byte bank groups (entries of one thread are 64 contiguous bytes); the rotation costs nothing,
-// it only makes the funnel-shift amount a register.
-__device__ __forceinline__ void wide_store4(uint4 *__restrict__ row, int c, int rot, unsigned Blo, unsigned Bhi,
-                                            unsigned Glo, unsigned Ghi, unsigned Rlo, unsigned Rhi, unsigned Mlo,
-                                            unsigned Mhi) {
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int e = (k + rot) & 3;
-        const unsigned sh = 8u * e;
-        row[c + e] = make_uint4(__funnelshift_r(Blo, Bhi, sh), __funnelshift_r(Glo, Ghi, sh), __funnelshift_r(Rlo, Rhi, sh),
-                                __funnelshift_r(Mlo, Mhi, sh));
-    }
-}
-
-// 24 interleaved image bytes (q0..q5 = pixels 0..7) -> B, G, R planes
-__device__ __forceinline__ void wide_planes(unsigned q0, unsigned q1, unsigned q2, unsigned q3, unsigned q4, unsigned q5,
-                                            unsigned &Blo, unsigned &Bhi, unsigned &Glo, unsigned &Ghi, unsigned &Rlo,
-                                            unsigned &Rhi) {
-    Blo = __byte_perm(__byte_perm(q0, q1, 0x0630), q2, 0x5210);
-    Glo = __byte_perm(__byte_perm(q0, q1, 0x0741), q2, 0x6210);
-    Rlo = __byte_perm(__byte_perm(q0, q1, 0x0052), q2, 0x7410);
-    Bhi = __byte_perm(__byte_perm(q3, q4, 0x0630), q5, 0x5210);
-    Ghi = __byte_perm(__byte_perm(q3, q4, 0x0741), q5, 0x6210);
-    Rhi = __byte_perm(__byte_perm(q3, q4, 0x0052), q5, 0x7410);
+    oB = vB >> 15; oG = vG >> 15; oR = vR >> 15;
+    oM = kMask ? vM >> 15 : 0;
 }
 
 // (B,G,R,mask) word of one source pixel with cv2's per-tap constant border
@@ -319,14 +261,14 @@ struct TileCtx {
     const uint32_t *foot;
     const uint32_t *tab;
     const int2 *gXY;                   // {X0[y], Y0[y]} of the tile's rows
-    int adx, bdx, fpitch, bx0, by0;   // fpitch: words (mode 0) or 16-byte entries (mode 3)
+    int adx, bdx, fpitch, bx0, by0;   // fpitch in 32-bit words
     const uint8_t *img, *msk;
     int H, W, ipitch, mpitch;
     const int16_t *tab16;
 };
 
 // one destination row of the warp: returns packed B | G<<8 | R<<16 | mask<<24
-// kMode: 0 = staged (B,G,R,mask) words, 1 = all border, 2 = generic (taps from global memory), 3 = staged wide entries
+// kMode: 0 = staged (B,G,R,mask) words, 1 = all border, 2 = generic (taps from global memory)
 template <int kMode, bool kMask>
 __device__ __forceinline__ unsigned fused_row(const TileCtx &c, int ly) {
     if (kMode == 1) return kBorderWord;
@@ -334,10 +276,6 @@ __device__ __forceinline__ unsigned fused_row(const TileCtx &c, int ly) {
     const int X = (xy0.x + c.adx) >> 5;
     const int Y = (xy0.y + c.bdx) >> 5;
     const uint32_t *wt = c.tab + (((X & 31) * 32 + (Y & 31)) << 2);      // slot = ax * 32 + ay (see the table fill)
-    if (kMode == 3) {
-        const uint4 *p = reinterpret_cast<const uint4 *>(c.foot) + ((Y >> 5) - 1 - c.by0) * c.fpitch + ((X >> 5) - 1 - c.bx0);
-        return bicubic_wide<kMask>(p, c.fpitch, wt);
-    }
     if (kMode == 0) {
         int oB, oG, oR, oM;
         const uint32_t *p = c.foot + ((Y >> 5) - 1 - c.by0) * c.fpitch + ((X >> 5) - 1 - c.bx0);
@@ -397,7 +335,7 @@ __device__ __forceinline__ float cell_rows(const TileCtx &c, const RowStore &rs,
     return macc;
 }
 
-template <int NG, bool kWantMask, bool kWide>
+template <int NG, bool kWantMask>
 __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a, int n_items) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem_raw);
@@ -411,18 +349,18 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
     uint32_t *foot = reinterpret_cast<uint32_t *>(gbase);
     int *geo = reinterpret_cast<int *>(gbase + (size_t)a.foot_cap * 4);
 
-    {   // dp4a weight table -> shared memory, once per persistent CTA: [phase][row]{hi,lo} -> hi[phase][row], lo[phase][row]
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.tab_dp4a);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_tab);
+    {   // weight table -> shared memory, once per persistent CTA, as two tables of 16-byte entries.
         // shared-memory slot of phase (ay, ax) = ax * 32 + ay: the 16-byte bank group of an entry is then ay & 7.  Along a
         // destination row ay moves by 32 sin(theta) per pixel and ax by 32 (cos(theta) - 1): for the rotations of the
         // augmentation (|theta| <= 40 deg) ax often stays put over a quarter-warp while ay changes, which with the
         // [ay][ax] order put 8 different entries into one bank group (measured 2.75 wavefronts per quarter-warp, 2.2 now)
+        // dp2a operands: OpenCV's int16 table as it is, tap rows 0-1 in the first table, tap rows 2-3 in the second
+        uint4 *dst = reinterpret_cast<uint4 *>(s_tab);
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.tab);
         for (int e = threadIdx.x; e < 1024; e += NG * kGroupThreads) {
-            const uint4 r01 = __ldg(src + 2 * e), r23 = __ldg(src + 2 * e + 1);
             const int slot = ((e & 31) << 5) | (e >> 5);
-            dst[slot] = make_uint4(r01.x, r01.z, r23.x, r23.z);
-            dst[1024 + slot] = make_uint4(r01.y, r01.w, r23.y, r23.w);
+            dst[slot] = __ldg(src + 2 * e);
+            dst[1024 + slot] = __ldg(src + 2 * e + 1);
         }
     }
 
@@ -505,74 +443,15 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
 
         // 4-byte aligned sources are read with plain 32-bit loads; the footprint then starts on a multiple of 4
         const bool al4 = ((((size_t)img | (size_t)msk) & 3) == 0) && (((d.img_pitch | d.mask_pitch) & 3) == 0);
-        // 8-byte aligned sources (the 32-bit word layout only): 64-bit loads, 8 pixels per thread, footprint on a multiple of 8
-        const bool al8 = !kWide && ((((size_t)img | (size_t)msk) & 7) == 0) && (((d.img_pitch | d.mask_pitch) & 7) == 0);
+        // 8-byte aligned sources: 64-bit loads, 8 pixels per thread, footprint on a multiple of 8
+        const bool al8 = ((((size_t)img | (size_t)msk) & 7) == 0) && (((d.img_pitch | d.mask_pitch) & 7) == 0);
         const int bx0 = al8 ? (mnx & ~7) : (al4 ? (mnx & ~3) : mnx), by0 = mny;
         const int fw = mxx - bx0 + 1, fh = mxy - mny + 1;
         const int fwa = al8 ? ((fw + 7) & ~7) : ((fw + 3) & ~3);
         int fpitch = (fwa + 31) & ~31;     // = 0 (mod 32): the bank of a tap is its column, whatever its row
         if ((long long)fpitch * fh > a.foot_cap) fpitch = fwa;
         const bool outside = sane && (mxx < 0 || mnx >= d.width || mxy < 0 || mny >= d.height);
-        // wide entries (16 bytes per source position, taps pre-packed): columns bx0 .. mxx-3; the pitch is a multiple
-        // of 8 entries, so the 16-byte bank group of an entry is its column whatever its row
-        const int upr = fw >> 2;                      // units (4 entries) per footprint row = ceil((fw - 3) / 4)
-        const int wpitch = (4 * upr + 7) & ~7;
-        const bool wide = kWide && sane && !outside && al4 && upr >= 1 && upr <= 64 && (long long)wpitch * fh * 4 <= a.foot_cap;
-        const bool staged = !wide && sane && !outside && (long long)fpitch * fh <= a.foot_cap;
-
-        if (kWide && wide) {
-            // ---- one thread = 4 entries of one footprint row = 7 source pixels (read as 8) -> four 16-byte stores;
-            //      units are numbered row-major over the footprint, two units (u, u + 128) in flight per thread ----
-            uint4 *wfoot = reinterpret_cast<uint4 *>(foot);
-            const int n_units = fh * upr;
-            const unsigned inv = (65536u + upr - 1) / upr;          // u / upr == (u * inv) >> 16 for u < 2^13
-            for (int u0 = t; u0 < n_units; u0 += 2 * kGroupThreads) {
-                int rr[2], cc[2], kind[2];                            // kind: 0 = interior, 1 = row outside, 2 = edge
-                unsigned q[2][6], m[2][2];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int u = u0 + h * kGroupThreads;
-                    const int r = (int)(((unsigned)u * inv) >> 16);
-                    rr[h] = r; cc[h] = (u - r * upr) << 2;
-                    const int xx = bx0 + cc[h], yy = by0 + r;
-                    kind[h] = (u >= n_units) ? 3 : ((unsigned)yy >= (unsigned)d.height ? 1 : ((xx >= 0 && xx + 7 < d.width) ? 0 : 2));
-                    if (kind[h] == 0) {
-                        const uint32_t *ip = reinterpret_cast<const uint32_t *>(img + (size_t)yy * d.img_pitch + 3 * xx);
-                        const uint32_t *mp = reinterpret_cast<const uint32_t *>(msk + (size_t)yy * d.mask_pitch + xx);
-#pragma unroll
-                        for (int i = 0; i < 6; i++) q[h][i] = __ldg(ip + i);
-                        m[h][0] = __ldg(mp); m[h][1] = __ldg(mp + 1);
-                    }
-                }
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    if (kind[h] == 3) break;
-                    unsigned Blo, Bhi, Glo, Ghi, Rlo, Rhi, Mlo, Mhi;
-                    if (kind[h] == 0) {
-                        wide_planes(q[h][0], q[h][1], q[h][2], q[h][3], q[h][4], q[h][5], Blo, Bhi, Glo, Ghi, Rlo, Rhi);
-                        Mlo = m[h][0]; Mhi = m[h][1];
-                    } else if (kind[h] == 1) {
-                        Blo = Bhi = Glo = Ghi = Rlo = Rhi = 0x7F7F7F7Fu; Mlo = Mhi = 0xFFFFFFFFu;
-                    } else {
-                        // a unit that straddles the left/right image edge: per-pixel border test, then 4x4 byte transposes
-                        unsigned w[8];
-#pragma unroll
-                        for (int i = 0; i < 7; i++)
-                            w[i] = bgrm_pixel(img, msk, d.height, d.width, d.img_pitch, d.mask_pitch, by0 + rr[h], bx0 + cc[h] + i);
-                        w[7] = w[6];
-                        const unsigned t0 = __byte_perm(w[0], w[1], 0x5140), t1 = __byte_perm(w[2], w[3], 0x5140);
-                        const unsigned t2 = __byte_perm(w[0], w[1], 0x7362), t3 = __byte_perm(w[2], w[3], 0x7362);
-                        const unsigned u0_ = __byte_perm(w[4], w[5], 0x5140), u1 = __byte_perm(w[6], w[7], 0x5140);
-                        const unsigned u2 = __byte_perm(w[4], w[5], 0x7362), u3 = __byte_perm(w[6], w[7], 0x7362);
-                        Blo = __byte_perm(t0, t1, 0x5410); Glo = __byte_perm(t0, t1, 0x7632);
-                        Rlo = __byte_perm(t2, t3, 0x5410); Mlo = __byte_perm(t2, t3, 0x7632);
-                        Bhi = __byte_perm(u0_, u1, 0x5410); Ghi = __byte_perm(u0_, u1, 0x7632);
-                        Rhi = __byte_perm(u2, u3, 0x5410); Mhi = __byte_perm(u2, u3, 0x7632);
-                    }
-                    wide_store4(wfoot + rr[h] * wpitch, cc[h], (cc[h] >> 3) & 3, Blo, Bhi, Glo, Ghi, Rlo, Rhi, Mlo, Mhi);
-                }
-            }
-        }
+        const bool staged = sane && !outside && (long long)fpitch * fh <= a.foot_cap;
 
         // ---- stage the footprint as (B,G,R,mask) words: one thread = 4 pixels = one 16-byte store ----
         if (staged && al8) {
@@ -686,7 +565,7 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
             const int gl = min(lane, tw - 1);     // lanes beyond the tile edge repeat its last pixel (never stored)
             c.foot = foot; c.tab = s_tab; c.gXY = reinterpret_cast<const int2 *>(gcur);
             const int2 abd = reinterpret_cast<const int2 *>(gcur + 2 * kTile)[gl];
-            c.adx = abd.x; c.bdx = abd.y; c.fpitch = wide ? wpitch : fpitch; c.bx0 = bx0; c.by0 = by0;
+            c.adx = abd.x; c.bdx = abd.y; c.fpitch = fpitch; c.bx0 = bx0; c.by0 = by0;
             c.img = img; c.msk = msk; c.H = d.height; c.W = d.width; c.ipitch = d.img_pitch; c.mpitch = d.mask_pitch;
             c.tab16 = a.tab;
             const bool lane_on = lane < tw;
@@ -698,8 +577,7 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
                           : out_sample + ((size_t)(y0 + r0) * kOutW + x0) * 3 + 4 * pk_word;
             rs.on = a.chw ? lane_on : ((lane & 3) != 3 && 4 * pk_word < 3 * tw);
             float macc;
-            if (kWide && wide) macc = cell_rows<3, kWantMask>(c, rs, r0, mw, b0, b1);
-            else if (staged) macc = cell_rows<0, kWantMask>(c, rs, r0, mw, b0, b1);
+            if (staged) macc = cell_rows<0, kWantMask>(c, rs, r0, mw, b0, b1);
             else if (outside) macc = cell_rows<1, kWantMask>(c, rs, r0, mw, b0, b1);
             else macc = cell_rows<2, kWantMask>(c, rs, r0, mw, b0, b1);
             if (kWantMask && l7 == 3 && lane_on) {
@@ -1257,7 +1135,7 @@ static size_t fused_smem_bytes(int ng) { return (size_t)kTabBytes + (size_t)ng *
 
 static std::atomic<unsigned> g_counter_ring{0};   // next work counter of DeviceTables::counters (all launches share the ring)
 
-template <int NG, bool kWide>
+template <int NG>
 static int launch_fused(const FusedArgs &fa_, bool want_mask, int n_items, int sm_count, cudaStream_t st) {
     FusedArgs fa = fa_;
     fa.foot_cap = fused_foot_cap(NG);
@@ -1273,13 +1151,13 @@ static int launch_fused(const FusedArgs &fa_, bool want_mask, int n_items, int s
     const size_t smem = fused_smem_bytes(NG);
     static bool attr_set = false;
     if (!attr_set) {
-        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, true, kWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, false, kWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const int grid = min((n_items + NG - 1) / NG, sm_count);
-    if (want_mask) k_warp_fused<NG, true, kWide><<<grid, NG * kGroupThreads, smem, st>>>(fa, n_items);
-    else k_warp_fused<NG, false, kWide><<<grid, NG * kGroupThreads, smem, st>>>(fa, n_items);
+    if (want_mask) k_warp_fused<NG, true><<<grid, NG * kGroupThreads, smem, st>>>(fa, n_items);
+    else k_warp_fused<NG, false><<<grid, NG * kGroupThreads, smem, st>>>(fa, n_items);
     return RMPE_OK;
 }
 
@@ -1330,30 +1208,19 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
             fa.mask_f64 = (b->flags & RMPE_GT_LABELS_F64) ? 1 : 0;
             fa.foot_cap = 0;
             const int n_items = b->batch * kTilesPerSample;
-            // default: 32-bit (B,G,R,mask) footprint words, 7 tile groups (896 threads, 72 registers, no spills) per SM.
-            // RMPE_WARP_GROUPS = 4 | 6 | 7 | 8 and RMPE_WARP_WIDE=1 (16-byte pre-packed footprint entries, 4 | 5 | 6
-            // groups) are kept for A/B tests; measured on B200 (GT batch 256): words 7 or 8 groups 0.354 ms (8 groups
-            // spill and leave a smaller footprint buffer), 6 groups 0.365 ms, 4 groups 0.404 ms; wide 5 groups 0.393 ms --
-            // the wide layout halves the issued instructions of the taps but pays for it in staging wavefronts, and
-            // both are bound by the shared-memory/L1 data pipe (profiles/r01r).
-            static const bool wide = [] {
-                const char *e = getenv("RMPE_WARP_WIDE");
-                return e ? atoi(e) != 0 : false;
-            }();
+            // 7 tile groups (896 threads, 72 registers, no spills) per SM; RMPE_WARP_GROUPS = 4 | 6 | 8 for A/B tests (measured
+            // on B200, GT batch 256: 7 groups 0.296 ms, 6 groups 0.31, 8 groups 0.32 -- 8 spill at 64 registers and leave a
+            // smaller footprint buffer)
             static const int ng = [] {
                 const char *e = getenv("RMPE_WARP_GROUPS");
                 int v = e ? atoi(e) : 0;
-                return (v == 4 || v == 5 || v == 6 || v == 7 || v == 8) ? v : 0;
+                return (v == 4 || v == 6 || v == 7 || v == 8) ? v : 0;
             }();
             ProfScope ps("k_warp_fused", st);
-            int rc;
-            if (wide) rc = ng == 4 ? launch_fused<4, true>(fa, want_mask, n_items, T.sm_count, st)
-                         : ng == 6 ? launch_fused<6, true>(fa, want_mask, n_items, T.sm_count, st)
-                                   : launch_fused<5, true>(fa, want_mask, n_items, T.sm_count, st);
-            else rc = ng == 4 ? launch_fused<4, false>(fa, want_mask, n_items, T.sm_count, st)
-                    : ng == 6 ? launch_fused<6, false>(fa, want_mask, n_items, T.sm_count, st)
-                    : ng == 8 ? launch_fused<8, false>(fa, want_mask, n_items, T.sm_count, st)
-                              : launch_fused<7, false>(fa, want_mask, n_items, T.sm_count, st);
+            int rc = ng == 4 ? launch_fused<4>(fa, want_mask, n_items, T.sm_count, st)
+                   : ng == 6 ? launch_fused<6>(fa, want_mask, n_items, T.sm_count, st)
+                   : ng == 8 ? launch_fused<8>(fa, want_mask, n_items, T.sm_count, st)
+                             : launch_fused<7>(fa, want_mask, n_items, T.sm_count, st);
             if (rc != RMPE_OK) return rc;
             mask_done = want_mask;
         }

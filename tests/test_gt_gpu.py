@@ -336,20 +336,23 @@ for seed0, P, hw in ((700, 3, (368, 368)), (720, 2, (240, 320)), (740, 4, (427, 
     ss = b["scale_self"] * np.random.RandomState(seed0).uniform(0.5, 2.5, 6)
     M = rmpe_b200.batch.aug_affine(flip, [a[1] for a in b["augs"]], [a[2] for a in b["augs"]], [a[3] for a in b["augs"]],
                                    b["centers"], ss)
-    r = rmpe_b200.batch.gt_batch_host(b["imgs"], b["masks"], b["joints"], b["n_persons"], M, flip, want_count=True)
+    import os
+    r = rmpe_b200.batch.gt_batch_host(b["imgs"], b["masks"], b["joints"], b["n_persons"], M, flip, want_count=True,
+                                      simple=bool(os.environ.get("RMPE_GT_SIMPLE")))
     for k in ("img", "mask", "labels", "joints", "count", "status"):
         h.update(np.ascontiguousarray(r[k]).tobytes())
 print("SHA", h.hexdigest())
 """
 
 
-@pytest.mark.parametrize("env", [{"RMPE_WARP_WIDE": "1"}, {"RMPE_WARP_WIDE": "1", "RMPE_WARP_GROUPS": "6"},
-                                 {"RMPE_WARP_GROUPS": "4"}, {"RMPE_WARP_GROUPS": "8"}, {"RMPE_RASTER_GROUPS": "2"},
-                                 {"RMPE_RASTER_GROUPS": "4"}],
-                         ids=["wide5", "wide6", "groups4", "groups8", "raster2", "raster4"])
+@pytest.mark.parametrize("env", [{"RMPE_WARP_GROUPS": "4"}, {"RMPE_WARP_GROUPS": "6"}, {"RMPE_WARP_GROUPS": "8"},
+                                 {"RMPE_WARP_PREFETCH": "1"}, {"RMPE_RASTER_GROUPS": "2"}, {"RMPE_RASTER_GROUPS": "4"},
+                                 {"RMPE_GT_SIMPLE": "1"}],
+                         ids=["groups4", "groups6", "groups8", "prefetch", "raster2", "raster4", "simple"])
 def test_kernel_variants_are_bit_identical(rmpe, env):
-    """The A/B variants kept in the library (footprint layout, tile groups per SM, rasteriser plane groups) read their
-    switch once per process: each runs in its own interpreter and must reproduce the default's outputs bit for bit."""
+    """The A/B variants kept in the library (tile groups per SM, L2 prefetch, rasteriser plane groups, straight-line kernels)
+    read their switch once per process: each runs in its own interpreter and must reproduce the default's outputs bit for
+    bit."""
     import os
     import subprocess
     import sys
@@ -357,7 +360,7 @@ def test_kernel_variants_are_bit_identical(rmpe, env):
 
     def run(extra):
         e = dict(os.environ)
-        for k in ("RMPE_WARP_WIDE", "RMPE_WARP_GROUPS", "RMPE_RASTER_GROUPS"):
+        for k in ("RMPE_WARP_GROUPS", "RMPE_WARP_PREFETCH", "RMPE_RASTER_GROUPS", "RMPE_GT_SIMPLE"):
             e.pop(k, None)
         e.update(extra)
         out = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT % ROOT], env=e, capture_output=True, text=True, timeout=600)
