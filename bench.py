@@ -247,7 +247,12 @@ def main():
 
     # CPU leg first: forked workers must not inherit a CUDA context
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    under_profiler = "NV_NSIGHT_INJECTION_TRANSPORT_TYPE" in os.environ   # set by ncu for the processes it launches
+    if under_profiler and not args.no_cpu:
+        # ncu injects into every child process; the forked CPU workers crash it (SIGSEGV).  A number printed under a
+        # profiler is never a bench value anyway.
+        print("bench.py: running under Nsight Compute, skipping the cpu_baseline leg", file=sys.stderr)
+    if rank == 0 and world == 1 and not args.no_cpu and not under_profiler:
         cpu = cpu_baseline()
 
     import torch
