@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
     uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem_raw);
     // the rasteriser that follows on the stream may be scheduled as soon as an SM is free (it waits for this grid's
     // completion itself before it touches the mask)
-    asm volatile("griddepcontrol.launch_dependents;");
+    pdl_trigger();
     const int group = threadIdx.x / kGroupThreads;
     const int t = threadIdx.x - group * kGroupThreads;
     const int warp = t >> 5, lane = t & 31;
@@ -1029,7 +1029,7 @@ __global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
     for (int q = 0; q < 4; q++) { y[q] = (pix + q) / kGrid; x[q] = (pix + q) - y[q] * kGrid; }
     // Launched with programmatic stream serialization behind k_warp_fused: everything above (joints, tables, limb records)
     // reads only the caller's inputs and overlaps the tail of the warp kernel; the 46x46 mask is its output, so wait here.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_wait();
     T m[4];
     {
         const T *mk = reinterpret_cast<const T *>(a.mask) + (size_t)b * kCells + pix;
@@ -1253,15 +1253,9 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
             const int kRsThreads = (kCellVec + 31) & ~31;
             const int pm = b->max_persons;
             const size_t smem = (size_t)kLimbs * pm * sizeof(LimbRec) + (size_t)pm * kParts * 3 * 8 + 2 * (size_t)kParts * pm * kGrid * 4;
-            cudaLaunchConfig_t cfg;
-            memset(&cfg, 0, sizeof(cfg));
-            cfg.gridDim = grid; cfg.blockDim = dim3(kRsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-            cudaLaunchAttribute pdl;
-            pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            pdl.val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = &pdl; cfg.numAttrs = 1;
-            if (ra.f64) RMPE_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_raster_small<double>, ra));
-            else RMPE_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_raster_small<float>, ra));
+            // programmatic stream serialization behind k_warp_fused (see the griddepcontrol.wait in the kernel)
+            if (ra.f64) RMPE_CUDA_TRY(launch_pdl(k_raster_small<double>, grid, dim3(kRsThreads), smem, st, ra));
+            else RMPE_CUDA_TRY(launch_pdl(k_raster_small<float>, grid, dim3(kRsThreads), smem, st, ra));
         } else {
             dim3 grid(3, b->batch);
             if (ra.f64) k_raster<double><<<grid, kRasterThreads, 0, st>>>(ra);
