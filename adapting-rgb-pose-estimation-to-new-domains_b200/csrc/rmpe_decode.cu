@@ -609,7 +609,8 @@ template <int KWX, int MAXROWS>
 __global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_constant__ MsJobs jobs, float thre1, int act_cap,
                                                               const ActEntry *__restrict__ act,
                                                               const float *__restrict__ act_A,
-                                                              const int32_t *__restrict__ act_count, int cand_cap,
+                                                              const int32_t *__restrict__ act_count,
+                                                              int32_t *__restrict__ next_item, int cand_cap,
                                                               int32_t *__restrict__ cand_key,
                                                               int32_t *__restrict__ cand_fp,
                                                               int32_t *__restrict__ cand_count,
@@ -622,9 +623,18 @@ __global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_const
     __shared__ int s_rng[RMPE_MAX_SCALES][4];
     __shared__ int s_loy[RMPE_MAX_SCALES][kScrRows];
     __shared__ int s_boff[RMPE_MAX_SCALES + 1], s_toff[RMPE_MAX_SCALES + 1];
+    __shared__ int s_item;
     const int n_act = min(*act_count, act_cap);
 
-    for (int ai = blockIdx.x; ai < n_act; ai += gridDim.x) {
+    // work items are handed out dynamically (one atomic per item): their cost is proportional to the number of
+    // active parts of the tile (1..18 for multi scale) and a CTA only sees a handful of them, so a static stride
+    // leaves the launch waiting for its unluckiest CTA
+    for (;;) {
+        __syncthreads();                                        // s_item of the previous round consumed
+        if (tid == 0) s_item = atomicAdd(next_item, 1);
+        __syncthreads();
+        const int ai = s_item;
+        if (ai >= n_act) break;
         const ActEntry E = act[ai];
         const MsJob &J = jobs.j[E.job];
         const int H = J.H, W = J.W, NS = J.n_scales;
@@ -1681,7 +1691,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
     double *ws_cand = (double *)take((size_t)B * kLimbs * MC * 4 * 8);
     int32_t *cand_key = (int32_t *)take(per_list * 2 * 4);
     int32_t *cand_fp = (int32_t *)take(per_list * 2 * 4);
-    int32_t *cand_count = (int32_t *)take(256);      // [0] candidates, [1..4] work items per kernel variant, [8] table error
+    int32_t *cand_count = (int32_t *)take(256);      // [0] candidates, [1..4] work items per kernel variant, [8] table error, [16..19] next item per variant
     int32_t *tab_err = cand_count + 8;
     const int act_cap = kActCap;
     ActEntry *act = (ActEntry *)take((size_t)4 * kActCap * sizeof(ActEntry));
@@ -1730,8 +1740,13 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
             size_t sm1 = 0, sm2 = 0, smM = 0, smB = 0;
             int n_tab = 0, max_len = 0;
             const int cand_cap = (int)std::min<size_t>(per_list * 2, (size_t)n * kParts * MP * 2);
-            if (f0 > 0) RMPE_CUDA_TRY(cudaMemsetAsync(cand_count, 0, 20, st));
-            const bool reuse_tables = (b->flags & RMPE_DECODE_REUSE_TABLES) != 0;
+            if (f0 > 0) {
+                RMPE_CUDA_TRY(cudaMemsetAsync(cand_count, 0, 20, st));
+                RMPE_CUDA_TRY(cudaMemsetAsync(cand_count + 16, 0, 16, st));
+            }
+            // the tables of a previous call are still there only if that call (same frames, same workspace) was ONE
+            // chunk: every further chunk rebuilds its tables in the same workspace region
+            const bool reuse_tables = (b->flags & RMPE_DECODE_REUSE_TABLES) != 0 && f0 == 0 && n == B;
             auto flush_tables = [&]() {
                 if (!n_tab) return;
                 if (reuse_tables) { n_tab = 0; max_len = 0; return; }
@@ -1740,6 +1755,9 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                 count_launch();
                 n_tab = 0; max_len = 0;
             };
+            // a chunk of screened frames only holds nothing but their tables: one memset for all of them
+            const bool tables_cleared = !reuse_tables && !any_single && !any_multi;
+            if (tables_cleared) RMPE_CUDA_TRY(cudaMemsetAsync(ws + frame_ws0, 0, o - frame_ws0, st));
             for (int i = 0; i < n; i++) {
                 if (!plans[i].screen) continue;
                 const RmpeFrameDesc &f = fr[i];
@@ -1757,7 +1775,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                     max_len = std::max(max_len, want.dst);
                 };
                 uint8_t *tp = u_ptr[i];
-                if (!reuse_tables) RMPE_CUDA_TRY(cudaMemsetAsync(tp, 0, p.bytes, st));   // row-mass maxima start at 0
+                if (!reuse_tables && !tables_cleared) RMPE_CUDA_TRY(cudaMemsetAsync(tp, 0, p.bytes, st));   // row-mass maxima start at 0
                 MsJob mj{};
                 for (int sI = 0; sI < f.n_scales; sI++) {
                     float *Ky = (float *)tp; tp += (size_t)f.height * p.kwy[sI] * 4;
@@ -1790,6 +1808,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
             auto screen = [&](const MsJobs &jobs, int nj, int mt, size_t smem, int variant, int slot) -> int {
                 if (!nj) return RMPE_OK;
                 int32_t *cnt = cand_count + 1 + slot;      // this variant's work-item counter (zeroed with cand_count)
+                int32_t *nxt = cand_count + 16 + slot;     // next item k_screen_pairs hands out
                 ActEntry *lst = act + (size_t)slot * act_cap;
                 float *lstA = act_A + (size_t)slot * act_cap * kParts;
                 // parts per work item: single-scale items are cheap to set up (balance first), multi-scale items
@@ -1806,16 +1825,16 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                     const int grid = sms * per_sm;
                     if (variant == 0)
                         RMPE_CUDA_TRY(launch_pdl(k_screen_pairs<10, kScrMaxSrcRows>, dim3(grid), dim3(kScrThreads), smem, st,
-                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, cand_cap, cand_key, cand_fp, cand_count, b->status));
+                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, nxt, cand_cap, cand_key, cand_fp, cand_count, b->status));
                     else if (variant == 1)
                         RMPE_CUDA_TRY(launch_pdl(k_screen_pairs<kScrMaxKW, kScrMaxSrcRows>, dim3(grid), dim3(kScrThreads), smem, st,
-                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, cand_cap, cand_key, cand_fp, cand_count, b->status));
+                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, nxt, cand_cap, cand_key, cand_fp, cand_count, b->status));
                     else if (variant == 2)
                         RMPE_CUDA_TRY(launch_pdl(k_screen_pairs<kMsKW, kMsMaxRows>, dim3(grid), dim3(kScrThreads), smem, st,
-                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, cand_cap, cand_key, cand_fp, cand_count, b->status));
+                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, nxt, cand_cap, cand_key, cand_fp, cand_count, b->status));
                     else
                         RMPE_CUDA_TRY(launch_pdl(k_screen_pairs<kMsKWBig, kMsMaxRowsBig>, dim3(grid), dim3(kScrThreads), smem, st,
-                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, cand_cap, cand_key, cand_fp, cand_count, b->status));
+                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, nxt, cand_cap, cand_key, cand_fp, cand_count, b->status));
                 }
                 count_launch(2);
                 return RMPE_OK;

@@ -309,26 +309,39 @@ __device__ __forceinline__ void store_row(const RowStore &rs, int j, unsigned bg
 }
 
 // the 8 destination rows (one cell row) of a warp: taps, stores, and the 8x8 -> 1 mask reduction of cv2.resize
-// returns the cell's float32 accumulator (valid in lanes 3 and 4 of the cell's 8-lane group)
+// returns the cell's float32 accumulator (valid in lane 3 of the cell's 8-lane group)
 template <int kMode, bool kWantMask>
-__device__ __forceinline__ float cell_rows(const TileCtx &c, const RowStore &rs, int r0, int mw, float b0, float b1) {
+__device__ __forceinline__ float cell_rows(const TileCtx &c, const RowStore &rs, int r0, float b0, float b1) {
 #pragma unroll
     for (int j = 0; j < 2; j++) store_row(rs, j, fused_row<kMode, false>(c, r0 + j));
-    float macc = 0.f;   // cv2.resize vertical pass, float32 FMA chain S3*b0 -> S2*b1 -> S1*b1 -> S0*b0
+    // rows 2..5 of the cell feed cv2.resize's 8:1 reduction of the mask: their mask bytes are collected in one word
+    // (byte j-2 = row j) and meet in lane 3 of the cell with THREE shuffles per cell row (one word from each of lanes
+    // 2, 4, 5) instead of two per mask row
+    unsigned mrows = 0;
 #pragma unroll
     for (int j = 5; j >= 2; j--) {
         const unsigned v4 = fused_row<kMode, kWantMask>(c, r0 + j);
         store_row(rs, j, v4);
-        if (kWantMask) {
-            // cv2.resize horizontal pass: exact int32 sum of (-192,1216,1216,-192) x cols 8c+2..8c+5
-            // (only lanes 2..5 of a cell carry a weight: 2+3 and 4+5 meet with xor 1, lanes 3 and 4 swap sums with xor 7;
-            // the total is valid in lanes 3 and 4 of the cell)
-            int v = (int)(v4 >> 24) * mw;
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 7);
-            const float Sj = (float)v;
-            macc = (j == 5) ? Sj * b0 : fmaf(Sj, (j == 2) ? b0 : b1, macc);
+        if (kWantMask) mrows = (mrows << 8) | (v4 >> 24);
+    }
+    float macc = 0.f;
+    if (kWantMask) {
+        const unsigned m2 = __shfl_up_sync(0xffffffffu, mrows, 1);
+        const unsigned m4 = __shfl_down_sync(0xffffffffu, mrows, 1);
+        const unsigned m5 = __shfl_down_sync(0xffffffffu, mrows, 2);
+        // horizontal pass: exact int32 sum of (-192,1216,1216,-192) x cols 8c+2..8c+5; vertical pass: float32 FMA chain
+        // S5*b0 -> S4*b1 -> S3*b1 -> S2*b0 (cv2.resize's order).  Meaningful in lane 3 of a cell only.
+        int S[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int inner = (int)__byte_perm(mrows, 0, 0x4440 + k) + (int)__byte_perm(m4, 0, 0x4440 + k);
+            const int outer = (int)__byte_perm(m2, 0, 0x4440 + k) + (int)__byte_perm(m5, 0, 0x4440 + k);
+            S[k] = 1216 * inner - 192 * outer;
         }
+        macc = (float)S[3] * b0;
+        macc = fmaf((float)S[2], b1, macc);
+        macc = fmaf((float)S[1], b1, macc);
+        macc = fmaf((float)S[0], b0, macc);
     }
 #pragma unroll
     for (int j = 6; j < 8; j++) store_row(rs, j, fused_row<kMode, false>(c, r0 + j));
@@ -365,7 +378,6 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
     }
 
     const int l7 = lane & 7;
-    const int mw = (l7 == 3 || l7 == 4) ? 1216 : ((l7 == 2 || l7 == 5) ? -192 : 0);
     const int pk_word = 3 * (lane >> 2) + (lane & 3);         // HWC row packing (store_row): lanes 4k+3 store nothing
     const unsigned pk_sel = (lane & 3) == 0 ? 0x4210u : ((lane & 3) == 1 ? 0x5421u : 0x6542u);
     const float sc = 1.0f / 4194304.0f;                       // 2^-22
@@ -577,9 +589,9 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
                           : out_sample + ((size_t)(y0 + r0) * kOutW + x0) * 3 + 4 * pk_word;
             rs.on = a.chw ? lane_on : ((lane & 3) != 3 && 4 * pk_word < 3 * tw);
             float macc;
-            if (staged) macc = cell_rows<0, kWantMask>(c, rs, r0, mw, b0, b1);
-            else if (outside) macc = cell_rows<1, kWantMask>(c, rs, r0, mw, b0, b1);
-            else macc = cell_rows<2, kWantMask>(c, rs, r0, mw, b0, b1);
+            if (staged) macc = cell_rows<0, kWantMask>(c, rs, r0, b0, b1);
+            else if (outside) macc = cell_rows<1, kWantMask>(c, rs, r0, b0, b1);
+            else macc = cell_rows<2, kWantMask>(c, rs, r0, b0, b1);
             if (kWantMask && l7 == 3 && lane_on) {
                 // rint, saturate; then /255.  (py_rmpe_transformer.py:92,95)
                 const int iv = min(255, max(0, __float2int_rn(macc)));

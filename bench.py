@@ -396,6 +396,33 @@ def main():
         e2e = {"value": world * BATCH / dt, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": n_e2e,
                "api": "rmpe_gt_batch_host (pinned host buffers; copies inside the call)"}
+        # what the interconnect alone takes for these bytes: the same pinned buffers copied in and out on two streams
+        # at once, no kernels (explains e2e against the device-resident value; not part of any timed figure above)
+        big_in = [keep[0], keep[1]]                       # imgs, masks
+        big_out = [keep[3], keep[5]]                      # img, labels
+        dev_in = [torch.empty_like(t, device=dev) for t in big_in]
+        dev_out = [torch.empty_like(t, device=dev) for t in big_out]
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+        def copies():
+            with torch.cuda.stream(s_in):
+                for d_, h_ in zip(dev_in, big_in):
+                    d_.copy_(h_, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                for d_, h_ in zip(dev_out, big_out):
+                    h_.copy_(d_, non_blocking=True)
+
+        copies()
+        torch.cuda.synchronize(dev)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            copies()
+        torch.cuda.synchronize(dev)
+        floor = max_ranks((time.perf_counter() - t0) / 5)
+        e2e["copy_floor_ms"] = floor * 1e3
+        e2e["frac_of_copy_floor"] = floor / dt
+        del dev_in, dev_out
 
     # ---- secondary metric: single-scale decode of ski.jpg-shaped frames ----
     decode = None

@@ -225,6 +225,28 @@ def test_random_frame_shapes(rmpe, seed):
     assert np.array_equal(r["subset"], o[1])
 
 
+def test_plan_of_many_shapes_rerun(rmpe):
+    """A device plan over more frames than one chunk (32) with a different shape per frame, run twice: the second run
+    asks for table reuse, which only holds for single-chunk batches (every chunk rebuilds its operator tables in the
+    same workspace region) -- found with the 1000-frame COCO-val-shaped run of BASELINE configs[3]."""
+    rng = np.random.RandomState(77)
+    cases = [("m%d" % k, int(rng.randint(48, 200)), int(rng.randint(48, 260)), int(rng.randint(1, 4)), 31000 + k,
+              bool(k % 2)) for k in range(40)]
+    frames = [frames_of(c) for c in cases]
+    plan = rmpe.batch.DecodeDevicePlan(frames)
+    plan.run()
+    res = plan.results()
+    plan.run()
+    plan.run()
+    res2 = plan.results()
+    for c, a, b in zip(cases, res, res2):
+        assert a["status"] == 0 and b["status"] == 0, c
+        assert np.array_equal(a["candidate"], b["candidate"]) and np.array_equal(a["subset"], b["subset"]), c
+    for i in (0, 17, 33, 39):
+        o = _oracle(cases[i], detail=False)
+        assert np.array_equal(res2[i]["candidate"], o[0]) and np.array_equal(res2[i]["subset"], o[1]), cases[i]
+
+
 def test_full_size_decode_batch_properties(rmpe):
     """BASELINE config 3 size on one device (64 ski-shaped frames in one call): a few frames equal the oracle,
     size-independent properties hold for all, and a second run is bit-identical (atomics only feed sorted lists)."""

@@ -97,7 +97,14 @@ def main():
     dp = rmpe_b200.batch.DecodeDevicePlan(frames)
     ms = ev_time(dp.run, max(3, args.iters // 2), warm=2)
     res = dp.results()
+    import time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dp.run()
+    host_ms = (time.perf_counter() - t0) * 1e3          # time the host needs to enqueue one pass (no synchronisation)
+    torch.cuda.synchronize()
     print(json.dumps({"config": "config3_multi_scale_coco_val_shapes", "frames": len(frames), "ms": ms,
+                      "host_enqueue_ms": host_ms,
                       "frames_per_s": len(frames) / ms * 1e3, "shapes": sorted(set(pick))[:6],
                       "persons_found_mean": float(np.mean([len(r["subset"]) for r in res])),
                       "status_nonzero": int(sum(1 for r in res if r["status"])),
