@@ -193,7 +193,7 @@ typedef struct RmpeFrameDesc {
 #define RMPE_DECODE_REUSE_TABLES 0x1 /* the workspace still holds the up-sampling/smoothing operator tables of a
                                         previous call with the same frames, capacities and workspace: skip rebuilding
                                         them (they depend on frame geometry only).  Honoured when the batch is processed
-                                        as one chunk (<= 32 frames that fit the workspace); larger batches reuse the
+                                        as one chunk (<= 64 frames that fit the workspace); larger batches reuse the
                                         table region per chunk and always rebuild */
 
 typedef struct RmpeDecodeBatch {
