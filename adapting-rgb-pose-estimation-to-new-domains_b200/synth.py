@@ -160,3 +160,26 @@ def single_scale_grid(H, W):
     """Output grid of the testing model for an unpadded (H,W) feed: three floor-halvings
     (SURVEY.md 8a D0)."""
     return ((H // 2) // 2) // 2, ((W // 2) // 2) // 2
+
+
+def multi_scale_feed_shapes(H, W, scale_search=(0.5, 1, 1.5, 2), boxsize=368, stride=8):
+    """eval_coco2014_multi_modes.py:61,69-71: per scale (resized height, pad_down, pad_right, blob rows, blob columns)."""
+    out = []
+    for x in scale_search:
+        m = x * boxsize / H
+        Ws, Hs = int(np.rint(W * m)), int(np.rint(H * m))
+        pd = 0 if Hs % stride == 0 else stride - Hs % stride
+        pr = 0 if Ws % stride == 0 else stride - Ws % stride
+        out.append((Hs, pd, pr, (Hs + pd) // stride, (Ws + pr) // stride))
+    return out
+
+
+def multi_scale_frame(seed, H, W, n_persons=3):
+    """One synthetic frame for process_multi_scale-style decode: the same persons rendered on the blob grid of every scale."""
+    _, _, persons = decode_blobs(seed, (H, W), (4, 4), n_persons)
+    sc = []
+    for (Hs, pd, pr, hs, ws) in multi_scale_feed_shapes(H, W):
+        paf, heat, _ = decode_blobs(seed + 1000 * len(sc), (H, W), (hs, ws), n_persons, persons=persons, stride=8.0 * H / Hs)
+        sc.append((paf, heat, pd, pr))
+    return dict(H=H, W=W, scales=sc)
+

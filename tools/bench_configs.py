@@ -45,18 +45,6 @@ def kernels(L, fn, iters=3):
     return out
 
 
-def multi_scale_feed_shapes(H, W, scale_search=(0.5, 1, 1.5, 2), boxsize=368, stride=8):
-    """eval_coco2014_multi_modes.py:61,69-71: per scale (pad_down, pad_right, hs, ws)."""
-    out = []
-    for x in scale_search:
-        m = x * boxsize / H
-        Ws, Hs = int(np.rint(W * m)), int(np.rint(H * m))
-        pd = 0 if Hs % stride == 0 else stride - Hs % stride
-        pr = 0 if Ws % stride == 0 else stride - Ws % stride
-        out.append((Hs, pd, pr, (Hs + pd) // stride, (Ws + pr) // stride))
-    return out
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=32)
@@ -86,14 +74,7 @@ def main():
     rng = np.random.RandomState(0)
     pool = [(hh, ww) for hh, ww, c in shapes for _ in range(c)]
     pick = [pool[i] for i in rng.choice(len(pool), size=args.frames, replace=False)]
-    frames = []
-    for i, (H, W) in enumerate(pick):
-        _, _, persons = S.decode_blobs(700 + i, (H, W), (4, 4), 3)
-        sc = []
-        for (Hs, pd, pr, hs, ws) in multi_scale_feed_shapes(H, W):
-            paf, heat, _ = S.decode_blobs(700 + i + 1000 * len(sc), (H, W), (hs, ws), 3, persons=persons, stride=8.0 * H / Hs)
-            sc.append((paf, heat, pd, pr))
-        frames.append(dict(H=H, W=W, scales=sc))
+    frames = [S.multi_scale_frame(700 + i, H, W, 3) for i, (H, W) in enumerate(pick)]
     dp = rmpe_b200.batch.DecodeDevicePlan(frames)
     ms = ev_time(dp.run, max(3, args.iters // 2), warm=2)
     res = dp.results()

@@ -24,6 +24,10 @@ def main():
     paf, heat, _ = rmpe_b200.synth.decode_blobs(3, (H, W), (h, w), 4)
     res = rmpe_b200.batch.decode_batch_host([dict(H=H, W=W, scales=[(paf, heat, 0, 0)])] * 2)
     assert res[0]["status"] == 0
+    # multi scale (4 scales, eval_method 1): two frames of different shapes
+    frames = [rmpe_b200.synth.multi_scale_frame(50 + i, H, W, 2) for i, (H, W) in enumerate(((120, 160), (97, 141)))]
+    res2 = rmpe_b200.batch.decode_batch_host(frames)
+    assert all(r["status"] == 0 for r in res2)
     print("sanitize_once done:", len(res[0]["subset"]), "persons")
 
 
