@@ -290,12 +290,14 @@ struct RowStore {
     uint8_t *op;        // HWC: this lane's word of the first row of the warp; CHW: pixel `lane` of plane 0
     unsigned pk_sel;
     bool on;
-    int chw;
 };
 
-// store destination row j (0..7) of the warp, one pixel per lane
+// store destination row j (0..7) of the warp, one pixel per lane.  The image layout is a template parameter of the
+// kernel: a run-time test here put a branch, a divergence check around the shuffle and a re-materialised output pointer
+// into every row (12 instructions where 4 do).
+template <bool kChw>
 __device__ __forceinline__ void store_row(const RowStore &rs, int j, unsigned bgr) {
-    if (!rs.chw) {
+    if (!kChw) {
         // 24 words of the 96-byte row.  Pixel l starts at byte 3l, so lane l = 4k + m (m = 0, 1, 2) holds, together with
         // its right neighbour's pixel, exactly the aligned word 3k + m (bytes 12k + 4m ..): ONE shuffle per row.
         const unsigned nb = __shfl_down_sync(0xffffffffu, bgr, 1);
@@ -310,10 +312,10 @@ __device__ __forceinline__ void store_row(const RowStore &rs, int j, unsigned bg
 
 // the 8 destination rows (one cell row) of a warp: taps, stores, and the 8x8 -> 1 mask reduction of cv2.resize
 // returns the cell's float32 accumulator (valid in lane 3 of the cell's 8-lane group)
-template <int kMode, bool kWantMask>
+template <int kMode, bool kWantMask, bool kChw>
 __device__ __forceinline__ float cell_rows(const TileCtx &c, const RowStore &rs, int r0, float b0, float b1) {
 #pragma unroll
-    for (int j = 0; j < 2; j++) store_row(rs, j, fused_row<kMode, false>(c, r0 + j));
+    for (int j = 0; j < 2; j++) store_row<kChw>(rs, j, fused_row<kMode, false>(c, r0 + j));
     // rows 2..5 of the cell feed cv2.resize's 8:1 reduction of the mask: their mask bytes are collected in one word
     // (byte j-2 = row j) and meet in lane 3 of the cell with THREE shuffles per cell row (one word from each of lanes
     // 2, 4, 5) instead of two per mask row
@@ -321,7 +323,7 @@ __device__ __forceinline__ float cell_rows(const TileCtx &c, const RowStore &rs,
 #pragma unroll
     for (int j = 5; j >= 2; j--) {
         const unsigned v4 = fused_row<kMode, kWantMask>(c, r0 + j);
-        store_row(rs, j, v4);
+        store_row<kChw>(rs, j, v4);
         if (kWantMask) mrows = (mrows << 8) | (v4 >> 24);
     }
     float macc = 0.f;
@@ -344,11 +346,11 @@ __device__ __forceinline__ float cell_rows(const TileCtx &c, const RowStore &rs,
         macc = fmaf((float)S[0], b0, macc);
     }
 #pragma unroll
-    for (int j = 6; j < 8; j++) store_row(rs, j, fused_row<kMode, false>(c, r0 + j));
+    for (int j = 6; j < 8; j++) store_row<kChw>(rs, j, fused_row<kMode, false>(c, r0 + j));
     return macc;
 }
 
-template <int NG, bool kWantMask>
+template <int NG, bool kWantMask, bool kChw>
 __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a, int n_items) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem_raw);
@@ -584,14 +586,14 @@ __global__ void __launch_bounds__(NG *kGroupThreads, 1) k_warp_fused(FusedArgs a
             const int r0 = 8 * warp;
             uint8_t *out_sample = a.out_img + (size_t)sample * (3 * kOutW * kOutH);
             RowStore rs;
-            rs.chw = a.chw; rs.pk_sel = pk_sel;
-            rs.op = a.chw ? out_sample + (size_t)(y0 + r0) * kOutW + x0 + lane
+            rs.pk_sel = pk_sel;
+            rs.op = kChw ? out_sample + (size_t)(y0 + r0) * kOutW + x0 + lane
                           : out_sample + ((size_t)(y0 + r0) * kOutW + x0) * 3 + 4 * pk_word;
-            rs.on = a.chw ? lane_on : ((lane & 3) != 3 && 4 * pk_word < 3 * tw);
+            rs.on = kChw ? lane_on : ((lane & 3) != 3 && 4 * pk_word < 3 * tw);
             float macc;
-            if (staged) macc = cell_rows<0, kWantMask>(c, rs, r0, b0, b1);
-            else if (outside) macc = cell_rows<1, kWantMask>(c, rs, r0, b0, b1);
-            else macc = cell_rows<2, kWantMask>(c, rs, r0, b0, b1);
+            if (staged) macc = cell_rows<0, kWantMask, kChw>(c, rs, r0, b0, b1);
+            else if (outside) macc = cell_rows<1, kWantMask, kChw>(c, rs, r0, b0, b1);
+            else macc = cell_rows<2, kWantMask, kChw>(c, rs, r0, b0, b1);
             if (kWantMask && l7 == 3 && lane_on) {
                 // rint, saturate; then /255.  (py_rmpe_transformer.py:92,95)
                 const int iv = min(255, max(0, __float2int_rn(macc)));
@@ -1163,13 +1165,21 @@ static int launch_fused(const FusedArgs &fa_, bool want_mask, int n_items, int s
     const size_t smem = fused_smem_bytes(NG);
     static bool attr_set = false;
     if (!attr_set) {
-        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const int grid = min((n_items + NG - 1) / NG, sm_count);
-    if (want_mask) k_warp_fused<NG, true><<<grid, NG * kGroupThreads, smem, st>>>(fa, n_items);
-    else k_warp_fused<NG, false><<<grid, NG * kGroupThreads, smem, st>>>(fa, n_items);
+    const dim3 block(NG * kGroupThreads);
+    if (fa.chw) {
+        if (want_mask) k_warp_fused<NG, true, true><<<grid, block, smem, st>>>(fa, n_items);
+        else k_warp_fused<NG, false, true><<<grid, block, smem, st>>>(fa, n_items);
+    } else {
+        if (want_mask) k_warp_fused<NG, true, false><<<grid, block, smem, st>>>(fa, n_items);
+        else k_warp_fused<NG, false, false><<<grid, block, smem, st>>>(fa, n_items);
+    }
     return RMPE_OK;
 }
 
