@@ -1811,14 +1811,19 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                 int32_t *nxt = cand_count + 16 + slot;     // next item k_screen_pairs hands out
                 ActEntry *lst = act + (size_t)slot * act_cap;
                 float *lstA = act_A + (size_t)slot * act_cap * kParts;
-                // parts per work item: single-scale items are cheap to set up (balance first), multi-scale items
+                // parts per work item (measured): single-scale items are cheap to set up (three parts), multi-scale items
                 // stage the operators of four scales (amortise them over up to six active parts of the tile)
                 static const int ms_group = [] {      // measured on 512 COCO-val-shaped frames: 18 parts per item 18.1 k frames/s, 9: 19.3 k, 6: 19.4 k
                     const char *e = getenv("RMPE_MS_GROUP");
                     int v = e ? atoi(e) : 6;
                     return (v >= 1 && v <= kParts) ? v : 6;
                 }();
-                const int group = (variant >= 2) ? ms_group : 2;
+                static const int ss_group = [] {      // 8 ski-shaped frames: 1 part per item 0.115 ms, 2: 0.109, 3: 0.107, 4: 0.111
+                    const char *e = getenv("RMPE_SS_GROUP");
+                    int v = e ? atoi(e) : 3;
+                    return (v >= 1 && v <= kParts) ? v : 3;
+                }();
+                const int group = (variant >= 2) ? ms_group : ss_group;
                 {
                     ProfScope ps("k_screen_plan", st);
                     k_screen_plan<<<dim3(mt, nj), kPlanThreads, 0, st>>>(jobs, (float)b->thre1, act_cap, group, lst, lstA, cnt, tab_err,
