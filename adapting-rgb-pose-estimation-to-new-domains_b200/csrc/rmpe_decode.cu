@@ -1450,6 +1450,7 @@ struct FramePlan {
 };
 
 static size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+constexpr int kScreenSlots = 5;     // launch groups of k_screen_pairs per chunk: single scale (2 widths), multi scale (light, heavy, wide)
 constexpr int kActCap = 1 << 15;   // work items per kernel variant and chunk (0.5 MB + 2.3 MB of bounds each)
 
 static int ceil_div_d(double a) { return (int)ceil(a - 1e-9); }
@@ -1521,13 +1522,16 @@ static FramePlan plan_frame(const RmpeFrameDesc &f, int stride, bool allow_scree
     return p;
 }
 
+// resident CTAs of k_screen_pairs per SM for a dynamic shared-memory need (+ static shared memory / reserve)
+static int ctas_per_sm(size_t smem) { return std::max(1, std::min(6, (int)((224 * 1024) / (std::max<size_t>(smem, 1) + 2048)))); }
+
 static size_t fixed_ws_bytes(int batch, int max_peaks, int max_cand) {
     size_t per_list = (size_t)batch * kParts * max_peaks;
     return al256(per_list * 4) /*raw_key*/ + al256(per_list * 8) /*raw_score*/ + al256((size_t)batch * kParts * 4) /*raw_count*/ +
            al256(per_list * 4) * 2 /*pk_x, pk_y*/ + al256(per_list * 8) /*pk_s*/ +
            al256((size_t)batch * kLimbs * max_cand * 4 * 8) /*ws_cand*/ +
            al256(per_list * 2 * 4) * 2 /*cand_key, cand_fp*/ + 256 /*cand_count, tab_err*/ +
-           al256((size_t)4 * kActCap * sizeof(ActEntry)) + al256((size_t)4 * kActCap * kParts * 4) /*work items*/ + 4096;
+           al256((size_t)kScreenSlots * kActCap * sizeof(ActEntry)) + al256((size_t)kScreenSlots * kActCap * kParts * 4) /*work items*/ + 4096;
 }
 
 static bool frame_ok(const RmpeFrameDesc &f, int stride) {
@@ -1648,14 +1652,17 @@ using namespace rmpe;
 
 extern "C" size_t rmpe_decode_workspace_bytes(int batch, const RmpeFrameDesc *frames_host, int max_peaks, int max_cand) {
     if (batch <= 0 || !frames_host) return 0;
-    // enough for chunks of up to 32 of the largest frame (a chunk takes up to kChunkFrames frames while they fit)
-    size_t biggest = 0;
+    // enough for a full chunk (kChunkFrames) of the largest screened frame -- those only keep their operator tables here,
+    // a few hundred KB each -- and for up to 32 of the largest frame that needs materialised maps (tens of MB each);
+    // a chunk takes frames while they fit, so any size that holds one frame works
+    size_t big_screen = 0, big_mat = 0;
     for (int i = 0; i < batch; i++) {
-        size_t b = plan_frame(frames_host[i], 8).bytes;
-        if (b > biggest) biggest = b;
+        const FramePlan p = plan_frame(frames_host[i], 8);
+        size_t &b = p.screen ? big_screen : big_mat;
+        if (p.bytes > b) b = p.bytes;
     }
-    int chunk = batch < 32 ? batch : 32;
-    return fixed_ws_bytes(batch, max_peaks, max_cand) + biggest * chunk + 4096;
+    const size_t n_screen = batch < kChunkFrames ? batch : kChunkFrames, n_mat = batch < 32 ? batch : 32;
+    return fixed_ws_bytes(batch, max_peaks, max_cand) + std::max(big_screen * n_screen, big_mat * n_mat) + 4096;
 }
 
 extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
@@ -1691,11 +1698,11 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
     double *ws_cand = (double *)take((size_t)B * kLimbs * MC * 4 * 8);
     int32_t *cand_key = (int32_t *)take(per_list * 2 * 4);
     int32_t *cand_fp = (int32_t *)take(per_list * 2 * 4);
-    int32_t *cand_count = (int32_t *)take(256);      // [0] candidates, [1..4] work items per kernel variant, [8] table error, [16..19] next item per variant
+    int32_t *cand_count = (int32_t *)take(256);      // [0] candidates, [1..5] work items per launch group, [8] table error, [16..20] next item per launch group
     int32_t *tab_err = cand_count + 8;
     const int act_cap = kActCap;
-    ActEntry *act = (ActEntry *)take((size_t)4 * kActCap * sizeof(ActEntry));
-    float *act_A = (float *)take((size_t)4 * kActCap * kParts * sizeof(float));
+    ActEntry *act = (ActEntry *)take((size_t)kScreenSlots * kActCap * sizeof(ActEntry));
+    float *act_A = (float *)take((size_t)kScreenSlots * kActCap * kParts * sizeof(float));
     RMPE_REQUIRE(off <= b->workspace_bytes, "workspace too small (see rmpe_decode_workspace_bytes)");
     const size_t frame_ws0 = off;
 
@@ -1735,14 +1742,17 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
         if (any_screen) {
             // ---- screen in float32 straight from the blobs, decide exactly per surviving pixel ----
             AxisJobs aj{};
-            MsJobs jobs1{}, jobs2{}, jobsM{}, jobsB{};      // single scale (Kx <= 10 / <= 12 wide), multi scale, multi scale wide
-            int n1 = 0, n2 = 0, nM = 0, nB = 0, t1 = 0, t2 = 0, tM = 0, tB = 0;
-            size_t sm1 = 0, sm2 = 0, smM = 0, smB = 0;
+            // single scale (Kx <= 10 / <= 12 wide), multi scale (two CTAs per SM fit / only one fits), multi scale wide.
+            // A launch allocates the largest shared-memory need among its frames: ONE frame above ~110 KB used to put a
+            // whole chunk at one CTA per SM (9 % of the COCO-val shapes are that wide, i.e. nearly every chunk of 64)
+            MsJobs jobs1{}, jobs2{}, jobsM{}, jobsH{}, jobsB{};
+            int n1 = 0, n2 = 0, nM = 0, nH = 0, nB = 0, t1 = 0, t2 = 0, tM = 0, tH = 0, tB = 0;
+            size_t sm1 = 0, sm2 = 0, smM = 0, smH = 0, smB = 0;
             int n_tab = 0, max_len = 0;
             const int cand_cap = (int)std::min<size_t>(per_list * 2, (size_t)n * kParts * MP * 2);
             if (f0 > 0) {
-                RMPE_CUDA_TRY(cudaMemsetAsync(cand_count, 0, 20, st));
-                RMPE_CUDA_TRY(cudaMemsetAsync(cand_count + 16, 0, 16, st));
+                RMPE_CUDA_TRY(cudaMemsetAsync(cand_count, 0, 4 * (1 + kScreenSlots), st));
+                RMPE_CUDA_TRY(cudaMemsetAsync(cand_count + 16, 0, 4 * kScreenSlots, st));
             }
             // the tables of a previous call are still there only if that call (same frames, same workspace) was ONE
             // chunk: every further chunk rebuilds its tables in the same workspace region
@@ -1798,7 +1808,8 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                 mj.tiles_x = (f.width + kScrTW - 1) / kScrTW;
                 mj.tiles = mj.tiles_x * ((f.height + kScrTH - 1) / kScrTH);
                 if (p.multi && p.big) { jobsB.j[nB++] = mj; tB = std::max(tB, mj.tiles); smB = std::max(smB, p.smem); }
-                else if (p.multi) { jobsM.j[nM++] = mj; tM = std::max(tM, mj.tiles); smM = std::max(smM, p.smem); }
+                else if (p.multi && ctas_per_sm(p.smem) >= 2) { jobsM.j[nM++] = mj; tM = std::max(tM, mj.tiles); smM = std::max(smM, p.smem); }
+                else if (p.multi) { jobsH.j[nH++] = mj; tH = std::max(tH, mj.tiles); smH = std::max(smH, p.smem); }
                 else if (p.kwx[0] <= 10) { jobs1.j[n1++] = mj; t1 = std::max(t1, mj.tiles); sm1 = std::max(sm1, p.smem); }
                 else { jobs2.j[n2++] = mj; t2 = std::max(t2, mj.tiles); sm2 = std::max(sm2, p.smem); }
             }
@@ -1831,7 +1842,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                 }
                 {
                     ProfScope ps("k_screen_pairs", st);
-                    const int per_sm = std::max(1, std::min(6, (int)((224 * 1024) / (std::max<size_t>(smem, 1) + 2048))));   // + static smem / reserve
+                    const int per_sm = ctas_per_sm(smem);
                     const int grid = sms * per_sm;
                     if (variant == 0)
                         RMPE_CUDA_TRY(launch_pdl(k_screen_pairs<10, kScrMaxSrcRows>, dim3(grid), dim3(kScrThreads), smem, st,
@@ -1853,6 +1864,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
             screen(jobs2, n2, t2, sm2, 1, 1);
             screen(jobsM, nM, tM, smM, 2, 2);
             screen(jobsB, nB, tB, smB, 3, 3);
+            screen(jobsH, nH, tH, smH, 2, 4);
             {
                 ProfScope ps("k_peak_verify", st);
                 const int grid = std::min(cand_cap, 8 * sms);
