@@ -605,6 +605,16 @@ __device__ __forceinline__ void ms_vertical(const float *__restrict__ sT, const 
     }
 }
 
+// ms_vertical over the staged rows [i0, end) only, NR of them (a multiple of four, >= end - i0); the window is moved down
+// if it would leave the MAXROWS-wide rows of Ky
+template <int NR, int MAXROWS>
+__device__ __forceinline__ void band_vertical(const float *__restrict__ sT, const float *__restrict__ sKy, int i0, int end,
+                                              int col, int half, float acc[kScrRows / 2]) {
+    static_assert(NR <= MAXROWS && NR % 4 == 0 && MAXROWS % 4 == 0, "float4 rows of Ky");
+    i0 = min(i0, MAXROWS - NR);
+    ms_vertical<NR, MAXROWS>(sT + i0 * kScrCols, sKy + i0, col, half, end - i0, acc);
+}
+
 template <int KWX, int MAXROWS>
 __global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_constant__ MsJobs jobs, float thre1, int act_cap,
                                                               const ActEntry *__restrict__ act,
@@ -623,6 +633,7 @@ __global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_const
     __shared__ int s_rng[RMPE_MAX_SCALES][4];
     __shared__ int s_loy[RMPE_MAX_SCALES][kScrRows];
     __shared__ int s_boff[RMPE_MAX_SCALES + 1], s_toff[RMPE_MAX_SCALES + 1];
+    __shared__ int s_band[RMPE_MAX_SCALES][2][2];   // staged rows [first, end) that the 17 tile rows of a half touch
     __shared__ int s_item;
     const int n_act = min(*act_count, act_cap);
 
@@ -651,6 +662,17 @@ __global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_const
                 s_toff[sc] = to; to += nr * kScrCols;
             }
             s_boff[NS] = bo; s_toff[NS] = to;
+        }
+        if (tid >= 32 && tid < 32 + 2 * NS) {
+            // Ky is zero outside [loy[r], loy[r] + kwy) of its row: the vertical pass of a half only needs that band
+            const int sc = (tid - 32) >> 1, hf = (tid - 32) & 1, r0 = s_rng[sc][0];
+            int lo = INT_MAX, hi = 0;
+            for (int r = hf * (kScrRows / 2); r < (hf + 1) * (kScrRows / 2); r++) {
+                lo = min(lo, s_loy[sc][r] - r0);
+                hi = max(hi, s_loy[sc][r] - r0 + J.sc[sc].kwy);
+            }
+            s_band[sc][hf][0] = max(lo, 0) & ~3;        // Ky rows are read as float4
+            s_band[sc][hf][1] = min(hi, s_rng[sc][1] - r0 + 1);
         }
         __syncthreads();
         float *sBall = reinterpret_cast<float *>(sm_raw);                 // 2 x [sc][nrows][ncols + KWX]: this part / next part
@@ -734,12 +756,16 @@ __global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_const
 #pragma unroll
             for (int q = 0; q < kScrRows / 2; q++) acc[q] = 0.f;
             for (int sc = 0; sc < NS; sc++) {
-                const int nrows = s_rng[sc][1] - s_rng[sc][0] + 1;
                 const float *sT = sTall + s_toff[sc];
                 const float *sKy = sKyAll + sc * kScrRows * MAXROWS;
-                if (MAXROWS > 16 && nrows > 16) ms_vertical<MAXROWS, MAXROWS>(sT, sKy, col, half, nrows, acc);
-                else if (nrows > 8) ms_vertical<16, MAXROWS>(sT, sKy, col, half, nrows, acc);
-                else ms_vertical<8, MAXROWS>(sT, sKy, col, half, nrows, acc);
+                // only the band of staged rows this half's 17 tile rows touch (the rest of Ky is zero: same sums)
+                const int i0 = s_band[sc][half][0], end = s_band[sc][half][1], len = end - i0;
+                if (len <= 8) band_vertical<8, MAXROWS>(sT, sKy, i0, end, col, half, acc);
+                else if (len <= 12) band_vertical<12, MAXROWS>(sT, sKy, i0, end, col, half, acc);
+                else if (MAXROWS <= 16 || len <= 16) band_vertical<16, MAXROWS>(sT, sKy, i0, end, col, half, acc);
+                else if (len <= 20) band_vertical<(MAXROWS >= 20 ? 20 : MAXROWS), MAXROWS>(sT, sKy, i0, end, col, half, acc);
+                else if (MAXROWS <= 24 || len <= 24) band_vertical<(MAXROWS >= 24 ? 24 : MAXROWS), MAXROWS>(sT, sKy, i0, end, col, half, acc);
+                else band_vertical<MAXROWS, MAXROWS>(sT, sKy, i0, end, col, half, acc);
             }
 #pragma unroll
             for (int q = 0; q < kScrRows / 2; q++) sS[(half * (kScrRows / 2) + q) * kScrCols + col] = acc[q];
