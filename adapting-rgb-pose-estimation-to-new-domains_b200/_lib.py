@@ -16,6 +16,7 @@ GT_NO_TRANSFORM = 0x4
 GT_NO_WARP = 0x8
 GT_SIMPLE_KERNELS = 0x10
 GT_WARP_ONLY = 0x20
+GT_PAF_AVERAGE = 0x40
 
 ST_ZERO_LIMB = 0x1
 ST_PEAK_OVERFLOW = 0x2
@@ -23,6 +24,8 @@ ST_CAND_OVERFLOW = 0x4
 ST_PERSON_OVERFLOW = 0x8
 ST_FOUND_GT2 = 0x10
 ST_SINGULAR = 0x20
+ST_PERSONS_CLAMPED = 0x40
+ABI_VERSION = 2
 
 MAX_SCALES = 4
 DECODE_REUSE_TABLES = 0x1
@@ -33,7 +36,7 @@ EXPORTS = [
     "rmpe_decode_workspace_bytes", "rmpe_decode_batch", "rmpe_decode_batch_host",
     "rmpe_debug_heat_maps", "rmpe_debug_paf_points", "rmpe_pad_right_down_corner",
     "rmpe_launch_count", "rmpe_profile_enable", "rmpe_profile_reset", "rmpe_profile_count",
-    "rmpe_profile_get", "rmpe_keras_batch", "rmpe_keras_batch_host",
+    "rmpe_profile_get", "rmpe_keras_batch", "rmpe_keras_batch_host", "rmpe_debug_assemble",
 ]
 
 _vp = C.c_void_p
@@ -54,7 +57,9 @@ class GtBatch(C.Structure):
                 ("src_img", _vp), ("src_mask", _vp), ("src_desc", _vp), ("joints", _vp),
                 ("n_persons", _vp), ("M", _vp), ("flip", _vp),
                 ("out_img", _vp), ("out_mask", _vp), ("out_labels", _vp), ("out_joints", _vp),
-                ("out_count", _vp), ("status", _vp)]
+                ("out_count", _vp), ("status", _vp),
+                ("sigma", C.c_double), ("thre", C.c_double),
+                ("out_vec_label", _vp), ("out_heat_label", _vp), ("out_vec_weights", _vp), ("out_heat_weights", _vp)]
 
 
 class GtBatchHost(C.Structure):
@@ -63,7 +68,9 @@ class GtBatchHost(C.Structure):
                 ("src_img", _vp), ("src_mask", _vp), ("joints", _vp), ("n_persons", _vp),
                 ("M", _vp), ("flip", _vp),
                 ("out_img", _vp), ("out_mask", _vp), ("out_labels", _vp), ("out_joints", _vp),
-                ("out_count", _vp), ("status", _vp)]
+                ("out_count", _vp), ("status", _vp),
+                ("sigma", C.c_double), ("thre", C.c_double),
+                ("out_vec_label", _vp), ("out_heat_label", _vp), ("out_vec_weights", _vp), ("out_heat_weights", _vp)]
 
 
 class KerasBatch(C.Structure):
@@ -138,7 +145,7 @@ def load():
     lib.rmpe_gt_batch.restype = C.c_int
     lib.rmpe_gt_batch_host.argtypes = [C.POINTER(GtBatchHost)]
     lib.rmpe_gt_batch_host.restype = C.c_int
-    lib.rmpe_decode_workspace_bytes.argtypes = [C.c_int, _vp, C.c_int, C.c_int]
+    lib.rmpe_decode_workspace_bytes.argtypes = [C.c_int, _vp, C.c_int, C.c_int, C.c_int]
     lib.rmpe_decode_workspace_bytes.restype = C.c_size_t
     lib.rmpe_decode_batch.argtypes = [C.POINTER(DecodeBatch), _vp]
     lib.rmpe_decode_batch.restype = C.c_int
@@ -160,6 +167,8 @@ def load():
     lib.rmpe_keras_batch.restype = C.c_int
     lib.rmpe_keras_batch_host.argtypes = [C.POINTER(KerasBatch)]
     lib.rmpe_keras_batch_host.restype = C.c_int
+    lib.rmpe_debug_assemble.argtypes = [C.c_int, C.c_int] + [_vp] * 8
+    lib.rmpe_debug_assemble.restype = C.c_int
     lib.rmpe_debug_bicubic_table.argtypes = [_vp]
     lib.rmpe_debug_bicubic_table.restype = C.c_int
     _lib = lib

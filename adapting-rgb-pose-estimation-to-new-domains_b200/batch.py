@@ -54,10 +54,13 @@ def aug_random(seeds):
 # GT, host buffers
 # ------------------------------------------------------------------------------------------
 def gt_batch_host(imgs, masks, joints, n_persons, M, flip, *, f64=False, chw=False, want_img=True,
-                  want_labels=True, want_count=False, simple=False, out=None):
+                  want_labels=True, want_count=False, simple=False, out=None, sigma=None, thre=None,
+                  keras=False, keras_weights=True, paf_average=False):
     """imgs (B,H,W,3) u8, masks (B,H,W) u8, joints (B,P,18,3) f64, n_persons (B,) i32,
     M (B,2,3) f64, flip (B,) u8.  Returns dict(img, mask, labels, joints, count, status).
-    `out` may carry preallocated (e.g. pinned) output arrays under the same keys."""
+    `out` may carry preallocated (e.g. pinned) output arrays under the same keys.
+    keras=True adds the NHWC tensors of DataIteratorBase.gen (training/ds_generators.py:52-63), written by the
+    rasteriser itself: y1 (B,46,46,38), y2 (B,46,46,19) and, with keras_weights, x1 / x2 (the mask repeated)."""
     lib = L.ensure_init()
     masks = L.c_contig(masks, np.uint8)
     B, H, W = masks.shape
@@ -72,22 +75,29 @@ def gt_batch_host(imgs, masks, joints, n_persons, M, flip, *, f64=False, chw=Fal
     flip = L.c_contig(flip, np.uint8).reshape(B)
     ft = np.float64 if f64 else np.float32
     out = dict(out or {})
+
+    def buf(key, shape, dtype):
+        a = out.get(key)
+        if a is None:
+            a = np.empty(shape, dtype)
+        assert a.shape == tuple(shape) and a.dtype == dtype and a.flags.c_contiguous, (key, a.shape, a.dtype)
+        return a
+
     res = {}
-    res["img"] = out.get("img") if want_img else None
-    if want_img and res["img"] is None:
-        res["img"] = np.empty((B, 3, G.height, G.width) if chw else (B, G.height, G.width, 3), np.uint8)
-    res["mask"] = out.get("mask") if out.get("mask") is not None else np.empty((B, GRID, GRID), ft)
-    res["labels"] = None
-    if want_labels:
-        res["labels"] = out.get("labels") if out.get("labels") is not None else np.empty((B, NL, GRID, GRID), ft)
-    res["joints"] = out.get("joints") if out.get("joints") is not None else np.empty((B, P, 18, 3), np.float64)
+    res["img"] = buf("img", (B, 3, G.height, G.width) if chw else (B, G.height, G.width, 3), np.uint8) if want_img else None
+    res["mask"] = buf("mask", (B, GRID, GRID), ft)
+    res["labels"] = buf("labels", (B, NL, GRID, GRID), ft) if want_labels else None
+    res["joints"] = buf("joints", (B, P, 18, 3), np.float64)
     res["count"] = np.empty((B, 19, GRID, GRID), np.int32) if want_count else None
     res["status"] = np.zeros(B, np.int32)
+    for k, c in (("y1", 38), ("y2", 19), ("x1", 38), ("x2", 19)):
+        res[k] = buf(k, (B, GRID, GRID, c), ft) if keras and (keras_weights or k[0] == "y") else None
     h = L.GtBatchHost()
     h.batch = B
     h.max_persons = P
     h.flags = (L.GT_LABELS_F64 if f64 else 0) | (L.GT_IMG_CHW if chw else 0) | \
-        (0 if want_img else L.GT_NO_WARP) | (L.GT_SIMPLE_KERNELS if simple else 0)
+        (0 if want_img else L.GT_NO_WARP) | (L.GT_SIMPLE_KERNELS if simple else 0) | \
+        (L.GT_PAF_AVERAGE if paf_average else 0)
     h.src_height, h.src_width = H, W
     h.src_img = L.ptr(imgs) if want_img else None
     h.src_mask = L.ptr(masks)
@@ -101,12 +111,16 @@ def gt_batch_host(imgs, masks, joints, n_persons, M, flip, *, f64=False, chw=Fal
     h.out_joints = L.ptr(res["joints"]) if P else None
     h.out_count = L.ptr(res["count"])
     h.status = L.ptr(res["status"])
+    h.sigma = float(sigma) if sigma is not None else 0.0
+    h.thre = float(thre) if thre is not None else 0.0
+    h.out_vec_label, h.out_heat_label = L.ptr(res["y1"]), L.ptr(res["y2"])
+    h.out_vec_weights, h.out_heat_weights = L.ptr(res["x1"]), L.ptr(res["x2"])
     L.check(lib.rmpe_gt_batch_host(C.byref(h)))
     return res
 
 
-def heatmaps_host(joints, n_persons, mask, *, f64=True, want_count=False):
-    """Heatmapper.create_heatmaps for a batch: joints (B,P,18,3) already in output coordinates,
+def heatmaps_host(joints, n_persons, mask, *, f64=True, want_count=False, sigma=None, thre=None, paf_average=False):
+    """Heatmapper(sigma, thre).create_heatmaps for a batch: joints (B,P,18,3) already in output coordinates,
     mask (B,46,46) in [0,1] (same dtype as the labels)."""
     lib = L.ensure_init()
     ft = np.float64 if f64 else np.float32
@@ -121,7 +135,9 @@ def heatmaps_host(joints, n_persons, mask, *, f64=True, want_count=False):
     h = L.GtBatchHost()
     h.batch = B
     h.max_persons = P
-    h.flags = L.GT_NO_TRANSFORM | (L.GT_LABELS_F64 if f64 else 0)
+    h.flags = L.GT_NO_TRANSFORM | (L.GT_LABELS_F64 if f64 else 0) | (L.GT_PAF_AVERAGE if paf_average else 0)
+    h.sigma = float(sigma) if sigma is not None else 0.0
+    h.thre = float(thre) if thre is not None else 0.0
     h.joints = L.ptr(joints) if P else None
     h.n_persons = L.ptr(n_persons)
     h.out_mask = L.ptr(mask)
@@ -163,7 +179,7 @@ class GtDevicePlan:
     the current torch stream and returns immediately."""
 
     def __init__(self, batch, max_persons, src_hw=(368, 368), f64=False, chw=False, want_count=False,
-                 device=None, keras=False):
+                 device=None, keras=False, sigma=None, thre=None):
         import torch
         self.torch = torch
         self.lib = L.ensure_init(device)
@@ -203,19 +219,19 @@ class GtDevicePlan:
         d.out_joints = L.ptr(self.out_joints)
         d.out_count = L.ptr(self.out_count)
         d.status = L.ptr(self.status)
+        d.sigma = float(sigma) if sigma is not None else 0.0
+        d.thre = float(thre) if thre is not None else 0.0
         self.desc_struct = d
-        self.keras = None
-        if keras:   # Keras-ready NHWC tensors (DataIteratorBase.gen) produced on the device right after the labels
+        self.keras = keras
+        if keras:   # Keras-ready NHWC tensors (DataIteratorBase.gen) written by the rasteriser itself
             self.x1 = torch.empty((batch, GRID, GRID, 38), dtype=ft, device=dev)
             self.x2 = torch.empty((batch, GRID, GRID, 19), dtype=ft, device=dev)
             self.y1 = torch.empty((batch, GRID, GRID, 38), dtype=ft, device=dev)
             self.y2 = torch.empty((batch, GRID, GRID, 19), dtype=ft, device=dev)
-            k = L.KerasBatch()
-            k.batch, k.flags = batch, (L.GT_LABELS_F64 if f64 else 0)
-            k.labels, k.mask = L.ptr(self.out_labels), L.ptr(self.out_mask)
-            k.vec_weights, k.heat_weights, k.vec_label, k.heat_label = (L.ptr(self.x1), L.ptr(self.x2), L.ptr(self.y1),
-                                                                        L.ptr(self.y2))
-            self.keras = k
+            d.out_vec_label, d.out_heat_label = L.ptr(self.y1), L.ptr(self.y2)
+            d.out_vec_weights, d.out_heat_weights = L.ptr(self.x1), L.ptr(self.x2)
+            if keras == "only":       # no planar labels at all
+                d.out_labels = None
 
     def upload(self, imgs, masks, joints, n_persons, M, flip, non_blocking=False):
         t = self.torch
@@ -235,8 +251,6 @@ class GtDevicePlan:
         if stream is None:
             stream = self.torch.cuda.current_stream(self.device).cuda_stream
         L.check(self.lib.rmpe_gt_batch(C.byref(d), C.c_void_p(stream)))
-        if self.keras is not None:
-            L.check(self.lib.rmpe_keras_batch(C.byref(self.keras), C.c_void_p(stream)))
 
 
 # ------------------------------------------------------------------------------------------
@@ -285,9 +299,16 @@ def decode_batch_host(frames, thre1=0.1, thre2=0.05, stride=8, max_peaks=128, ma
                       max_persons=64, want_limb_candidates=False):
     """Decode a list of frames (see make_frames) from host blobs; returns a list of dicts with
     candidate (N,4) f64, subset (M,20) f64, connections, special_k, status."""
-    lib = L.ensure_init()
     desc, heat, paf = make_frames(frames)
-    B = len(frames)
+    return decode_batch_host_raw(desc, heat, paf, thre1, thre2, stride, max_peaks, max_cand, max_persons,
+                                 want_limb_candidates)
+
+
+def decode_batch_host_raw(desc, heat, paf, thre1=0.1, thre2=0.05, stride=8, max_peaks=128, max_cand=1024,
+                          max_persons=64, want_limb_candidates=False):
+    """decode_batch_host on an already flattened batch: desc (FRAME_DESC_DTYPE array), heat / paf flat f32."""
+    lib = L.ensure_init()
+    B = len(desc)
     MP, MC, MS = max_peaks, max_cand, max_persons
     cand = np.zeros((B, 18 * MP, 4), np.float64)
     npk = np.zeros((B, 18), np.int32)
@@ -340,7 +361,7 @@ class DecodeDevicePlan:
         self.sub = torch.zeros((B, max_persons, 20), dtype=f64, device=dev)
         self.nsub = torch.zeros(B, dtype=torch.int32, device=dev)
         self.status = torch.zeros(B, dtype=torch.int32, device=dev)
-        need = int(self.lib.rmpe_decode_workspace_bytes(B, L.ptr(desc), max_peaks, max_cand))
+        need = int(self.lib.rmpe_decode_workspace_bytes(B, L.ptr(desc), max_peaks, max_cand, stride))
         if workspace_bytes is None:
             workspace_bytes = need
         self.workspace = torch.empty(int(workspace_bytes), dtype=torch.uint8, device=dev)

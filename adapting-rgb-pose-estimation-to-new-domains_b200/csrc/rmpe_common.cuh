@@ -60,9 +60,9 @@ struct DeviceTables {
     const int16_t *bicubic_i16;   // [32][32][4][4]  OpenCV initInterTab2D(INTER_CUBIC, fixpt)
     const uint32_t *bicubic_dp4a; // [32][32][4][2]  per tap row: {hi bytes (s8 x4), lo bytes (u8 x4)}
     int sm_count;
-    int32_t *counters;            // kCounterRing work counters of the persistent kernels, one 128-byte line each
+    int32_t *counters;            // kCounterRing work counters of the persistent kernels (one per stream), one 128-byte line each
 };
-constexpr int kCounterRing = 64;      // launches that may be in flight at once (each takes the next counter of the ring)
+constexpr int kCounterRing = 1024;    // work-counter slots of the persistent kernels: one per launching stream (rmpe_gt.cu)
 constexpr int kCounterStride = 32;    // int32 per counter line
 // Programmatic dependent launch: a kernel launched with launch_pdl may be scheduled while its predecessor on the stream
 // still runs (once every CTA of the predecessor has called pdl_trigger or exited); it must call pdl_wait before it reads

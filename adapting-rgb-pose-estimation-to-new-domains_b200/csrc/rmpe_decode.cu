@@ -1676,14 +1676,14 @@ static int ensure_smooth_attr() {
 
 using namespace rmpe;
 
-extern "C" size_t rmpe_decode_workspace_bytes(int batch, const RmpeFrameDesc *frames_host, int max_peaks, int max_cand) {
-    if (batch <= 0 || !frames_host) return 0;
+extern "C" size_t rmpe_decode_workspace_bytes(int batch, const RmpeFrameDesc *frames_host, int max_peaks, int max_cand, int stride) {
+    if (batch <= 0 || !frames_host || stride <= 0) return 0;
     // enough for a full chunk (kChunkFrames) of the largest screened frame -- those only keep their operator tables here,
     // a few hundred KB each -- and for up to 32 of the largest frame that needs materialised maps (tens of MB each);
     // a chunk takes frames while they fit, so any size that holds one frame works
     size_t big_screen = 0, big_mat = 0;
     for (int i = 0; i < batch; i++) {
-        const FramePlan p = plan_frame(frames_host[i], 8);
+        const FramePlan p = plan_frame(frames_host[i], stride);    // the same plan rmpe_decode_batch makes with b->stride
         size_t &b = p.screen ? big_screen : big_mat;
         if (p.bytes > b) b = p.bytes;
     }
@@ -1783,11 +1783,13 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
             // the tables of a previous call are still there only if that call (same frames, same workspace) was ONE
             // chunk: every further chunk rebuilds its tables in the same workspace region
             const bool reuse_tables = (b->flags & RMPE_DECODE_REUSE_TABLES) != 0 && f0 == 0 && n == B;
+            bool tables_failed = false;
             auto flush_tables = [&]() {
                 if (!n_tab) return;
                 if (reuse_tables) { n_tab = 0; max_len = 0; return; }
                 ProfScope ps("k_axis_tables", st);
                 k_axis_tables<<<dim3((max_len + 127) / 128, n_tab), 128, 0, st>>>(aj, tab_err);
+                if (cudaGetLastError() != cudaSuccess) tables_failed = true;
                 count_launch();
                 n_tab = 0; max_len = 0;
             };
@@ -1840,6 +1842,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                 else { jobs2.j[n2++] = mj; t2 = std::max(t2, mj.tiles); sm2 = std::max(sm2, p.smem); }
             }
             flush_tables();
+            if (tables_failed) { set_error("k_axis_tables launch failed"); return RMPE_E_CUDA; }
             // plan (which (tile, part) pairs can hold a peak) + pairs (screen them), per kernel variant
             const int sms = tables().sm_count;
             auto screen = [&](const MsJobs &jobs, int nj, int mt, size_t smem, int variant, int slot) -> int {
@@ -1865,6 +1868,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                     ProfScope ps("k_screen_plan", st);
                     k_screen_plan<<<dim3(mt, nj), kPlanThreads, 0, st>>>(jobs, (float)b->thre1, act_cap, group, lst, lstA, cnt, tab_err,
                                                                        b->status);
+                    RMPE_CUDA_TRY(cudaGetLastError());
                 }
                 {
                     ProfScope ps("k_screen_pairs", st);
@@ -1886,11 +1890,12 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                 count_launch(2);
                 return RMPE_OK;
             };
-            screen(jobs1, n1, t1, sm1, 0, 0);
-            screen(jobs2, n2, t2, sm2, 1, 1);
-            screen(jobsM, nM, tM, smM, 2, 2);
-            screen(jobsB, nB, tB, smB, 3, 3);
-            screen(jobsH, nH, tH, smH, 2, 4);
+            // a failed launch must not let the verify / finalize kernels run on stale lists
+            if ((rc = screen(jobs1, n1, t1, sm1, 0, 0)) != RMPE_OK) return rc;
+            if ((rc = screen(jobs2, n2, t2, sm2, 1, 1)) != RMPE_OK) return rc;
+            if ((rc = screen(jobsM, nM, tM, smM, 2, 2)) != RMPE_OK) return rc;
+            if ((rc = screen(jobsB, nB, tB, smB, 3, 3)) != RMPE_OK) return rc;
+            if ((rc = screen(jobsH, nH, tH, smH, 2, 4)) != RMPE_OK) return rc;
             {
                 ProfScope ps("k_peak_verify", st);
                 const int grid = std::min(cand_cap, 8 * sms);
@@ -2003,6 +2008,26 @@ extern "C" int rmpe_debug_heat_maps(const RmpeFrameDesc *f, const float *heat_de
     cudaFree(tmp);
     if (rc != RMPE_OK) return rc;
     RMPE_CUDA_TRY(e);
+    RMPE_CUDA_TRY(cudaGetLastError());
+    return RMPE_OK;
+}
+
+// k_assemble on caller-made connection lists of ONE frame: the only way to reach the reference's `found > 2` IndexError
+// (eval...:192-195) -- lists that come out of k_limbs are one-to-one per limb and never produce it.
+extern "C" int rmpe_debug_assemble(int max_peaks, int max_persons, const double *candidate_dev, const double *connections_dev,
+                                   const int32_t *n_conn_dev, const int32_t *n_peaks_dev, double *subset_dev,
+                                   int32_t *n_subset_dev, int32_t *status_dev, void *stream_) {
+    if (!is_initialised()) { set_error("rmpe_init not called"); return RMPE_E_NOTINIT; }
+    RMPE_REQUIRE(candidate_dev && connections_dev && n_conn_dev && n_peaks_dev && subset_dev && n_subset_dev && status_dev, "null argument");
+    RMPE_REQUIRE(max_peaks > 0 && max_peaks <= kMaxPeaksCap && max_persons > 0 && max_persons <= kMaxSubsetCap, "capacities");
+    int rc = ensure_smooth_attr();
+    if (rc != RMPE_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream_;
+    RMPE_CUDA_TRY(cudaMemsetAsync(status_dev, 0, sizeof(int32_t), st));
+    const size_t asm_smem = ((size_t)kAsmRowCap * 2 + (size_t)kAsmConnRows * 3 + (size_t)kParts * max_peaks) * 8 + (size_t)kParts * kAsmRowCap * 4;
+    k_assemble<<<1, 32, asm_smem, st>>>(0, max_peaks, max_persons, candidate_dev, connections_dev, n_conn_dev, n_peaks_dev,
+                                        subset_dev, n_subset_dev, status_dev);
+    count_launch();
     RMPE_CUDA_TRY(cudaGetLastError());
     return RMPE_OK;
 }

@@ -9,7 +9,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
 
 #include "rmpe_common.cuh"
 
@@ -669,10 +672,12 @@ __global__ void __launch_bounds__(128) k_mask46(MaskArgs a) {
 }
 
 // ==========================================================================================
-// k_raster: (57,46,46) labels of one sample.  grid = (3 channel groups, batch):
-//   group 0: 18 Gaussian part maps (max-merge) + background, group 1: limbs 0..9, group 2: 10..18.
-// Each thread owns float4 runs of a plane (pixels 4i..4i+3) so every store is a coalesced
-// 128-bit write; joints are transformed (T4) in shared memory by every CTA, group 0 writes them.
+// Rasteriser (H1-H5 + T4): (57,46,46) labels of one sample from its joints and its 46x46 mask.
+//   k_raster_small  <= 4 persons (COCO crops), planar labels: one CTA per sample, every table built once, a thread
+//                   owns one float4 run of pixels for all 57 planes, no barrier in the plane loop.
+//   k_raster_roles  any person count (crowded scenes) and / or the Keras-ready NHWC tensors: two CTAs per sample,
+//                   one per ROLE (18 Gaussian maps + background | 19 limbs), same barrier-free plane loops.
+// Joints are transformed (T4) into shared memory by every CTA; the first CTA of a sample writes them out.
 // ==========================================================================================
 struct RasterArgs {
     const double *joints;
@@ -680,7 +685,7 @@ struct RasterArgs {
     const double *M;
     const uint8_t *flip;
     const void *mask;     // [B][46][46] f32/f64
-    void *labels;
+    void *labels;         // planar [B][57][46][46] or null
     double *out_joints;
     int32_t *out_count;
     int32_t *status;
@@ -688,6 +693,11 @@ struct RasterArgs {
     int f64;
     int no_transform;
     double sigma, thre;
+    // k_raster_roles only
+    void *y1, *y2, *x1, *x2;   // NHWC tensors (training/ds_generators.py:52-63), each may be null
+    int part_batch;            // parts whose exp tables are resident at once (18: one pass)
+    int band_px;               // NHWC: pixels staged per pass (544, 272 or 136)
+    int paf_average;           // RMPE_GT_PAF_AVERAGE
 };
 
 struct LimbRec {
@@ -715,10 +725,6 @@ __device__ __forceinline__ bool band_on(const LimbRec &r, double dd, double thre
     return fabs(__ddiv_rn(dd, r.norm2)) <= thre;
 }
 
-constexpr int kRasterThreads = 288;
-constexpr int kRasterChunks = 2;  // 2 * 288 >= 529
-constexpr int kHeatBatch = 32;    // persons whose separable exp tables are resident at once
-
 template <typename T>
 __device__ inline void store4(T *p, float a, float b, float c, float d, const T m[4]);
 template <>
@@ -731,31 +737,35 @@ __device__ inline void store4<double>(double *p, float a, float b, float c, floa
     reinterpret_cast<double2 *>(p)[1] = make_double2((double)c * m[2], (double)d * m[3]);
 }
 
+template <typename T>
+__device__ __forceinline__ void store_pair(T *p, T a, T b);
+template <>
+__device__ __forceinline__ void store_pair<float>(float *p, float a, float b) { *reinterpret_cast<float2 *>(p) = make_float2(a, b); }
+template <>
+__device__ __forceinline__ void store_pair<double>(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
+
 // python-3 round(): half to even, on an f64 value already divided by the stride
 __device__ inline int py_round(double v) { return __double2int_rn(v); }
 
-template <typename T>
-__global__ void __launch_bounds__(kRasterThreads) k_raster(RasterArgs a) {
-    const int b = blockIdx.y;
-    const int group = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int P = min(a.n_persons[b], kMaxPersonsGt);
+// persons of sample b that the kernels look at: n_persons is caller data, never trusted beyond the person stride
+__device__ __forceinline__ int raster_persons(const RasterArgs &a, int b, int cap, bool &clamped) {
+    const int n = a.n_persons[b];
+    const int hi = min(a.max_persons, cap);
+    clamped = n < 0 || n > hi;
+    return max(0, min(n, hi));
+}
 
-    __shared__ double s_j[kMaxPersonsGt * kParts * 3];
-    __shared__ float s_ex[kHeatBatch * kGrid];
-    __shared__ float s_ey[kHeatBatch * kGrid];
-    __shared__ LimbRec s_rec[kMaxPersonsGt];
-
-    // ---- T4: keypoint transform + flip swap (py_rmpe_transformer.py:100-111) ----
-    for (int i = tid; i < P * kParts; i += kRasterThreads) {
-        int p = i / kParts, part = i - p * kParts;
+// ---- T4: keypoint transform + flip swap (py_rmpe_transformer.py:100-111) into shared memory ----
+__device__ __forceinline__ void raster_joints(const RasterArgs &a, int b, int P, double *s_j, int tid, int nthreads) {
+    for (int i = tid; i < P * kParts; i += nthreads) {
+        const int p = i / kParts, part = i - p * kParts;
         const double *jin = a.joints + ((size_t)b * a.max_persons + p) * (kParts * 3);
         double ox, oy, ov;
         if (a.no_transform) {
             ox = jin[part * 3 + 0]; oy = jin[part * 3 + 1]; ov = jin[part * 3 + 2];
         } else {
-            int sp = a.flip[b] ? c_flip_partner[part] : part;
-            double x = jin[sp * 3 + 0], y = jin[sp * 3 + 1];
+            const int sp = a.flip[b] ? c_flip_partner[part] : part;
+            const double x = jin[sp * 3 + 0], y = jin[sp * 3 + 1];
             ov = jin[sp * 3 + 2];
             const double *M = a.M + 6 * b;
             // numpy matmul order: t = M0*x; t = fma(M1, y, t); out = t + M2
@@ -763,168 +773,65 @@ __global__ void __launch_bounds__(kRasterThreads) k_raster(RasterArgs a) {
             oy = __dadd_rn(__fma_rn(M[4], y, __dmul_rn(M[3], x)), M[5]);
         }
         s_j[i * 3 + 0] = ox; s_j[i * 3 + 1] = oy; s_j[i * 3 + 2] = ov;
-        if (group == 0 && a.out_joints) {
-            double *jo = a.out_joints + ((size_t)b * a.max_persons + p) * (kParts * 3) + part * 3;
-            jo[0] = ox; jo[1] = oy; jo[2] = ov;
-        }
     }
-    __syncthreads();
+}
+__device__ __forceinline__ void raster_joints_out(const RasterArgs &a, int b, int P, const double *s_j, int tid, int nthreads) {
+    if (!a.out_joints) return;
+    double *jo = a.out_joints + (size_t)b * a.max_persons * (kParts * 3);
+    for (int i = tid; i < P * kParts * 3; i += nthreads) jo[i] = s_j[i];
+}
 
-    // mask values of this thread's pixels
-    T m[kRasterChunks][4];
-    const T *mk = reinterpret_cast<const T *>(a.mask) + (size_t)b * kCells;
-#pragma unroll
-    for (int c = 0; c < kRasterChunks; c++) {
-        int i = tid + c * kRasterThreads;
-#pragma unroll
-        for (int q = 0; q < 4; q++) m[c][q] = (i < kCellVec) ? mk[4 * i + q] : (T)0;
-    }
-    T *lab = reinterpret_cast<T *>(a.labels) + (size_t)b * kLayers * kCells;
+// ---- H1/H2 tables of one (part, person, cell): cell centres 8i + 3.5 (py_rmpe_heatmapper.py:22-23, 51-57) ----
+__device__ __forceinline__ void raster_exp_entry(const double *j, int cidx, float inv2s2, float &ex, float &ey) {
+    const double g = 8.0 * cidx + 3.5;
+    const float dx = (float)(g - j[0]), dy = (float)(g - j[1]);
+    const bool vis = j[2] < 2.0;
+    ex = vis ? expf(-(dx * dx) * inv2s2) : 0.f;
+    ey = vis ? expf(-(dy * dy) * inv2s2) : 0.f;
+}
 
-    if (group == 0) {
-        // ---- H2/H3: Gaussian part maps with max merge, background = 1 - max ----
-        const float inv2s2 = (float)(1.0 / (2.0 * a.sigma * a.sigma));
-        float bk[kRasterChunks][4];
-#pragma unroll
-        for (int c = 0; c < kRasterChunks; c++)
-#pragma unroll
-            for (int q = 0; q < 4; q++) bk[c][q] = 0.f;
-        for (int part = 0; part < kParts; part++) {
-            float v[kRasterChunks][4];
-#pragma unroll
-            for (int c = 0; c < kRasterChunks; c++)
-#pragma unroll
-                for (int q = 0; q < 4; q++) v[c][q] = 0.f;
-            for (int pb = 0; pb < P; pb += kHeatBatch) {
-                const int np = min(kHeatBatch, P - pb);
-                for (int i = tid; i < np * kGrid; i += kRasterThreads) {
-                    int p = i / kGrid, cidx = i - p * kGrid;
-                    const double *j = s_j + ((pb + p) * kParts + part) * 3;
-                    double g = 8.0 * cidx + 3.5;   // cell centres (py_rmpe_heatmapper.py:22-23)
-                    float dx = (float)(g - j[0]), dy = (float)(g - j[1]);
-                    bool vis = j[2] < 2.0;
-                    s_ex[i] = vis ? expf(-(dx * dx) * inv2s2) : 0.f;
-                    s_ey[i] = vis ? expf(-(dy * dy) * inv2s2) : 0.f;
-                }
-                __syncthreads();
-#pragma unroll
-                for (int c = 0; c < kRasterChunks; c++) {
-                    int i = tid + c * kRasterThreads;
-                    if (i < kCellVec) {
-                        int pix = 4 * i;
-                        int y[4], x[4];
-#pragma unroll
-                        for (int q = 0; q < 4; q++) { y[q] = (pix + q) / kGrid; x[q] = (pix + q) - y[q] * kGrid; }
-                        for (int p = 0; p < np; p++) {
-#pragma unroll
-                            for (int q = 0; q < 4; q++)
-                                v[c][q] = fmaxf(v[c][q], s_ey[p * kGrid + y[q]] * s_ex[p * kGrid + x[q]]);
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-#pragma unroll
-            for (int c = 0; c < kRasterChunks; c++) {
-                int i = tid + c * kRasterThreads;
-                if (i < kCellVec) {
-#pragma unroll
-                    for (int q = 0; q < 4; q++) bk[c][q] = fmaxf(bk[c][q], v[c][q]);
-                    store4<T>(lab + (size_t)(38 + part) * kCells + 4 * i, v[c][0], v[c][1], v[c][2], v[c][3], m[c]);
-                }
+// ---- H4 record of one (limb, person) (py_rmpe_heatmapper.py:69-114); returns true for a zero-length limb ----
+__device__ __forceinline__ bool raster_limb_rec(const double *jf, const double *jt, double thre, LimbRec &r) {
+    bool zero = false;
+    r.minx = r.maxx = r.miny = r.maxy = 0;
+    r.x1 = jf[0]; r.y1 = jf[1];
+    const double x2 = jt[0], y2 = jt[1];
+    r.xD = __dsub_rn(x2, r.x1); r.yD = __dsub_rn(y2, r.y1);
+    // distances(): sqrt(xD**2 + yD**2); put_vector_maps: sqrt(dx*dx + dy*dy) -- same value
+    r.norm2 = __dsqrt_rn(__dadd_rn(__dmul_rn(r.xD, r.xD), __dmul_rn(r.yD, r.yD)));
+    r.ux = r.uy = 0.f;
+    r.tn = r.en = 0.0;
+    if (jf[2] < 2.0 && jt[2] < 2.0) {
+        if (r.norm2 == 0.0) {
+            zero = true;
+        } else {
+            r.ux = (float)__ddiv_rn(r.xD, r.norm2);
+            r.uy = (float)__ddiv_rn(r.yD, r.norm2);
+            band_prepare(r, thre);
+            const double mnx = r.x1 < x2 ? r.x1 : x2, mxx = r.x1 < x2 ? x2 : r.x1;
+            const double mny = r.y1 < y2 ? r.y1 : y2, mxy = r.y1 < y2 ? y2 : r.y1;
+            const int a0 = py_round(__ddiv_rn(__dsub_rn(mnx, thre), 8.0));
+            const int b0 = py_round(__ddiv_rn(__dsub_rn(mny, thre), 8.0));
+            const int a1 = py_round(__ddiv_rn(__dadd_rn(mxx, thre), 8.0));
+            const int b1 = py_round(__ddiv_rn(__dadd_rn(mxy, thre), 8.0));
+            if (a1 >= 0 && b1 >= 0) {
+                r.minx = max(a0, 0); r.miny = max(b0, 0);
+                r.maxx = min(a1, kGrid); r.maxy = min(b1, kGrid);
+                if (r.maxy <= r.miny) r.maxx = r.minx;  // empty slice
             }
         }
-#pragma unroll
-        for (int c = 0; c < kRasterChunks; c++) {
-            int i = tid + c * kRasterThreads;
-            if (i < kCellVec)
-                store4<T>(lab + (size_t)56 * kCells + 4 * i, 1.f - bk[c][0], 1.f - bk[c][1], 1.f - bk[c][2],
-                          1.f - bk[c][3], m[c]);
-        }
-        return;
     }
+    return zero;
+}
 
-    // ---- H4: part-affinity fields, limbs [k0,k1) ----
-    const int k0 = (group == 1) ? 0 : 10, k1 = (group == 1) ? 10 : kLimbs;
-    const double thre = a.thre;
-    // rows covered by this warp's pixels (for a warp-uniform reject of far-away limbs)
-    for (int k = k0; k < k1; k++) {
-        const int fr = c_limb_from[k], to = c_limb_to[k];
-        for (int p = tid; p < P; p += kRasterThreads) {
-            const double *jf = s_j + (p * kParts + fr) * 3, *jt = s_j + (p * kParts + to) * 3;
-            LimbRec r;
-            r.minx = r.maxx = r.miny = r.maxy = 0;
-            r.x1 = jf[0]; r.y1 = jf[1];
-            double x2 = jt[0], y2 = jt[1];
-            r.xD = __dsub_rn(x2, r.x1); r.yD = __dsub_rn(y2, r.y1);
-            // distances(): sqrt(xD**2 + yD**2); put_vector_maps: sqrt(dx*dx + dy*dy) -- same value
-            r.norm2 = __dsqrt_rn(__dadd_rn(__dmul_rn(r.xD, r.xD), __dmul_rn(r.yD, r.yD)));
-            r.ux = r.uy = 0.f;
-            r.tn = r.en = 0.0;
-            if (jf[2] < 2.0 && jt[2] < 2.0) {
-                if (r.norm2 == 0.0) {
-                    atomicOr(a.status + b, RMPE_ST_ZERO_LIMB);
-                } else {
-                    r.ux = (float)__ddiv_rn(r.xD, r.norm2);
-                    r.uy = (float)__ddiv_rn(r.yD, r.norm2);
-                    band_prepare(r, thre);
-                    double mnx = r.x1 < x2 ? r.x1 : x2, mxx = r.x1 < x2 ? x2 : r.x1;
-                    double mny = r.y1 < y2 ? r.y1 : y2, mxy = r.y1 < y2 ? y2 : r.y1;
-                    int a0 = py_round(__ddiv_rn(__dsub_rn(mnx, thre), 8.0));
-                    int b0 = py_round(__ddiv_rn(__dsub_rn(mny, thre), 8.0));
-                    int a1 = py_round(__ddiv_rn(__dadd_rn(mxx, thre), 8.0));
-                    int b1 = py_round(__ddiv_rn(__dadd_rn(mxy, thre), 8.0));
-                    if (a1 >= 0 && b1 >= 0) {
-                        r.minx = max(a0, 0); r.miny = max(b0, 0);
-                        r.maxx = min(a1, kGrid); r.maxy = min(b1, kGrid);
-                        if (r.maxy <= r.miny) r.maxx = r.minx;  // empty slice
-                    }
-                }
-            }
-            s_rec[p] = r;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int c = 0; c < kRasterChunks; c++) {
-            int i = tid + c * kRasterThreads;
-            // warp-uniform row range of this chunk's 32 threads
-            int ibase = (tid & ~31) + c * kRasterThreads;
-            int wy0 = (4 * ibase) / kGrid, wy1 = min(kCells - 1, 4 * ibase + 127) / kGrid;
-            float vx[4] = {0.f, 0.f, 0.f, 0.f}, vy[4] = {0.f, 0.f, 0.f, 0.f};
-            int cnt[4] = {0, 0, 0, 0};
-            int pix = 4 * i;
-            int y[4], x[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) { y[q] = (pix + q) / kGrid; x[q] = (pix + q) - y[q] * kGrid; }
-            if (ibase < kCellVec) {
-                for (int p = 0; p < P; p++) {
-                    const LimbRec &r = s_rec[p];
-                    if (r.maxx <= r.minx || r.maxy <= wy0 || r.miny > wy1) continue;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        if (x[q] >= r.minx && x[q] < r.maxx && y[q] >= r.miny && y[q] < r.maxy) {
-                            double X = (double)(8 * x[q]), Y = (double)(8 * y[q]);
-                            const double dd = __dsub_rn(__dmul_rn(r.xD, __dsub_rn(r.y1, Y)),
-                                                        __dmul_rn(__dsub_rn(r.x1, X), r.yD));
-                            if (band_on(r, dd, thre)) { vx[q] = r.ux; vy[q] = r.uy; cnt[q]++; }
-                        }
-                    }
-                }
-            }
-            if (i < kCellVec) {
-                store4<T>(lab + (size_t)(2 * k) * kCells + pix, vx[0], vx[1], vx[2], vx[3], m[c]);
-                store4<T>(lab + (size_t)(2 * k + 1) * kCells + pix, vy[0], vy[1], vy[2], vy[3], m[c]);
-                if (a.out_count)
-                    *reinterpret_cast<int4 *>(a.out_count + ((size_t)b * kLimbs + k) * kCells + pix) =
-                        make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
-            }
-        }
-        __syncthreads();
-    }
+// distance numerator of a grid cell's top-left corner (8x, 8y) to the limb's line, f64 un-fused (distances(), :141-155)
+__device__ __forceinline__ double raster_dd(const LimbRec &r, int x, int y) {
+    const double X = (double)(8 * x), Y = (double)(8 * y);
+    return __dsub_rn(__dmul_rn(r.xD, __dsub_rn(r.y1, Y)), __dmul_rn(__dsub_rn(r.x1, X), r.yD));
 }
 
 // ==========================================================================================
-// k_raster_small: the same rasteriser for the common case of <= 4 persons per sample (COCO crops).
+// k_raster_small: <= 4 persons per sample (COCO crops), planar labels.
 // grid = (plane groups, batch); a thread owns ONE float4 run of pixels and writes it for all planes of its group.
 // Everything the planes need is built once per CTA -- transformed joints, the separable exp tables of the group's
 // parts x persons, the limb records of the group's limbs x persons -- so the plane loop has no barrier and every
@@ -941,7 +848,8 @@ __global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
     const int grp = blockIdx.x, n_grp = gridDim.x;
     const int tid = threadIdx.x;
     const int kRsThreads = blockDim.x;
-    const int P = min(a.n_persons[b], kRsMaxP);
+    bool clamped;
+    const int P = raster_persons(a, b, kRsMaxP, clamped);
     // planes of this group: parts [part_lo, part_hi) are stored, the background needs the max over all 18 parts
     int part_lo = 0, part_hi = kParts, limb_lo = 0, limb_hi = kLimbs;
     bool want_bkg = true;
@@ -962,88 +870,43 @@ __global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
     double *s_j = reinterpret_cast<double *>(s_rec + kLimbs * PM);             // [PM][18][3]
     float *s_ex = reinterpret_cast<float *>(s_j + PM * kParts * 3);            // [18][P][46]
     float *s_ey = s_ex + kParts * PM * kGrid;
+    __shared__ int s_zero;
+    if (tid == 0) s_zero = 0;
 
-    // ---- T4: keypoint transform + flip swap (py_rmpe_transformer.py:100-111) ----
-    for (int i = tid; i < P * kParts; i += kRsThreads) {
-        int p = i / kParts, part = i - p * kParts;
-        const double *jin = a.joints + ((size_t)b * a.max_persons + p) * (kParts * 3);
-        double ox, oy, ov;
-        if (a.no_transform) {
-            ox = jin[part * 3 + 0]; oy = jin[part * 3 + 1]; ov = jin[part * 3 + 2];
-        } else {
-            int sp = a.flip[b] ? c_flip_partner[part] : part;
-            double x = jin[sp * 3 + 0], y = jin[sp * 3 + 1];
-            ov = jin[sp * 3 + 2];
-            const double *M = a.M + 6 * b;
-            ox = __dadd_rn(__fma_rn(M[1], y, __dmul_rn(M[0], x)), M[2]);
-            oy = __dadd_rn(__fma_rn(M[4], y, __dmul_rn(M[3], x)), M[5]);
-        }
-        s_j[i * 3 + 0] = ox; s_j[i * 3 + 1] = oy; s_j[i * 3 + 2] = ov;
-        if (grp == 0 && a.out_joints) {
-            double *jo = a.out_joints + ((size_t)b * a.max_persons + p) * (kParts * 3) + part * 3;
-            jo[0] = ox; jo[1] = oy; jo[2] = ov;
-        }
-    }
+    raster_joints(a, b, P, s_j, tid, kRsThreads);
     __syncthreads();
 
-    // ---- H1/H2 tables: ex/ey[part][person][cell], cell centres 8i + 3.5 (py_rmpe_heatmapper.py:22-23, 51-57) ----
     const float inv2s2 = (float)(1.0 / (2.0 * a.sigma * a.sigma));
     for (int i = tab_lo * P * kGrid + tid; i < tab_hi * P * kGrid; i += kRsThreads) {
         const int cidx = i % kGrid, pp = i / kGrid;           // pp = part * P + p
         const int part = pp / P, p = pp - part * P;
-        const double *j = s_j + (p * kParts + part) * 3;
-        const double g = 8.0 * cidx + 3.5;
-        const float dx = (float)(g - j[0]), dy = (float)(g - j[1]);
-        const bool vis = j[2] < 2.0;
-        s_ex[i] = vis ? expf(-(dx * dx) * inv2s2) : 0.f;
-        s_ey[i] = vis ? expf(-(dy * dy) * inv2s2) : 0.f;
+        raster_exp_entry(s_j + (p * kParts + part) * 3, cidx, inv2s2, s_ex[i], s_ey[i]);
     }
     // ---- H4 limb records: [limb][person] ----
     const double thre = a.thre;
     for (int i = limb_lo * P + tid; i < limb_hi * P; i += kRsThreads) {
         const int k = i / P, p = i - k * P;
-        const double *jf = s_j + (p * kParts + c_limb_from[k]) * 3, *jt = s_j + (p * kParts + c_limb_to[k]) * 3;
         LimbRec r;
-        r.minx = r.maxx = r.miny = r.maxy = 0;
-        r.x1 = jf[0]; r.y1 = jf[1];
-        const double x2 = jt[0], y2 = jt[1];
-        r.xD = __dsub_rn(x2, r.x1); r.yD = __dsub_rn(y2, r.y1);
-        r.norm2 = __dsqrt_rn(__dadd_rn(__dmul_rn(r.xD, r.xD), __dmul_rn(r.yD, r.yD)));
-        r.ux = r.uy = 0.f;
-        r.tn = r.en = 0.0;
-        if (jf[2] < 2.0 && jt[2] < 2.0) {
-            if (r.norm2 == 0.0) {
-                atomicOr(a.status + b, RMPE_ST_ZERO_LIMB);
-            } else {
-                r.ux = (float)__ddiv_rn(r.xD, r.norm2);
-                r.uy = (float)__ddiv_rn(r.yD, r.norm2);
-                band_prepare(r, thre);
-                const double mnx = r.x1 < x2 ? r.x1 : x2, mxx = r.x1 < x2 ? x2 : r.x1;
-                const double mny = r.y1 < y2 ? r.y1 : y2, mxy = r.y1 < y2 ? y2 : r.y1;
-                const int a0 = py_round(__ddiv_rn(__dsub_rn(mnx, thre), 8.0));
-                const int b0 = py_round(__ddiv_rn(__dsub_rn(mny, thre), 8.0));
-                const int a1 = py_round(__ddiv_rn(__dadd_rn(mxx, thre), 8.0));
-                const int b1 = py_round(__ddiv_rn(__dadd_rn(mxy, thre), 8.0));
-                if (a1 >= 0 && b1 >= 0) {
-                    r.minx = max(a0, 0); r.miny = max(b0, 0);
-                    r.maxx = min(a1, kGrid); r.maxy = min(b1, kGrid);
-                    if (r.maxy <= r.miny) r.maxx = r.minx;  // empty slice
-                }
-            }
-        }
+        if (raster_limb_rec(s_j + (p * kParts + c_limb_from[k]) * 3, s_j + (p * kParts + c_limb_to[k]) * 3, thre, r)) s_zero = 1;
         s_rec[i] = r;
     }
     __syncthreads();
 
+    // Launched with programmatic stream serialization behind k_warp_fused: everything above (joints, tables, limb records)
+    // reads only the caller's inputs and touches no global memory, so it overlaps the tail of the warp kernel; the 46x46
+    // mask is that kernel's output and status / out_joints are shared with it, so wait before the first of them.
+    pdl_wait();
+    if (grp == 0) {
+        raster_joints_out(a, b, P, s_j, tid, kRsThreads);
+        if (tid == 0 && (s_zero || clamped))
+            atomicOr(a.status + b, (s_zero ? RMPE_ST_ZERO_LIMB : 0) | (clamped ? RMPE_ST_PERSONS_CLAMPED : 0));
+    }
     const int run = tid;
     if (run >= kCellVec) return;
     const int pix = 4 * run;
     int y[4], x[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) { y[q] = (pix + q) / kGrid; x[q] = (pix + q) - y[q] * kGrid; }
-    // Launched with programmatic stream serialization behind k_warp_fused: everything above (joints, tables, limb records)
-    // reads only the caller's inputs and overlaps the tail of the warp kernel; the 46x46 mask is its output, so wait here.
-    pdl_wait();
     T m[4];
     {
         const T *mk = reinterpret_cast<const T *>(a.mask) + (size_t)b * kCells + pix;
@@ -1085,9 +948,7 @@ __global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 if (x[q] >= box.x && x[q] < box.y && y[q] >= box.z && y[q] < box.w) {
-                    const double X = (double)(8 * x[q]), Y = (double)(8 * y[q]);
-                    const double dd = __dsub_rn(__dmul_rn(r.xD, __dsub_rn(r.y1, Y)), __dmul_rn(__dsub_rn(r.x1, X), r.yD));
-                    if (band_on(r, dd, thre)) { vx[q] = r.ux; vy[q] = r.uy; cnt[q]++; }
+                    if (band_on(r, raster_dd(r, x[q], y[q]), thre)) { vx[q] = r.ux; vy[q] = r.uy; cnt[q]++; }
                 }
             }
         }
@@ -1096,6 +957,252 @@ __global__ void __launch_bounds__(544) k_raster_small(RasterArgs a) {
         if (a.out_count)
             *reinterpret_cast<int4 *>(a.out_count + ((size_t)b * kLimbs + k) * kCells + pix) =
                 make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
+    }
+}
+
+// ==========================================================================================
+// k_raster_roles: crowded scenes (up to 64 persons) and the NHWC (Keras) outputs.
+// grid = (2 roles, batch): role 0 = 18 Gaussian part maps + background (+ joints out), role 1 = 19 limbs.  Each CTA builds
+// what its planes need ONCE -- role 0 the separable exp tables [part][person][46] (all 18 parts when they fit, else in
+// batches of `part_batch` parts, one barrier pair per batch), role 1 the 19 x P limb records -- and then runs barrier-free
+// plane loops like k_raster_small: 20 persons = 132 KB of tables + 30 KB of records instead of 36 table rebuilds and
+// 38 barriers per sample.
+//   planar labels (kNhwc = false): a thread owns one float4 run of pixels, every store a coalesced 128-bit write.
+//   kNhwc: the tensors DataIteratorBase.gen builds on the host (training/ds_generators.py:52-63) leave the kernel directly:
+//     y2 = labels[38:57] as (46,46,19), y1 = labels[0:38] as (46,46,38), x2 / x1 = the mask repeated.  A thread owns one
+//     PIXEL of a band of `band_px` pixels and puts its 19 / 38 channel values into a [pixel][channel] band buffer in shared
+//     memory (odd word stride / 64-bit pairs: conflict-free); the band is one contiguous piece of the NHWC tensor and
+//     leaves as flat 128-bit copies.  Optional planar outputs (labels, count) are still written, as scalar coalesced stores.
+// ==========================================================================================
+constexpr int kRrThreads = 544;
+constexpr int kHeatCh = kParts + 1;    // 19 channels of y2 / x2
+constexpr int kPafCh = 2 * kLimbs;     // 38 channels of y1 / x1
+
+template <typename T>
+__device__ __forceinline__ void flat_copy16(T *dst, const T *src_smem, int n_elems, int tid) {
+    // n_elems * sizeof(T) is a multiple of 16 and dst is 16-byte aligned (checked on the host)
+    const int n16 = (int)((size_t)n_elems * sizeof(T) / 16);
+    const uint4 *s = reinterpret_cast<const uint4 *>(src_smem);
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+    for (int i = tid; i < n16; i += kRrThreads) d[i] = s[i];
+}
+// x[e] = mask of pixel e / C for the band's elements (mask repeated over the channels)
+template <typename T, int C>
+__device__ __forceinline__ void flat_mask_repeat(T *dst, const T *s_m, int n_px, int tid) {
+    constexpr int V = 16 / sizeof(T);
+    const int n16 = n_px * C / V;     // n_px * C * sizeof(T) is a multiple of 16
+    for (int i = tid; i < n16; i += kRrThreads) {
+        T v[V];
+#pragma unroll
+        for (int q = 0; q < V; q++) v[q] = s_m[(i * V + q) / C];
+        *reinterpret_cast<uint4 *>(dst + (size_t)i * V) = *reinterpret_cast<const uint4 *>(v);
+    }
+}
+
+template <typename T, bool kNhwc>
+__global__ void __launch_bounds__(kRrThreads) k_raster_roles(RasterArgs a) {
+    const int b = blockIdx.y, role = blockIdx.x;
+    const int tid = threadIdx.x;
+    bool clamped;
+    const int P = raster_persons(a, b, kMaxPersonsGt, clamped);
+    const int PM = a.max_persons;
+    extern __shared__ __align__(16) uint8_t rr_smem[];
+    double *s_j = reinterpret_cast<double *>(rr_smem);                      // [PM][18][3]
+    uint8_t *rest = rr_smem + (((size_t)PM * kParts * 3 * 8 + 15) & ~(size_t)15);
+    __shared__ int s_zero;
+    if (tid == 0) s_zero = 0;
+    raster_joints(a, b, P, s_j, tid, kRrThreads);
+    __syncthreads();
+    const T *mk = reinterpret_cast<const T *>(a.mask) + (size_t)b * kCells;
+
+    if (role == 0) {
+        // ================= 18 Gaussian part maps + background =================
+        const int PB = a.part_batch;
+        float *s_ex = reinterpret_cast<float *>(rest);                      // [PB][P][46]
+        float *s_ey = s_ex + (size_t)PB * PM * kGrid;
+        const float inv2s2 = (float)(1.0 / (2.0 * a.sigma * a.sigma));
+        auto build = [&](int pb0, int npb) {
+            for (int i = tid; i < npb * P * kGrid; i += kRrThreads) {
+                const int cidx = i % kGrid, pp = i / kGrid;
+                const int part = pb0 + pp / P, p = pp % P;
+                raster_exp_entry(s_j + (p * kParts + part) * 3, cidx, inv2s2, s_ex[i], s_ey[i]);
+            }
+        };
+        build(0, min(PB, kParts));
+        __syncthreads();
+        pdl_wait();       // see k_raster_small: nothing above touches global memory that another kernel writes
+        raster_joints_out(a, b, P, s_j, tid, kRrThreads);
+        if (tid == 0 && clamped) atomicOr(a.status + b, RMPE_ST_PERSONS_CLAMPED);
+        if (!kNhwc) {
+            const int pix = 4 * tid;
+            const bool on = tid < kCellVec;
+            int y[4], x[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) { y[q] = (pix + q) / kGrid; x[q] = (pix + q) - y[q] * kGrid; }
+            T m[4] = {(T)0, (T)0, (T)0, (T)0};
+            if (on) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) m[q] = mk[pix + q];
+            }
+            T *lab = reinterpret_cast<T *>(a.labels) + (size_t)b * kLayers * kCells + pix;
+            float bk[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int pb0 = 0; pb0 < kParts; pb0 += PB) {
+                const int npb = min(PB, kParts - pb0);
+                if (pb0) { __syncthreads(); build(pb0, npb); __syncthreads(); }
+                if (!on) continue;
+                for (int pl = 0; pl < npb; pl++) {
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+                    const float *ex = s_ex + (size_t)pl * P * kGrid, *ey = s_ey + (size_t)pl * P * kGrid;
+#pragma unroll 4
+                    for (int p = 0; p < P; p++, ex += kGrid, ey += kGrid) {
+                        const float2 ea = *reinterpret_cast<const float2 *>(ex + x[0]);
+                        const float2 eb = *reinterpret_cast<const float2 *>(ex + x[2]);
+                        const float ya = ey[y[0]], yb = ey[y[2]];
+                        v[0] = fmaxf(v[0], ya * ea.x); v[1] = fmaxf(v[1], ya * ea.y);
+                        v[2] = fmaxf(v[2], yb * eb.x); v[3] = fmaxf(v[3], yb * eb.y);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) bk[q] = fmaxf(bk[q], v[q]);
+                    store4<T>(lab + (size_t)(38 + pb0 + pl) * kCells, v[0], v[1], v[2], v[3], m);
+                }
+            }
+            if (on) store4<T>(lab + (size_t)56 * kCells, 1.f - bk[0], 1.f - bk[1], 1.f - bk[2], 1.f - bk[3], m);
+        } else {
+            // NHWC: all 18 parts' tables are resident (part_batch == 18, the host guarantees it)
+            const int BP = a.band_px;
+            T *s_band = reinterpret_cast<T *>(reinterpret_cast<uint8_t *>(s_ey + (size_t)PB * PM * kGrid));   // [BP][19]
+            T *s_m = s_band + (size_t)BP * kHeatCh;
+            T *lab = a.labels ? reinterpret_cast<T *>(a.labels) + (size_t)b * kLayers * kCells : nullptr;
+            for (int band0 = 0; band0 < kCells; band0 += BP) {
+                const int n_px = min(BP, kCells - band0);
+                if (tid < n_px) {
+                    const int pix = band0 + tid;
+                    const int y = pix / kGrid, x = pix - y * kGrid;
+                    const T m = mk[pix];
+                    s_m[tid] = m;
+                    float bk = 0.f;
+                    T *o = s_band + (size_t)tid * kHeatCh;
+                    for (int part = 0; part < kParts; part++) {
+                        float v = 0.f;
+                        const float *ex = s_ex + (size_t)part * P * kGrid + x, *ey = s_ey + (size_t)part * P * kGrid + y;
+#pragma unroll 4
+                        for (int p = 0; p < P; p++) v = fmaxf(v, ey[p * kGrid] * ex[p * kGrid]);
+                        bk = fmaxf(bk, v);
+                        const T out = (T)v * m;
+                        o[part] = out;
+                        if (lab) lab[(size_t)(38 + part) * kCells + pix] = out;
+                    }
+                    const T outb = (T)(1.f - bk) * m;
+                    o[kParts] = outb;
+                    if (lab) lab[(size_t)56 * kCells + pix] = outb;
+                }
+                __syncthreads();
+                const size_t go = ((size_t)b * kCells + band0) * kHeatCh;
+                if (a.y2) flat_copy16<T>(reinterpret_cast<T *>(a.y2) + go, s_band, n_px * kHeatCh, tid);
+                if (a.x2) flat_mask_repeat<T, kHeatCh>(reinterpret_cast<T *>(a.x2) + go, s_m, n_px, tid);
+                __syncthreads();
+            }
+        }
+        return;
+    }
+
+    // ================= 19 limbs: part-affinity fields =================
+    LimbRec *s_rec = reinterpret_cast<LimbRec *>(rest);                      // [19][P]
+    const double thre = a.thre;
+    for (int i = tid; i < kLimbs * P; i += kRrThreads) {
+        const int k = i / P, p = i - k * P;
+        LimbRec r;
+        if (raster_limb_rec(s_j + (p * kParts + c_limb_from[k]) * 3, s_j + (p * kParts + c_limb_to[k]) * 3, thre, r)) s_zero = 1;
+        s_rec[i] = r;
+    }
+    __syncthreads();
+    pdl_wait();
+    if (tid == 0 && s_zero) atomicOr(a.status + b, RMPE_ST_ZERO_LIMB);
+    const bool avg = a.paf_average != 0;
+    // one pixel against the records of limb k: the reference's overwrite in person order (last band that covers the pixel
+    // wins), or the averaging variant (f64 sums in person order, divided by the count)
+    auto limb_pixel = [&](int k, int x, int y, float &vx, float &vy, int &cnt) {
+        vx = 0.f; vy = 0.f; cnt = 0;
+        double sx = 0.0, sy = 0.0;
+        const LimbRec *rk = s_rec + k * P;
+        for (int p = 0; p < P; p++) {
+            const LimbRec &r = rk[p];
+            const int4 box = *reinterpret_cast<const int4 *>(&r.minx);
+            if (x >= box.x && x < box.y && y >= box.z && y < box.w) {
+                if (band_on(r, raster_dd(r, x, y), thre)) {
+                    vx = r.ux; vy = r.uy; cnt++;
+                    if (avg) { sx = __dadd_rn(sx, __ddiv_rn(r.xD, r.norm2)); sy = __dadd_rn(sy, __ddiv_rn(r.yD, r.norm2)); }
+                }
+            }
+        }
+        if (avg && cnt > 0) { vx = (float)__ddiv_rn(sx, (double)cnt); vy = (float)__ddiv_rn(sy, (double)cnt); }
+    };
+    if (!kNhwc) {
+        if (tid >= kCellVec) return;
+        const int pix = 4 * tid;
+        int y[4], x[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { y[q] = (pix + q) / kGrid; x[q] = (pix + q) - y[q] * kGrid; }
+        T m[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) m[q] = mk[pix + q];
+        T *lab = reinterpret_cast<T *>(a.labels) + (size_t)b * kLayers * kCells + pix;
+        const int ymin = y[0], ymax = y[3];
+        for (int k = 0; k < kLimbs; k++) {
+            float vx[4] = {0.f, 0.f, 0.f, 0.f}, vy[4] = {0.f, 0.f, 0.f, 0.f};
+            int cnt[4] = {0, 0, 0, 0};
+            if (!avg) {
+                const LimbRec *rk = s_rec + k * P;
+                for (int p = 0; p < P; p++) {
+                    const LimbRec &r = rk[p];
+                    const int4 box = *reinterpret_cast<const int4 *>(&r.minx);      // minx, maxx, miny, maxy
+                    if (box.y <= box.x || box.w <= ymin || box.z > ymax) continue;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (x[q] >= box.x && x[q] < box.y && y[q] >= box.z && y[q] < box.w) {
+                            if (band_on(r, raster_dd(r, x[q], y[q]), thre)) { vx[q] = r.ux; vy[q] = r.uy; cnt[q]++; }
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++) limb_pixel(k, x[q], y[q], vx[q], vy[q], cnt[q]);
+            }
+            store4<T>(lab + (size_t)(2 * k) * kCells, vx[0], vx[1], vx[2], vx[3], m);
+            store4<T>(lab + (size_t)(2 * k + 1) * kCells, vy[0], vy[1], vy[2], vy[3], m);
+            if (a.out_count)
+                *reinterpret_cast<int4 *>(a.out_count + ((size_t)b * kLimbs + k) * kCells + pix) =
+                    make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
+        }
+    } else {
+        const int BP = a.band_px;
+        T *s_band = reinterpret_cast<T *>(rest + (((size_t)kLimbs * PM * sizeof(LimbRec) + 15) & ~(size_t)15));   // [BP][38]
+        T *s_m = s_band + (size_t)BP * kPafCh;
+        T *lab = a.labels ? reinterpret_cast<T *>(a.labels) + (size_t)b * kLayers * kCells : nullptr;
+        for (int band0 = 0; band0 < kCells; band0 += BP) {
+            const int n_px = min(BP, kCells - band0);
+            if (tid < n_px) {
+                const int pix = band0 + tid;
+                const int y = pix / kGrid, x = pix - y * kGrid;
+                const T m = mk[pix];
+                s_m[tid] = m;
+                T *o = s_band + (size_t)tid * kPafCh;
+                for (int k = 0; k < kLimbs; k++) {
+                    float vx, vy;
+                    int cnt;
+                    limb_pixel(k, x, y, vx, vy, cnt);
+                    const T ox = (T)vx * m, oy = (T)vy * m;
+                    store_pair<T>(o + 2 * k, ox, oy);      // one 64- / 128-bit store: conflict-free at the 38-word pixel stride
+                    if (lab) { lab[(size_t)(2 * k) * kCells + pix] = ox; lab[(size_t)(2 * k + 1) * kCells + pix] = oy; }
+                    if (a.out_count) a.out_count[((size_t)b * kLimbs + k) * kCells + pix] = cnt;
+                }
+            }
+            __syncthreads();
+            const size_t go = ((size_t)b * kCells + band0) * kPafCh;
+            if (a.y1) flat_copy16<T>(reinterpret_cast<T *>(a.y1) + go, s_band, n_px * kPafCh, tid);
+            if (a.x1) flat_mask_repeat<T, kPafCh>(reinterpret_cast<T *>(a.x1) + go, s_m, n_px, tid);
+            __syncthreads();
+        }
     }
 }
 
@@ -1147,7 +1254,23 @@ static int fused_foot_cap(int ng) {
 }
 static size_t fused_smem_bytes(int ng) { return (size_t)kTabBytes + (size_t)ng * ((size_t)fused_foot_cap(ng) * 4 + kGroupFixedBytes); }
 
-static std::atomic<unsigned> g_counter_ring{0};   // next work counter of DeviceTables::counters (all launches share the ring)
+// Work counter of a launch: one slot per stream.  Launches on one stream are ordered (a counter is zeroed and used by
+// one launch at a time), launches on different streams never share a slot, so any number of them may be in flight.
+// Streams beyond the table's size share its last slots by hash (kCounterRing streams is far more than the library or a
+// sane caller creates); a destroyed stream's slot is simply reused by the next stream with that handle.
+static int32_t *counter_for_stream(cudaStream_t st) {
+    static std::mutex mu;
+    static std::unordered_map<cudaStream_t, int> slots;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = slots.find(st);
+    int slot;
+    if (it != slots.end()) slot = it->second;
+    else {
+        slot = (int)slots.size() < kCounterRing ? (int)slots.size() : (int)(((size_t)st >> 4) % kCounterRing);
+        slots.emplace(st, slot);
+    }
+    return tables().counters + (size_t)slot * kCounterStride;
+}
 
 template <int NG>
 static int launch_fused(const FusedArgs &fa_, bool want_mask, int n_items, int sm_count, cudaStream_t st) {
@@ -1160,17 +1283,19 @@ static int launch_fused(const FusedArgs &fa_, bool want_mask, int n_items, int s
         return e ? atoi(e) : 0;
     }();
     fa.prefetch = prefetch;
-    fa.counter = tables().counters + (size_t)(g_counter_ring.fetch_add(1) % kCounterRing) * kCounterStride;
+    fa.counter = counter_for_stream(st);
     RMPE_CUDA_TRY(cudaMemsetAsync(fa.counter, 0, sizeof(int32_t), st));
     const size_t smem = fused_smem_bytes(NG);
-    static bool attr_set = false;
-    if (!attr_set) {
-        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RMPE_CUDA_TRY(cudaFuncSetAttribute(k_warp_fused<NG, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static std::once_flag attr_once;
+    static cudaError_t attr_rc = cudaSuccess;
+    std::call_once(attr_once, [smem] {
+        cudaError_t e = cudaFuncSetAttribute(k_warp_fused<NG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_warp_fused<NG, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_warp_fused<NG, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_warp_fused<NG, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_rc = e;
+    });
+    RMPE_CUDA_TRY(attr_rc);
     const int grid = min((n_items + NG - 1) / NG, sm_count);
     const dim3 block(NG * kGroupThreads);
     if (fa.chw) {
@@ -1257,15 +1382,25 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
         k_mask46<<<grid, 128, 0, st>>>(ma);
         count_launch();
     }
-    if (b->out_labels && !warp_only) {
+    const bool nhwc = b->out_vec_label || b->out_heat_label || b->out_vec_weights || b->out_heat_weights;
+    if ((b->out_labels || nhwc) && !warp_only) {
         RasterArgs ra;
+        memset(&ra, 0, sizeof(ra));
         ra.joints = b->joints; ra.n_persons = b->n_persons; ra.M = b->M; ra.flip = b->flip;
         ra.mask = b->out_mask; ra.labels = b->out_labels; ra.out_joints = b->out_joints;
         ra.out_count = b->out_count; ra.status = b->status; ra.max_persons = b->max_persons;
         ra.f64 = (b->flags & RMPE_GT_LABELS_F64) ? 1 : 0; ra.no_transform = no_transform ? 1 : 0;
-        ra.sigma = 7.0; ra.thre = 8.0;
-        ProfScope ps("k_raster", st);
-        if (b->max_persons <= kRsMaxP && !simple) {
+        // Heatmapper(sigma=7., thre=8.) (py_rmpe_heatmapper.py:10-14); 0 = the reference's defaults
+        ra.sigma = b->sigma > 0.0 ? b->sigma : 7.0;
+        ra.thre = b->thre > 0.0 ? b->thre : 8.0;
+        ra.paf_average = (b->flags & RMPE_GT_PAF_AVERAGE) ? 1 : 0;
+        ra.y1 = b->out_vec_label; ra.y2 = b->out_heat_label; ra.x1 = b->out_vec_weights; ra.x2 = b->out_heat_weights;
+        RMPE_REQUIRE((((size_t)ra.y1 | (size_t)ra.y2 | (size_t)ra.x1 | (size_t)ra.x2 | (size_t)ra.labels) & 15) == 0,
+                     "label outputs must be 16-byte aligned");
+        const int pm = b->max_persons;
+        const size_t esz = ra.f64 ? 8 : 4;
+        bool two_pass = false;       // NHWC for more persons than the one-pass kernel holds tables for
+        if (!nhwc && pm <= kRsMaxP && !simple && !ra.paf_average) {
             static const int groups = [] {
                 const char *e = getenv("RMPE_RASTER_GROUPS");
                 int v = e ? atoi(e) : kRsGroups;
@@ -1273,17 +1408,84 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
             }();
             dim3 grid(groups, b->batch);
             const int kRsThreads = (kCellVec + 31) & ~31;
-            const int pm = b->max_persons;
             const size_t smem = (size_t)kLimbs * pm * sizeof(LimbRec) + (size_t)pm * kParts * 3 * 8 + 2 * (size_t)kParts * pm * kGrid * 4;
+            ProfScope ps("k_raster", st);
             // programmatic stream serialization behind k_warp_fused (see the griddepcontrol.wait in the kernel)
             if (ra.f64) RMPE_CUDA_TRY(launch_pdl(k_raster_small<double>, grid, dim3(kRsThreads), smem, st, ra));
             else RMPE_CUDA_TRY(launch_pdl(k_raster_small<float>, grid, dim3(kRsThreads), smem, st, ra));
+            count_launch();
         } else {
-            dim3 grid(3, b->batch);
-            if (ra.f64) k_raster<double><<<grid, kRasterThreads, 0, st>>>(ra);
-            else k_raster<float><<<grid, kRasterThreads, 0, st>>>(ra);
+            // k_raster_roles: shared memory = joints + max(role 0: exp tables of `part_batch` parts [+ band], role 1: limb
+            // records [+ band]).  All 18 parts resident when that fits (no barrier in the plane loop); when the grid is more
+            // than one wave of CTAs a smaller batch that lets two CTAs share an SM is preferred.
+            static const int smem_target_kb = [] {
+                const char *e = getenv("RMPE_RASTER_SMEM_KB");
+                int v = e ? atoi(e) : 104;
+                return (v >= 16 && v <= 220) ? v : 104;
+            }();
+            const size_t cap = (size_t)220 * 1024;
+            const size_t sj = ((size_t)pm * kParts * 3 * 8 + 15) & ~(size_t)15;
+            const size_t per_part = 2 * (size_t)pm * kGrid * 4;
+            const size_t recs = ((size_t)kLimbs * pm * sizeof(LimbRec) + 15) & ~(size_t)15;
+            auto fit_parts = [&](size_t budget) { return per_part ? (int)std::min<size_t>(kParts, budget > sj ? (budget - sj) / per_part : 0) : kParts; };
+            size_t smem = 0;
+            bool use_nhwc = nhwc;
+            if (use_nhwc) {
+                ra.part_batch = kParts;
+                ra.band_px = 0;
+                const int bands[3] = {544, 272, 136};
+                auto need = [&](int bp) {
+                    return sj + std::max(per_part * kParts + (size_t)bp * (kHeatCh + 1) * esz, recs + (size_t)bp * (kPafCh + 1) * esz);
+                };
+                for (int i = 0; i < 3 && !ra.band_px; i++) if (need(bands[i]) <= (size_t)smem_target_kb * 1024) ra.band_px = bands[i];
+                for (int i = 0; i < 3 && !ra.band_px; i++) if (need(bands[i]) <= cap) ra.band_px = bands[i];
+                if (ra.band_px) smem = need(ra.band_px);
+                else { use_nhwc = false; two_pass = true; }
+            }
+            if (!use_nhwc) {
+                RMPE_REQUIRE(ra.labels != nullptr, "out_labels is required (planar labels; also the scratch of the NHWC outputs "
+                                                   "when max_persons is too large for the one-pass kernel)");
+                const bool one_wave = 2 * b->batch <= T.sm_count;
+                int pb = fit_parts(one_wave ? cap : (size_t)smem_target_kb * 1024);
+                if (pb < 1) pb = fit_parts(cap);
+                RMPE_REQUIRE(pb >= 1, "max_persons too large for the rasteriser's shared memory");
+                ra.part_batch = pb;
+                smem = sj + std::max(per_part * pb, recs);
+                ra.y1 = ra.y2 = ra.x1 = ra.x2 = nullptr;
+            }
+            static std::once_flag roles_attr;
+            static cudaError_t roles_attr_rc = cudaSuccess;
+            std::call_once(roles_attr, [] {
+                const int mx = kMaxSmemOptin;
+                cudaError_t e = cudaFuncSetAttribute(k_raster_roles<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(k_raster_roles<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(k_raster_roles<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(k_raster_roles<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+                roles_attr_rc = e;
+            });
+            RMPE_CUDA_TRY(roles_attr_rc);
+            dim3 grid(2, b->batch);
+            {
+                ProfScope ps("k_raster", st);
+                if (ra.f64) {
+                    if (use_nhwc) RMPE_CUDA_TRY(launch_pdl(k_raster_roles<double, true>, grid, dim3(kRrThreads), smem, st, ra));
+                    else RMPE_CUDA_TRY(launch_pdl(k_raster_roles<double, false>, grid, dim3(kRrThreads), smem, st, ra));
+                } else {
+                    if (use_nhwc) RMPE_CUDA_TRY(launch_pdl(k_raster_roles<float, true>, grid, dim3(kRrThreads), smem, st, ra));
+                    else RMPE_CUDA_TRY(launch_pdl(k_raster_roles<float, false>, grid, dim3(kRrThreads), smem, st, ra));
+                }
+                count_launch();
+            }
+            if (two_pass) {
+                RmpeKerasBatch kb;
+                kb.batch = b->batch; kb.flags = b->flags & RMPE_GT_LABELS_F64;
+                kb.labels = b->out_labels; kb.mask = b->out_mask;
+                kb.vec_weights = b->out_vec_weights; kb.heat_weights = b->out_heat_weights;
+                kb.vec_label = b->out_vec_label; kb.heat_label = b->out_heat_label;
+                const int rc = rmpe_keras_batch(&kb, st);
+                if (rc != RMPE_OK) return rc;
+            }
         }
-        count_launch();
     }
     RMPE_CUDA_TRY(cudaGetLastError());
     return RMPE_OK;

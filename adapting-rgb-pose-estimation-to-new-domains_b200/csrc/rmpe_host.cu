@@ -119,14 +119,75 @@ struct Arena {
 struct State {
     bool init = false;
     int device = -1;
+    int generation = 0;           // bumped by every rmpe_init: per-thread contexts of an earlier life are rebuilt
     DeviceTables tab{};
     void *tab_mem = nullptr;
-    Arena arena;
-    cudaStream_t stream = nullptr;
-    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};   // chunk pipeline of the host-buffer GT wrapper
-    std::mutex mu;
+    std::mutex mu;                // lifetime only (init / shutdown / context registry): never held across a data call
 };
 static State g;
+
+// Everything a *_host call needs besides its arguments -- device arena, main stream, the three streams of the chunk
+// pipeline -- belongs to the CALLING THREAD: Keras worker threads (ds_generators.py:209 under fit_generator) call side
+// by side without serialising on a library lock.  The contexts are registered so that rmpe_shutdown can free them.
+struct HostCtx {
+    Arena arena;
+    cudaStream_t stream = nullptr;
+    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
+    int generation = -1;
+    bool registered = false;
+    void release() {
+        if (arena.dev) cudaFree(arena.dev);
+        arena = Arena{};
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+        for (int i = 0; i < 3; i++) { if (pipe[i]) cudaStreamDestroy(pipe[i]); pipe[i] = nullptr; }
+        generation = -1;
+    }
+    ~HostCtx();
+};
+static std::vector<HostCtx *> g_ctxs;     // guarded by g.mu
+HostCtx::~HostCtx() {
+    std::lock_guard<std::mutex> lk(g.mu);
+    g_ctxs.erase(std::remove(g_ctxs.begin(), g_ctxs.end(), this), g_ctxs.end());
+    if (g.init && generation == g.generation) { cudaSetDevice(g.device); release(); }
+}
+static thread_local HostCtx t_ctx;
+
+// the calling thread's context, ready for use on the library's device
+static int host_ctx(HostCtx **out) {
+    HostCtx &c = t_ctx;
+    int gen;
+    {
+        std::lock_guard<std::mutex> lk(g.mu);
+        if (!g.init) { set_error("rmpe_init not called"); return RMPE_E_NOTINIT; }
+        gen = g.generation;
+        if (!c.registered) { g_ctxs.push_back(&c); c.registered = true; }
+    }
+    RMPE_CUDA_TRY(cudaSetDevice(g.device));
+    if (c.generation != gen) {
+        c.arena = Arena{}; c.stream = nullptr; c.pipe[0] = c.pipe[1] = c.pipe[2] = nullptr;   // an earlier life's handles died with its shutdown
+        RMPE_CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 3; i++) RMPE_CUDA_TRY(cudaStreamCreateWithFlags(&c.pipe[i], cudaStreamNonBlocking));
+        c.generation = gen;
+    }
+    *out = &c;
+    return RMPE_OK;
+}
+// error exit of a *_host call: no copy that touches the caller's buffers may still be in flight when it returns
+static int host_fail(HostCtx &c, int rc) {
+    cudaStreamSynchronize(c.stream);
+    for (int i = 0; i < 3; i++) cudaStreamSynchronize(c.pipe[i]);
+    return rc;
+}
+#define RMPE_HOST_TRY(expr)                                                               \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            rmpe::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),       \
+                            __FILE__, __LINE__);                                          \
+            return host_fail(*ctx, RMPE_E_CUDA);                                          \
+        }                                                                                 \
+    } while (0)
 
 bool is_initialised() { return g.init; }
 const DeviceTables &tables() { return g.tab; }
@@ -216,9 +277,8 @@ extern "C" int rmpe_init(int device) {
     g.tab.bicubic_dp4a = (const uint32_t *)((uint8_t *)g.tab_mem + b16);
     g.tab.sm_count = prop.multiProcessorCount;
     RMPE_CUDA_TRY(cudaMalloc(&g.tab.counters, (size_t)kCounterRing * kCounterStride * sizeof(int32_t)));
-    RMPE_CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 3; i++) RMPE_CUDA_TRY(cudaStreamCreateWithFlags(&g.pipe[i], cudaStreamNonBlocking));
     g.device = device;
+    g.generation++;
     g.init = true;
     return RMPE_OK;
 }
@@ -230,11 +290,8 @@ extern "C" void rmpe_shutdown(void) {
     cudaDeviceSynchronize();
     if (g.tab_mem) cudaFree(g.tab_mem);
     if (g.tab.counters) cudaFree(g.tab.counters);
-    if (g.arena.dev) cudaFree(g.arena.dev);
-    if (g.stream) cudaStreamDestroy(g.stream);
-    for (int i = 0; i < 3; i++) { if (g.pipe[i]) cudaStreamDestroy(g.pipe[i]); g.pipe[i] = nullptr; }
+    for (HostCtx *c : g_ctxs) c->release();       // arenas and streams of every thread that made a *_host call
     g.init = false; g.device = -1; g.tab = DeviceTables{}; g.tab_mem = nullptr;
-    g.arena = Arena{}; g.stream = nullptr;
 }
 
 extern "C" const char *rmpe_last_error(void) { return t_error; }
@@ -384,46 +441,62 @@ extern "C" int rmpe_gt_batch_host(const RmpeGtBatchHost *h) {
     RMPE_REQUIRE(h != nullptr, "descriptor is null");
     RMPE_REQUIRE(h->batch >= 0, "negative batch");
     if (h->batch == 0) return RMPE_OK;
-    std::lock_guard<std::mutex> lk(g.mu);
-    RMPE_CUDA_TRY(cudaSetDevice(g.device));
+    HostCtx *ctx = nullptr;
+    int rc = host_ctx(&ctx);
+    if (rc != RMPE_OK) return rc;
     const int B = h->batch;
     const bool no_transform = (h->flags & RMPE_GT_NO_TRANSFORM) != 0;
     const bool no_warp = (h->flags & RMPE_GT_NO_WARP) != 0 || no_transform;
     const bool f64 = (h->flags & RMPE_GT_LABELS_F64) != 0;
+    const bool nhwc = h->out_vec_label || h->out_heat_label || h->out_vec_weights || h->out_heat_weights;
     const size_t esz = f64 ? 8 : 4;
+    RMPE_REQUIRE(h->max_persons >= 0 && h->max_persons <= kMaxPersonsGt, "max_persons must be in [0,64]");
+    if (!no_transform) RMPE_REQUIRE(h->src_mask && h->M && h->flip && h->src_height > 0 && h->src_width > 0, "missing source");
+    if (!no_warp) RMPE_REQUIRE(h->src_img != nullptr, "src_img is null");
+    RMPE_REQUIRE(h->n_persons != nullptr && (h->max_persons == 0 || h->joints != nullptr), "joints / n_persons");
+    RMPE_REQUIRE(!no_transform || h->out_mask != nullptr, "with RMPE_GT_NO_TRANSFORM out_mask is the input mask");
+    // n_persons lives on the host here: validate it instead of letting the kernels clamp it
+    for (int i = 0; i < B; i++)
+        RMPE_REQUIRE(h->n_persons[i] >= 0 && h->n_persons[i] <= h->max_persons, "n_persons[i] must be in [0, max_persons]");
     const size_t img_b = no_warp ? 0 : (size_t)B * h->src_height * h->src_width * 3;
     const size_t msk_b = no_transform ? 0 : (size_t)B * h->src_height * h->src_width;
     const size_t jnt_b = (size_t)B * h->max_persons * kParts * 3 * sizeof(double);
     const size_t oimg_b = no_warp ? 0 : (size_t)B * 3 * kOutW * kOutH;
     const size_t omsk_b = (size_t)B * kCells * esz;
-    const size_t olab_b = (size_t)B * kLayers * kCells * esz;  // always produced: the rasteriser also writes the joints
+    // planar labels are produced when asked for, and when nothing else would make the rasteriser run (it writes the joints)
+    const bool planar = h->out_labels != nullptr || !nhwc || h->max_persons > 24;
+    const size_t olab_b = planar ? (size_t)B * kLayers * kCells * esz : 0;
+    const size_t o38_b = (size_t)B * kCells * 38 * esz, o19_b = (size_t)B * kCells * 19 * esz;
     const size_t ocnt_b = h->out_count ? (size_t)B * kLimbs * kCells * sizeof(int32_t) : 0;
-    if (!no_transform) RMPE_REQUIRE(h->src_mask && h->M && h->flip && h->src_height > 0 && h->src_width > 0, "missing source");
-    if (!no_warp) RMPE_REQUIRE(h->src_img != nullptr, "src_img is null");
-    RMPE_REQUIRE(h->n_persons != nullptr && (h->max_persons == 0 || h->joints != nullptr), "joints / n_persons");
-    RMPE_REQUIRE(!no_transform || h->out_mask != nullptr, "with RMPE_GT_NO_TRANSFORM out_mask is the input mask");
 
     size_t need = Arena::need(img_b) + Arena::need(msk_b) + Arena::need(B * sizeof(RmpeSrcDesc)) + Arena::need(jnt_b) * 2 +
                   Arena::need(B * 4) * 2 + Arena::need(B * 48) + Arena::need(B) + Arena::need(oimg_b) +
-                  Arena::need(omsk_b) + Arena::need(olab_b) + Arena::need(ocnt_b);
-    int rc = g.arena.reserve(need);
+                  Arena::need(omsk_b) + Arena::need(olab_b) + Arena::need(ocnt_b) +
+                  (h->out_vec_label ? Arena::need(o38_b) : 0) + (h->out_vec_weights ? Arena::need(o38_b) : 0) +
+                  (h->out_heat_label ? Arena::need(o19_b) : 0) + (h->out_heat_weights ? Arena::need(o19_b) : 0);
+    rc = ctx->arena.reserve(need);
     if (rc != RMPE_OK) return rc;
-    g.arena.reset();
-    cudaStream_t st = g.stream;
+    Arena &A = ctx->arena;
+    A.reset();
+    cudaStream_t st = ctx->stream;
 
-    uint8_t *d_img = (uint8_t *)g.arena.take(img_b);
-    uint8_t *d_msk = (uint8_t *)g.arena.take(msk_b);
-    RmpeSrcDesc *d_desc = (RmpeSrcDesc *)g.arena.take(B * sizeof(RmpeSrcDesc));
-    double *d_j = (double *)g.arena.take(jnt_b);
-    double *d_jo = (double *)g.arena.take(jnt_b);
-    int32_t *d_np = (int32_t *)g.arena.take(B * 4);
-    int32_t *d_st = (int32_t *)g.arena.take(B * 4);
-    double *d_M = (double *)g.arena.take(B * 48);
-    uint8_t *d_flip = (uint8_t *)g.arena.take(B);
-    uint8_t *d_oimg = (uint8_t *)g.arena.take(oimg_b);
-    void *d_omsk = g.arena.take(omsk_b);
-    void *d_olab = g.arena.take(olab_b);
-    int32_t *d_ocnt = (int32_t *)g.arena.take(ocnt_b);
+    uint8_t *d_img = (uint8_t *)A.take(img_b);
+    uint8_t *d_msk = (uint8_t *)A.take(msk_b);
+    RmpeSrcDesc *d_desc = (RmpeSrcDesc *)A.take(B * sizeof(RmpeSrcDesc));
+    double *d_j = (double *)A.take(jnt_b);
+    double *d_jo = (double *)A.take(jnt_b);
+    int32_t *d_np = (int32_t *)A.take(B * 4);
+    int32_t *d_st = (int32_t *)A.take(B * 4);
+    double *d_M = (double *)A.take(B * 48);
+    uint8_t *d_flip = (uint8_t *)A.take(B);
+    uint8_t *d_oimg = (uint8_t *)A.take(oimg_b);
+    uint8_t *d_omsk = (uint8_t *)A.take(omsk_b);
+    uint8_t *d_olab = olab_b ? (uint8_t *)A.take(olab_b) : nullptr;
+    int32_t *d_ocnt = (int32_t *)A.take(ocnt_b);
+    uint8_t *d_y1 = h->out_vec_label ? (uint8_t *)A.take(o38_b) : nullptr;
+    uint8_t *d_x1 = h->out_vec_weights ? (uint8_t *)A.take(o38_b) : nullptr;
+    uint8_t *d_y2 = h->out_heat_label ? (uint8_t *)A.take(o19_b) : nullptr;
+    uint8_t *d_x2 = h->out_heat_weights ? (uint8_t *)A.take(o19_b) : nullptr;
 
     std::vector<RmpeSrcDesc> desc(B);
     for (int i = 0; i < B; i++) {
@@ -433,14 +506,14 @@ extern "C" int rmpe_gt_batch_host(const RmpeGtBatchHost *h) {
         desc[i].img_pitch = 3 * h->src_width; desc[i].mask_pitch = h->src_width;
     }
     // small per-sample tables first, on the main stream; the chunk streams wait for them
-    RMPE_CUDA_TRY(cudaMemcpyAsync(d_desc, desc.data(), B * sizeof(RmpeSrcDesc), cudaMemcpyHostToDevice, st));
-    if (jnt_b) RMPE_CUDA_TRY(cudaMemcpyAsync(d_j, h->joints, jnt_b, cudaMemcpyHostToDevice, st));
-    RMPE_CUDA_TRY(cudaMemcpyAsync(d_np, h->n_persons, B * 4, cudaMemcpyHostToDevice, st));
+    RMPE_HOST_TRY(cudaMemcpyAsync(d_desc, desc.data(), B * sizeof(RmpeSrcDesc), cudaMemcpyHostToDevice, st));
+    if (jnt_b) RMPE_HOST_TRY(cudaMemcpyAsync(d_j, h->joints, jnt_b, cudaMemcpyHostToDevice, st));
+    RMPE_HOST_TRY(cudaMemcpyAsync(d_np, h->n_persons, B * 4, cudaMemcpyHostToDevice, st));
     if (!no_transform) {
-        RMPE_CUDA_TRY(cudaMemcpyAsync(d_M, h->M, B * 48, cudaMemcpyHostToDevice, st));
-        RMPE_CUDA_TRY(cudaMemcpyAsync(d_flip, h->flip, B, cudaMemcpyHostToDevice, st));
+        RMPE_HOST_TRY(cudaMemcpyAsync(d_M, h->M, B * 48, cudaMemcpyHostToDevice, st));
+        RMPE_HOST_TRY(cudaMemcpyAsync(d_flip, h->flip, B, cudaMemcpyHostToDevice, st));
     }
-    RMPE_CUDA_TRY(cudaStreamSynchronize(st));
+    RMPE_HOST_TRY(cudaStreamSynchronize(st));
 
     // Chunk pipeline: sources in, kernels, results out, round-robin over three streams, so that the
     // host-to-device copy of chunk c+1, the kernels of chunk c and the device-to-host copy of chunk c-1
@@ -452,44 +525,51 @@ extern "C" int rmpe_gt_batch_host(const RmpeGtBatchHost *h) {
     }();
     const int chunk = B <= 8 ? B : std::max(8, (B + n_chunks - 1) / n_chunks);
     const size_t src_img_b = (size_t)h->src_height * h->src_width * 3, src_msk_b = (size_t)h->src_height * h->src_width;
+    const size_t lab1 = (size_t)kLayers * kCells * esz, msk1 = (size_t)kCells * esz;
+    const size_t s38 = (size_t)kCells * 38 * esz, s19 = (size_t)kCells * 19 * esz;
     for (int c0 = 0, ci = 0; c0 < B; c0 += chunk, ci++) {
         const int n = std::min(chunk, B - c0);
-        cudaStream_t cs = g.pipe[ci % 3];
-        if (img_b) RMPE_CUDA_TRY(cudaMemcpyAsync(d_img + c0 * src_img_b, h->src_img + c0 * src_img_b, n * src_img_b, cudaMemcpyHostToDevice, cs));
-        if (msk_b) RMPE_CUDA_TRY(cudaMemcpyAsync(d_msk + c0 * src_msk_b, h->src_mask + c0 * src_msk_b, n * src_msk_b, cudaMemcpyHostToDevice, cs));
+        cudaStream_t cs = ctx->pipe[ci % 3];
+        if (img_b) RMPE_HOST_TRY(cudaMemcpyAsync(d_img + c0 * src_img_b, h->src_img + c0 * src_img_b, n * src_img_b, cudaMemcpyHostToDevice, cs));
+        if (msk_b) RMPE_HOST_TRY(cudaMemcpyAsync(d_msk + c0 * src_msk_b, h->src_mask + c0 * src_msk_b, n * src_msk_b, cudaMemcpyHostToDevice, cs));
         if (no_transform)
-            RMPE_CUDA_TRY(cudaMemcpyAsync((uint8_t *)d_omsk + (size_t)c0 * kCells * esz, (const uint8_t *)h->out_mask + (size_t)c0 * kCells * esz,
-                                          (size_t)n * kCells * esz, cudaMemcpyHostToDevice, cs));
+            RMPE_HOST_TRY(cudaMemcpyAsync(d_omsk + c0 * msk1, (const uint8_t *)h->out_mask + c0 * msk1, n * msk1, cudaMemcpyHostToDevice, cs));
         RmpeGtBatch d;
         memset(&d, 0, sizeof(d));
         d.batch = n; d.max_persons = h->max_persons; d.flags = h->flags;
+        d.sigma = h->sigma; d.thre = h->thre;
         d.src_img = d_img; d.src_mask = d_msk; d.src_desc = d_desc + c0;     // descriptor offsets are batch-relative
         d.joints = d_j + (size_t)c0 * h->max_persons * kParts * 3; d.n_persons = d_np + c0;
         d.M = d_M + 6 * c0; d.flip = d_flip + c0;
         d.out_img = no_warp ? nullptr : d_oimg + (size_t)c0 * 3 * kOutW * kOutH;
-        d.out_mask = (uint8_t *)d_omsk + (size_t)c0 * kCells * esz;
-        d.out_labels = (uint8_t *)d_olab + (size_t)c0 * kLayers * kCells * esz;
+        d.out_mask = d_omsk + c0 * msk1;
+        d.out_labels = d_olab ? d_olab + c0 * lab1 : nullptr;
         d.out_joints = d_jo + (size_t)c0 * h->max_persons * kParts * 3;
         d.out_count = h->out_count ? d_ocnt + (size_t)c0 * kLimbs * kCells : nullptr;
+        d.out_vec_label = d_y1 ? d_y1 + c0 * s38 : nullptr; d.out_vec_weights = d_x1 ? d_x1 + c0 * s38 : nullptr;
+        d.out_heat_label = d_y2 ? d_y2 + c0 * s19 : nullptr; d.out_heat_weights = d_x2 ? d_x2 + c0 * s19 : nullptr;
         d.status = d_st + c0;
         rc = rmpe_gt_batch(&d, cs);
-        if (rc != RMPE_OK) return rc;
+        if (rc != RMPE_OK) return host_fail(*ctx, rc);
         if (h->out_img && oimg_b)
-            RMPE_CUDA_TRY(cudaMemcpyAsync(h->out_img + (size_t)c0 * 3 * kOutW * kOutH, d.out_img, (size_t)n * 3 * kOutW * kOutH, cudaMemcpyDeviceToHost, cs));
+            RMPE_HOST_TRY(cudaMemcpyAsync(h->out_img + (size_t)c0 * 3 * kOutW * kOutH, d.out_img, (size_t)n * 3 * kOutW * kOutH, cudaMemcpyDeviceToHost, cs));
         if (h->out_labels)
-            RMPE_CUDA_TRY(cudaMemcpyAsync((uint8_t *)h->out_labels + (size_t)c0 * kLayers * kCells * esz, d.out_labels,
-                                          (size_t)n * kLayers * kCells * esz, cudaMemcpyDeviceToHost, cs));
+            RMPE_HOST_TRY(cudaMemcpyAsync((uint8_t *)h->out_labels + c0 * lab1, d.out_labels, n * lab1, cudaMemcpyDeviceToHost, cs));
+        if (d_y1) RMPE_HOST_TRY(cudaMemcpyAsync((uint8_t *)h->out_vec_label + c0 * s38, d.out_vec_label, n * s38, cudaMemcpyDeviceToHost, cs));
+        if (d_y2) RMPE_HOST_TRY(cudaMemcpyAsync((uint8_t *)h->out_heat_label + c0 * s19, d.out_heat_label, n * s19, cudaMemcpyDeviceToHost, cs));
+        if (d_x1) RMPE_HOST_TRY(cudaMemcpyAsync((uint8_t *)h->out_vec_weights + c0 * s38, d.out_vec_weights, n * s38, cudaMemcpyDeviceToHost, cs));
+        if (d_x2) RMPE_HOST_TRY(cudaMemcpyAsync((uint8_t *)h->out_heat_weights + c0 * s19, d.out_heat_weights, n * s19, cudaMemcpyDeviceToHost, cs));
         if (h->out_count)
-            RMPE_CUDA_TRY(cudaMemcpyAsync(h->out_count + (size_t)c0 * kLimbs * kCells, d.out_count, (size_t)n * kLimbs * kCells * 4, cudaMemcpyDeviceToHost, cs));
+            RMPE_HOST_TRY(cudaMemcpyAsync(h->out_count + (size_t)c0 * kLimbs * kCells, d.out_count, (size_t)n * kLimbs * kCells * 4, cudaMemcpyDeviceToHost, cs));
     }
-    for (int i = 0; i < 3; i++) RMPE_CUDA_TRY(cudaStreamSynchronize(g.pipe[i]));
+    for (int i = 0; i < 3; i++) RMPE_HOST_TRY(cudaStreamSynchronize(ctx->pipe[i]));
     // the small outputs leave in one piece at the end: their host buffers are usually pageable, and a
     // device-to-host copy into pageable memory blocks the issuing thread -- inside the loop it would
     // serialise the chunk pipeline
-    if (h->out_mask && !no_transform) RMPE_CUDA_TRY(cudaMemcpyAsync(h->out_mask, d_omsk, omsk_b, cudaMemcpyDeviceToHost, st));
-    if (h->out_joints && jnt_b) RMPE_CUDA_TRY(cudaMemcpyAsync(h->out_joints, d_jo, jnt_b, cudaMemcpyDeviceToHost, st));
-    if (h->status) RMPE_CUDA_TRY(cudaMemcpyAsync(h->status, d_st, B * 4, cudaMemcpyDeviceToHost, st));
-    RMPE_CUDA_TRY(cudaStreamSynchronize(st));
+    if (h->out_mask && !no_transform) RMPE_HOST_TRY(cudaMemcpyAsync(h->out_mask, d_omsk, omsk_b, cudaMemcpyDeviceToHost, st));
+    if (h->out_joints && jnt_b) RMPE_HOST_TRY(cudaMemcpyAsync(h->out_joints, d_jo, jnt_b, cudaMemcpyDeviceToHost, st));
+    if (h->status) RMPE_HOST_TRY(cudaMemcpyAsync(h->status, d_st, B * 4, cudaMemcpyDeviceToHost, st));
+    RMPE_HOST_TRY(cudaStreamSynchronize(st));
     return RMPE_OK;
 }
 
@@ -498,33 +578,35 @@ extern "C" int rmpe_keras_batch_host(const RmpeKerasBatch *h) {
     RMPE_REQUIRE(h != nullptr && h->batch >= 0, "descriptor");
     if (h->batch == 0) return RMPE_OK;
     RMPE_REQUIRE(h->mask != nullptr, "mask is required");
-    std::lock_guard<std::mutex> lk(g.mu);
-    RMPE_CUDA_TRY(cudaSetDevice(g.device));
+    HostCtx *ctx = nullptr;
+    int rc = host_ctx(&ctx);
+    if (rc != RMPE_OK) return rc;
+    Arena &A = ctx->arena;
     const size_t esz = (h->flags & RMPE_GT_LABELS_F64) ? 8 : 4;
     const size_t B = (size_t)h->batch;
     const size_t lab_b = h->labels ? B * kLayers * kCells * esz : 0, msk_b = B * kCells * esz;
     const size_t o38 = B * kCells * 38 * esz, o19 = B * kCells * 19 * esz;
-    int rc = g.arena.reserve(Arena::need(lab_b) + Arena::need(msk_b) + 2 * Arena::need(o38) + 2 * Arena::need(o19));
+    rc = A.reserve(Arena::need(lab_b) + Arena::need(msk_b) + 2 * Arena::need(o38) + 2 * Arena::need(o19));
     if (rc != RMPE_OK) return rc;
-    g.arena.reset();
-    cudaStream_t st = g.stream;
+    A.reset();
+    cudaStream_t st = ctx->stream;
     RmpeKerasBatch d = *h;
-    void *d_lab = lab_b ? g.arena.take(lab_b) : nullptr;
-    void *d_msk = g.arena.take(msk_b);
-    if (lab_b) RMPE_CUDA_TRY(cudaMemcpyAsync(d_lab, h->labels, lab_b, cudaMemcpyHostToDevice, st));
-    RMPE_CUDA_TRY(cudaMemcpyAsync(d_msk, h->mask, msk_b, cudaMemcpyHostToDevice, st));
+    void *d_lab = lab_b ? A.take(lab_b) : nullptr;
+    void *d_msk = A.take(msk_b);
+    if (lab_b) RMPE_HOST_TRY(cudaMemcpyAsync(d_lab, h->labels, lab_b, cudaMemcpyHostToDevice, st));
+    RMPE_HOST_TRY(cudaMemcpyAsync(d_msk, h->mask, msk_b, cudaMemcpyHostToDevice, st));
     d.labels = d_lab; d.mask = d_msk;
-    d.vec_weights = h->vec_weights ? g.arena.take(o38) : nullptr;
-    d.heat_weights = h->heat_weights ? g.arena.take(o19) : nullptr;
-    d.vec_label = h->vec_label ? g.arena.take(o38) : nullptr;
-    d.heat_label = h->heat_label ? g.arena.take(o19) : nullptr;
+    d.vec_weights = h->vec_weights ? A.take(o38) : nullptr;
+    d.heat_weights = h->heat_weights ? A.take(o19) : nullptr;
+    d.vec_label = h->vec_label ? A.take(o38) : nullptr;
+    d.heat_label = h->heat_label ? A.take(o19) : nullptr;
     rc = rmpe_keras_batch(&d, st);
-    if (rc != RMPE_OK) return rc;
-    if (h->vec_weights) RMPE_CUDA_TRY(cudaMemcpyAsync(h->vec_weights, d.vec_weights, o38, cudaMemcpyDeviceToHost, st));
-    if (h->heat_weights) RMPE_CUDA_TRY(cudaMemcpyAsync(h->heat_weights, d.heat_weights, o19, cudaMemcpyDeviceToHost, st));
-    if (h->vec_label) RMPE_CUDA_TRY(cudaMemcpyAsync(h->vec_label, d.vec_label, o38, cudaMemcpyDeviceToHost, st));
-    if (h->heat_label) RMPE_CUDA_TRY(cudaMemcpyAsync(h->heat_label, d.heat_label, o19, cudaMemcpyDeviceToHost, st));
-    RMPE_CUDA_TRY(cudaStreamSynchronize(st));
+    if (rc != RMPE_OK) return host_fail(*ctx, rc);
+    if (h->vec_weights) RMPE_HOST_TRY(cudaMemcpyAsync(h->vec_weights, d.vec_weights, o38, cudaMemcpyDeviceToHost, st));
+    if (h->heat_weights) RMPE_HOST_TRY(cudaMemcpyAsync(h->heat_weights, d.heat_weights, o19, cudaMemcpyDeviceToHost, st));
+    if (h->vec_label) RMPE_HOST_TRY(cudaMemcpyAsync(h->vec_label, d.vec_label, o38, cudaMemcpyDeviceToHost, st));
+    if (h->heat_label) RMPE_HOST_TRY(cudaMemcpyAsync(h->heat_label, d.heat_label, o19, cudaMemcpyDeviceToHost, st));
+    RMPE_HOST_TRY(cudaStreamSynchronize(st));
     return RMPE_OK;
 }
 
@@ -573,10 +655,24 @@ extern "C" int rmpe_decode_batch_host(const RmpeDecodeBatchHost *h) {
     RMPE_REQUIRE(h->candidate && h->n_peaks && h->subset && h->n_subset, "candidate / subset outputs");
     RMPE_REQUIRE(h->max_peaks > 0 && h->max_peaks <= 1024 && h->max_cand > 0 && h->max_cand <= 4096 &&
                      h->max_persons > 0 && h->max_persons <= 128, "capacities");
-    std::lock_guard<std::mutex> lk(g.mu);
-    RMPE_CUDA_TRY(cudaSetDevice(g.device));
+    RMPE_REQUIRE(h->stride > 0, "stride");
     const int B = h->batch, MP = h->max_peaks, MC = h->max_cand, MS = h->max_persons;
-    size_t ws_bytes = rmpe_decode_workspace_bytes(B, h->frames, MP, MC);
+    // every blob a descriptor names must lie inside the caller's arrays (the kernels trust the offsets)
+    for (int i = 0; i < B; i++) {
+        const RmpeFrameDesc &f = h->frames[i];
+        RMPE_REQUIRE(f.n_scales >= 1 && f.n_scales <= RMPE_MAX_SCALES, "frame descriptor: n_scales");
+        for (int s = 0; s < f.n_scales; s++) {
+            RMPE_REQUIRE(f.grid_h[s] > 0 && f.grid_w[s] > 0 && f.heat_offset[s] >= 0 && f.paf_offset[s] >= 0, "frame descriptor: grid / offsets");
+            const size_t cells = (size_t)f.grid_h[s] * f.grid_w[s];
+            RMPE_REQUIRE((size_t)f.heat_offset[s] + cells * 19 <= h->heat_elems, "frame descriptor: heat blob beyond heat_elems");
+            RMPE_REQUIRE((size_t)f.paf_offset[s] + cells * 38 <= h->paf_elems, "frame descriptor: PAF blob beyond paf_elems");
+        }
+    }
+    HostCtx *ctx = nullptr;
+    int rc = host_ctx(&ctx);
+    if (rc != RMPE_OK) return rc;
+    Arena &A = ctx->arena;
+    size_t ws_bytes = rmpe_decode_workspace_bytes(B, h->frames, MP, MC, h->stride);
     const size_t cand_b = (size_t)B * kParts * MP * 4 * 8, npk_b = (size_t)B * kParts * 4;
     const size_t conn_b = (size_t)B * kLimbs * MP * 5 * 8, nconn_b = (size_t)B * kLimbs * 4;
     const size_t lc_b = h->limb_cand ? (size_t)B * kLimbs * MC * 4 * 8 : 0;
@@ -584,27 +680,27 @@ extern "C" int rmpe_decode_batch_host(const RmpeDecodeBatchHost *h) {
     size_t need = Arena::need(h->heat_elems * 4) + Arena::need(h->paf_elems * 4) + Arena::need(B * sizeof(RmpeFrameDesc)) +
                   Arena::need(cand_b) + Arena::need(npk_b) + Arena::need(conn_b) + Arena::need(nconn_b) * 2 +
                   Arena::need(lc_b) + Arena::need(sub_b) + Arena::need(B * 4) * 2 + Arena::need(ws_bytes);
-    int rc = g.arena.reserve(need);
+    rc = A.reserve(need);
     if (rc != RMPE_OK) return rc;
-    g.arena.reset();
-    cudaStream_t st = g.stream;
-    float *d_heat = (float *)g.arena.take(h->heat_elems * 4);
-    float *d_paf = (float *)g.arena.take(h->paf_elems * 4);
-    RmpeFrameDesc *d_fr = (RmpeFrameDesc *)g.arena.take(B * sizeof(RmpeFrameDesc));
-    double *d_cand = (double *)g.arena.take(cand_b);
-    int32_t *d_npk = (int32_t *)g.arena.take(npk_b);
-    double *d_conn = (double *)g.arena.take(conn_b);
-    int32_t *d_nconn = (int32_t *)g.arena.take(nconn_b);
-    int32_t *d_nlc = (int32_t *)g.arena.take(nconn_b);
-    double *d_lc = lc_b ? (double *)g.arena.take(lc_b) : nullptr;
-    double *d_sub = (double *)g.arena.take(sub_b);
-    int32_t *d_nsub = (int32_t *)g.arena.take(B * 4);
-    int32_t *d_st = (int32_t *)g.arena.take(B * 4);
-    void *d_ws = g.arena.take(ws_bytes);
-    RMPE_CUDA_TRY(cudaMemcpyAsync(d_heat, h->heat, h->heat_elems * 4, cudaMemcpyHostToDevice, st));
-    RMPE_CUDA_TRY(cudaMemcpyAsync(d_paf, h->paf, h->paf_elems * 4, cudaMemcpyHostToDevice, st));
-    RMPE_CUDA_TRY(cudaMemcpyAsync(d_fr, h->frames, B * sizeof(RmpeFrameDesc), cudaMemcpyHostToDevice, st));
-    RMPE_CUDA_TRY(cudaMemsetAsync(d_npk, 0, npk_b, st));
+    A.reset();
+    cudaStream_t st = ctx->stream;
+    float *d_heat = (float *)A.take(h->heat_elems * 4);
+    float *d_paf = (float *)A.take(h->paf_elems * 4);
+    RmpeFrameDesc *d_fr = (RmpeFrameDesc *)A.take(B * sizeof(RmpeFrameDesc));
+    double *d_cand = (double *)A.take(cand_b);
+    int32_t *d_npk = (int32_t *)A.take(npk_b);
+    double *d_conn = (double *)A.take(conn_b);
+    int32_t *d_nconn = (int32_t *)A.take(nconn_b);
+    int32_t *d_nlc = (int32_t *)A.take(nconn_b);
+    double *d_lc = lc_b ? (double *)A.take(lc_b) : nullptr;
+    double *d_sub = (double *)A.take(sub_b);
+    int32_t *d_nsub = (int32_t *)A.take(B * 4);
+    int32_t *d_st = (int32_t *)A.take(B * 4);
+    void *d_ws = A.take(ws_bytes);
+    RMPE_HOST_TRY(cudaMemcpyAsync(d_heat, h->heat, h->heat_elems * 4, cudaMemcpyHostToDevice, st));
+    RMPE_HOST_TRY(cudaMemcpyAsync(d_paf, h->paf, h->paf_elems * 4, cudaMemcpyHostToDevice, st));
+    RMPE_HOST_TRY(cudaMemcpyAsync(d_fr, h->frames, B * sizeof(RmpeFrameDesc), cudaMemcpyHostToDevice, st));
+    RMPE_HOST_TRY(cudaMemsetAsync(d_npk, 0, npk_b, st));
     RmpeDecodeBatch d;
     memset(&d, 0, sizeof(d));
     d.batch = B; d.max_peaks = MP; d.max_cand = MC; d.max_persons = MS; d.stride = h->stride; d.flags = h->flags;
@@ -614,16 +710,45 @@ extern "C" int rmpe_decode_batch_host(const RmpeDecodeBatchHost *h) {
     d.limb_cand = d_lc; d.n_limb_cand = d_nlc; d.subset = d_sub; d.n_subset = d_nsub; d.status = d_st;
     d.workspace = d_ws; d.workspace_bytes = ws_bytes;
     rc = rmpe_decode_batch(&d, st);
-    if (rc != RMPE_OK) return rc;
-    RMPE_CUDA_TRY(cudaMemcpyAsync(h->candidate, d_cand, cand_b, cudaMemcpyDeviceToHost, st));
-    RMPE_CUDA_TRY(cudaMemcpyAsync(h->n_peaks, d_npk, npk_b, cudaMemcpyDeviceToHost, st));
-    if (h->connections) RMPE_CUDA_TRY(cudaMemcpyAsync(h->connections, d_conn, conn_b, cudaMemcpyDeviceToHost, st));
-    if (h->n_conn) RMPE_CUDA_TRY(cudaMemcpyAsync(h->n_conn, d_nconn, nconn_b, cudaMemcpyDeviceToHost, st));
-    if (h->limb_cand) RMPE_CUDA_TRY(cudaMemcpyAsync(h->limb_cand, d_lc, lc_b, cudaMemcpyDeviceToHost, st));
-    if (h->n_limb_cand) RMPE_CUDA_TRY(cudaMemcpyAsync(h->n_limb_cand, d_nlc, nconn_b, cudaMemcpyDeviceToHost, st));
-    RMPE_CUDA_TRY(cudaMemcpyAsync(h->subset, d_sub, sub_b, cudaMemcpyDeviceToHost, st));
-    RMPE_CUDA_TRY(cudaMemcpyAsync(h->n_subset, d_nsub, B * 4, cudaMemcpyDeviceToHost, st));
-    if (h->status) RMPE_CUDA_TRY(cudaMemcpyAsync(h->status, d_st, B * 4, cudaMemcpyDeviceToHost, st));
-    RMPE_CUDA_TRY(cudaStreamSynchronize(st));
+    if (rc != RMPE_OK) return host_fail(*ctx, rc);
+    // Counts first; then only the filled prefix of every capacity-sized table comes back (a frame fills ~50 of its
+    // 18 x max_peaks candidate rows): one strided copy per table, row = the largest prefix any frame / limb uses.
+    std::vector<int32_t> npk((size_t)B * kParts), nconn((size_t)B * kLimbs), nlc((size_t)B * kLimbs), nsub(B);
+    RMPE_HOST_TRY(cudaMemcpyAsync(npk.data(), d_npk, npk_b, cudaMemcpyDeviceToHost, st));
+    RMPE_HOST_TRY(cudaMemcpyAsync(nconn.data(), d_nconn, nconn_b, cudaMemcpyDeviceToHost, st));
+    if (h->limb_cand) RMPE_HOST_TRY(cudaMemcpyAsync(nlc.data(), d_nlc, nconn_b, cudaMemcpyDeviceToHost, st));
+    RMPE_HOST_TRY(cudaMemcpyAsync(nsub.data(), d_nsub, B * 4, cudaMemcpyDeviceToHost, st));
+    if (h->status) RMPE_HOST_TRY(cudaMemcpyAsync(h->status, d_st, B * 4, cudaMemcpyDeviceToHost, st));
+    RMPE_HOST_TRY(cudaStreamSynchronize(st));
+    int max_cand_rows = 0, max_conn = 0, max_lc = 0, max_sub = 0;
+    for (int i = 0; i < B; i++) {
+        int tot = 0;
+        for (int p = 0; p < kParts; p++) tot += std::min(npk[(size_t)i * kParts + p], MP);
+        max_cand_rows = std::max(max_cand_rows, tot);
+        for (int k = 0; k < kLimbs; k++) {
+            max_conn = std::max(max_conn, std::min(nconn[(size_t)i * kLimbs + k], MP));
+            max_lc = std::max(max_lc, std::min(nlc[(size_t)i * kLimbs + k], MC));
+        }
+        max_sub = std::max(max_sub, std::min(nsub[i], MS));
+    }
+    memcpy(h->n_peaks, npk.data(), npk_b);
+    if (h->n_conn) memcpy(h->n_conn, nconn.data(), nconn_b);
+    if (h->n_limb_cand) {
+        if (h->limb_cand) memcpy(h->n_limb_cand, nlc.data(), nconn_b);
+        else memset(h->n_limb_cand, 0, nconn_b);
+    }
+    memcpy(h->n_subset, nsub.data(), B * 4);
+    if (max_cand_rows)
+        RMPE_HOST_TRY(cudaMemcpy2DAsync(h->candidate, (size_t)kParts * MP * 32, d_cand, (size_t)kParts * MP * 32, (size_t)max_cand_rows * 32,
+                                        B, cudaMemcpyDeviceToHost, st));
+    if (h->connections && max_conn)
+        RMPE_HOST_TRY(cudaMemcpy2DAsync(h->connections, (size_t)MP * 40, d_conn, (size_t)MP * 40, (size_t)max_conn * 40, (size_t)B * kLimbs,
+                                        cudaMemcpyDeviceToHost, st));
+    if (h->limb_cand && max_lc)
+        RMPE_HOST_TRY(cudaMemcpy2DAsync(h->limb_cand, (size_t)MC * 32, d_lc, (size_t)MC * 32, (size_t)max_lc * 32, (size_t)B * kLimbs,
+                                        cudaMemcpyDeviceToHost, st));
+    if (max_sub)
+        RMPE_HOST_TRY(cudaMemcpy2DAsync(h->subset, (size_t)MS * 160, d_sub, (size_t)MS * 160, (size_t)max_sub * 160, B, cudaMemcpyDeviceToHost, st));
+    RMPE_HOST_TRY(cudaStreamSynchronize(st));
     return RMPE_OK;
 }

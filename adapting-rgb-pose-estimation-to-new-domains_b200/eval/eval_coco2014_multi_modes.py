@@ -47,29 +47,36 @@ def decode_frames(frames, params, model_params=None, **caps):
     return _batch.decode_batch_host(frames, thre1=params['thre1'], thre2=params['thre2'], stride=stride, **caps)
 
 
+_PEAK_RADIUS = 4
+_LIMB_HALF_WIDTH = 4
+_LIMB_BLEND = 0.6        # weight of the freshly painted limb over the canvas so far
+
+
+def _limb_polygon(p0, p1):
+    """Outline of the ellipse the reference paints for a limb between peaks p0 and p1 (x, y): centred on the
+    truncated midpoint, half the limb long, _LIMB_HALF_WIDTH wide, rotated to whole degrees."""
+    (xa, ya), (xb, yb) = p0, p1
+    centre = (int((xa + xb) / 2.0), int((ya + yb) / 2.0))
+    half_len = int(math.hypot(xa - xb, ya - yb) / 2)
+    tilt = int(math.degrees(math.atan2(ya - yb, xa - xb)))
+    return cv2.ellipse2Poly(centre, (half_len, _LIMB_HALF_WIDTH), tilt, 0, 360, 1)
+
+
 def draw_canvas(canvas, candidate, subset, n_peaks):
-    """Reference drawing tail (:417-441): circles on every peak, blended limb ellipses."""
-    off = 0
-    for i in range(18):
-        for j in range(int(n_peaks[i])):
-            x, y = int(candidate[off + j, 0]), int(candidate[off + j, 1])
-            cv2.circle(canvas, (x, y), 4, colors[i], thickness=-1)
-        off += int(n_peaks[i])
-    stickwidth = 4
-    for i in range(17):
-        for n in range(len(subset)):
-            index = subset[n][np.array(limbSeq[i]) - 1]
-            if -1 in index:
+    """Overlay equal to the reference's drawing tail (eval...:417-441; D7, outside the GPU path): a filled dot on every
+    peak in its part colour, then limb by limb (the 17 body limbs, not the ear-shoulder pair) and person by person a
+    filled ellipse blended 60:40 over everything painted before it."""
+    part_of_row = np.repeat(np.arange(18), np.asarray(n_peaks[:18], dtype=int))
+    for row, part in enumerate(part_of_row):
+        cv2.circle(canvas, (int(candidate[row, 0]), int(candidate[row, 1])), _PEAK_RADIUS, colors[part], thickness=-1)
+    for limb, (part_a, part_b) in enumerate(limbSeq[:17]):
+        for person in subset:
+            ia, ib = int(person[part_a - 1]), int(person[part_b - 1])
+            if ia < 0 or ib < 0:
                 continue
-            cur_canvas = canvas.copy()
-            Y = candidate[index.astype(int), 0]
-            X = candidate[index.astype(int), 1]
-            mX, mY = np.mean(X), np.mean(Y)
-            length = ((X[0] - X[1]) ** 2 + (Y[0] - Y[1]) ** 2) ** 0.5
-            angle = math.degrees(math.atan2(X[0] - X[1], Y[0] - Y[1]))
-            polygon = cv2.ellipse2Poly((int(mY), int(mX)), (int(length / 2), stickwidth), int(angle), 0, 360, 1)
-            cv2.fillConvexPoly(cur_canvas, polygon, colors[i])
-            canvas = cv2.addWeighted(canvas, 0.4, cur_canvas, 0.6, 0)
+            painted = canvas.copy()
+            cv2.fillConvexPoly(painted, _limb_polygon(candidate[ia, :2], candidate[ib, :2]), colors[limb])
+            canvas = cv2.addWeighted(canvas, 1.0 - _LIMB_BLEND, painted, _LIMB_BLEND, 0)
     return canvas
 
 

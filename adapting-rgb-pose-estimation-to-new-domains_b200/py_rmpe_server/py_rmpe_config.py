@@ -1,7 +1,8 @@
 """Constants of the target-generation path -- same names, values and channel layout as the
 reference's py_rmpe_server/py_rmpe_config.py:12-55 (RmpeGlobalConfig, TransformationParams)
-and :58-95 (RmpeCocoConfig.convert).  The CUDA side holds the same tables in
-csrc/rmpe_constants.cuh; tests/test_config.py checks the two agree.
+and :58-95 (RmpeCocoConfig.convert).  The CUDA side holds the same tables as __constant__ arrays in
+csrc/rmpe_common.cuh (c_limb_from / c_limb_to / c_flip_partner); tests/test_host_logic.py::test_config_tables
+checks the two agree.
 """
 import numpy as np
 

@@ -1,43 +1,3 @@
-"""Drop-in for the reference's py_rmpe_server/py_rmpe_heatmapper_mask.py (same algorithm as py_rmpe_heatmapper.py; Heatmapper :8-138,
-distances :144-155).  create_heatmaps() hands joints + mask to the sm_100a rasteriser
-(k_raster) and returns the (57,46,46) float64 stack; there is no NumPy rasteriser here."""
-import numpy as np
-
-from .. import batch as _batch
-from .py_rmpe_config import RmpeGlobalConfig, TransformationParams
-
-
-class Heatmapper:
-
-    def __init__(self, sigma=TransformationParams.sigma, thre=TransformationParams.paf_thre):
-        if float(sigma) != 7. or float(thre) != 8.:
-            raise NotImplementedError("the sm_100a rasteriser is built for sigma=7, paf_thre=8 "
-                                      "(TransformationParams defaults)")
-        self.double_sigma2 = 2 * sigma * sigma
-        self.thre = thre
-        stride = RmpeGlobalConfig.stride
-        # kept for callers that inspect them (reference :22-25): cell centres / cell top-left
-        self.grid_x = np.arange(RmpeGlobalConfig.width // stride) * stride + stride / 2 - 0.5
-        self.grid_y = np.arange(RmpeGlobalConfig.height // stride) * stride + stride / 2 - 0.5
-        self.Y, self.X = np.mgrid[0:RmpeGlobalConfig.height:stride, 0:RmpeGlobalConfig.width:stride]
-
-    def create_heatmaps(self, joints, mask, return_count=False):
-        joints = np.asarray(joints, dtype=np.float64)
-        P = joints.shape[0]
-        res = _batch.heatmaps_host(joints.reshape(1, P, 18, 3), [P], np.asarray(mask, dtype=np.float64)[None],
-                                   f64=True, want_count=return_count)
-        if res["status"][0] & 1:
-            print("Parts are too close to each other. Length is zero. Skipping")  # reference :81-84
-        if return_count:
-            return res["labels"][0], res["count"][0]
-        return res["labels"][0]
-
-
-def distances(X, Y, x1, y1, x2, y2):
-    """Point-to-line distance helper of the reference (:144-155); host-side convenience only --
-    the rasteriser evaluates the same un-fused f64 expression on the device."""
-    xD = (x2 - x1)
-    yD = (y2 - y1)
-    norm2 = np.sqrt(xD ** 2 + yD ** 2)
-    dist = xD * (y1 - Y) - (x1 - X) * yD
-    return np.abs(dist / norm2)
+"""The reference keeps a second copy of the rasteriser in py_rmpe_server/py_rmpe_heatmapper_mask.py (same class, same
+signatures); here both module paths resolve to the one implementation in py_rmpe_heatmapper.py."""
+from .py_rmpe_heatmapper import Heatmapper, distances  # noqa: F401

@@ -1,7 +1,8 @@
 """Drop-in for the reference's py_rmpe_server/py_rmpe_transformer.py (AugmentSelection :10-78,
 Transformer.transform :83-114).  Same names, arguments, return values and in-place mutation of
 meta['joints']; the arithmetic runs in the sm_100a kernels behind include/rmpe_b200.h
-(k_warp_tile, k_mask46, k_raster) -- nothing here computes pixels on the CPU."""
+(k_warp_fused: image + mask warp and the 368->46 mask reduction; k_raster_small / k_raster_roles: keypoint
+transform) -- nothing here computes pixels on the CPU."""
 import random
 
 import numpy as np

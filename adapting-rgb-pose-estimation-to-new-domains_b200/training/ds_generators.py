@@ -4,8 +4,8 @@
 `gen(n_stages)` yields `[x (B,368,368,3) u8, x1 (B,46,46,38), x2 (B,46,46,19)], [y1 (B,46,46,38),
 y2 (B,46,46,19)] * n_stages` like the reference.  The per-sample transposes / repeats / concatenations
 of the reference (:47-77) run as ONE pass of k_keras_batch over the whole batch (rmpe_keras_batch);
-`FusedDataIterator` additionally runs warp + mask + labels for the whole batch in one call instead
-of sample by sample.  `DataGeneratorClient` (:109-186) is the ZMQ PULL side of py_rmpe_server/rmpe_server.py;
+`FusedDataIterator` runs warp + mask + labels for the whole batch in ONE C call whose rasteriser writes the
+NHWC tensors itself (RmpeGtBatchHost.out_vec_label ...): one host-to-device and one device-to-host trip per batch.  `DataGeneratorClient` (:109-186) is the ZMQ PULL side of py_rmpe_server/rmpe_server.py;
 the wire format lives in rmpe_server.send_arrays / recv_arrays."""
 import numpy as np
 
@@ -107,7 +107,7 @@ class DataIterator(DataIteratorBase):
 class FusedDataIterator(DataIteratorBase):
     """Batched superset: `source` yields raw (img HxWx3 u8, mask HxW u8, meta) triples of one
     geometry (what RawDataIterator.read_data returns); a whole batch goes through ONE
-    rmpe_gt_batch_host call and ONE rmpe_keras_batch_host call."""
+    rmpe_gt_batch_host call: the planar (57,46,46) labels never exist, the rasteriser emits y1 / y2 / x1 / x2."""
 
     def __init__(self, source, augment=True, batch_size=10):
         super(FusedDataIterator, self).__init__(batch_size)
@@ -133,12 +133,11 @@ class FusedDataIterator(DataIteratorBase):
                                   [a.scale for a in augs], [m['objpos'][0] for _, _, m in buf],
                                   [m['scale_provided'][0] for _, _, m in buf])
             r = _batch.gt_batch_host(np.stack([b[0] for b in buf]), np.stack([b[1] for b in buf]), joints, n_persons, M,
-                                     [1 if a.flip else 0 for a in augs], f64=True)
-            kb = _batch.keras_batch_host(r["labels"], r["mask"])
+                                     [1 if a.flip else 0 for a in augs], f64=True, want_labels=False, keras=True)
             for i, (_, _, m) in enumerate(buf):
                 if n_persons[i]:
                     m['joints'][:, :, :] = r["joints"][i, :n_persons[i]]
                 self.keypoints[i] = m['joints']
             buf = []
-            yield [r["img"], kb["x1"], kb["x2"]], [kb["y1"], kb["y2"]] * n_stages
+            yield [r["img"], r["x1"], r["x2"]], [r["y1"], r["y2"]] * n_stages
             self.keypoints = [None] * self.batch_size

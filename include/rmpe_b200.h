@@ -28,7 +28,8 @@
 extern "C" {
 #endif
 
-#define RMPE_ABI_VERSION 1
+#define RMPE_ABI_VERSION 2   /* 2: sigma / thre and the NHWC (Keras) outputs in RmpeGtBatch[Host], stride in
+                                  rmpe_decode_workspace_bytes, RMPE_ST_PERSONS_CLAMPED */
 
 /* error codes */
 #define RMPE_OK 0
@@ -53,6 +54,7 @@ extern "C" {
 #define RMPE_ST_PERSON_OVERFLOW 0x8  /* more assembled persons than max_persons */
 #define RMPE_ST_FOUND_GT2 0x10       /* the reference would raise IndexError (eval...:192-195) */
 #define RMPE_ST_SINGULAR 0x20        /* affine matrix not invertible (cv2 would produce border) */
+#define RMPE_ST_PERSONS_CLAMPED 0x40 /* n_persons[i] was outside [0, max_persons]: clamped, extra persons ignored */
 
 /* ---------------------------------------------------------------------------------------- */
 /* lifetime                                                                                   */
@@ -99,6 +101,9 @@ typedef struct RmpeSrcDesc {
 #define RMPE_GT_NO_WARP 0x8        /* skip image warp (labels + mask + joints only) */
 #define RMPE_GT_SIMPLE_KERNELS 0x10 /* debugging: straight-line kernels without smem staging */
 #define RMPE_GT_WARP_ONLY 0x20      /* image warp only (per-kernel timing in bench.py) */
+#define RMPE_GT_PAF_AVERAGE 0x40    /* NON-reference variant: PAF vectors averaged over the persons whose band covers a
+                                       pixel (the lines commented out at py_rmpe_heatmapper.py:119-126) instead of the
+                                       reference's last-person-wins overwrite */
 
 typedef struct RmpeGtBatch {
     int32_t batch;
@@ -120,13 +125,26 @@ typedef struct RmpeGtBatch {
     double *out_joints;           /* [batch][max_persons][18][3] */
     int32_t *out_count;           /* optional [batch][19][46][46]: put_vector_maps' local `count` */
     int32_t *status;              /* [batch] */
+    /* Heatmapper(sigma, thre) (py_rmpe_heatmapper.py:10-14); 0 selects the reference defaults 7.0 / 8.0 */
+    double sigma;
+    double thre;
+    /* Keras-ready NHWC tensors of DataIteratorBase.gen (training/ds_generators.py:47-63), written by the rasteriser
+     * itself; each may be NULL.  With any of them set, out_labels may be NULL.  Element type follows
+     * RMPE_GT_LABELS_F64. */
+    void *out_vec_label;          /* y1 [batch][46][46][38] = labels[0:38] */
+    void *out_heat_label;         /* y2 [batch][46][46][19] = labels[38:57] */
+    void *out_vec_weights;        /* x1 [batch][46][46][38] = mask repeated */
+    void *out_heat_weights;       /* x2 [batch][46][46][19] */
 } RmpeGtBatch;
 
 int rmpe_gt_batch(const RmpeGtBatch *b, void *stream);
 
 /* Same path with HOST buffers (the call the Python drop-in classes make).  Source images must
- * share one (height,width); copies go through the library's pinned staging arena and are
- * inside the call.  Any output pointer may be NULL to skip its read-back. */
+ * share one (height,width).  Copies are inside the call: cudaMemcpyAsync straight between the caller's
+ * buffers and a device arena owned by the calling thread (no host staging copy -- pin the buffers to let
+ * the chunk pipeline overlap copies and kernels; pageable buffers work but serialise).  Any output
+ * pointer may be NULL to skip its read-back.  Calls from different host threads do not serialise: each
+ * thread has its own arena and streams. */
 typedef struct RmpeGtBatchHost {
     int32_t batch;
     int32_t max_persons;
@@ -146,6 +164,12 @@ typedef struct RmpeGtBatchHost {
     double *out_joints;
     int32_t *out_count;
     int32_t *status;
+    double sigma;                 /* as in RmpeGtBatch */
+    double thre;
+    void *out_vec_label;
+    void *out_heat_label;
+    void *out_vec_weights;
+    void *out_heat_weights;
 } RmpeGtBatchHost;
 
 int rmpe_gt_batch_host(const RmpeGtBatchHost *b);
@@ -226,7 +250,7 @@ typedef struct RmpeDecodeBatch {
 } RmpeDecodeBatch;
 
 size_t rmpe_decode_workspace_bytes(int batch, const RmpeFrameDesc *frames_host, int max_peaks,
-                                   int max_cand);
+                                   int max_cand, int stride);
 int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream);
 
 /* Host-buffer variant: blobs and results in host memory; frames is a host array. */
@@ -257,13 +281,20 @@ typedef struct RmpeDecodeBatchHost {
 
 int rmpe_decode_batch_host(const RmpeDecodeBatchHost *b);
 
-/* debugging / stage-parity hooks: materialise D1 (upsampled or scale-averaged heat map, planar
+/* debugging / stage-parity hooks (model stride 8 only): materialise D1 (upsampled or scale-averaged heat map, planar
  * [18][H][W], float32 for n_scales==1 else float64) and D2's smoothed map for one frame. */
 int rmpe_debug_heat_maps(const RmpeFrameDesc *frame_host, const float *heat_dev, void *up_out_dev,
                          void *smooth_out_dev, void *stream);
 /* evaluate the up-sampled PAF at integer points (n x (c,y,x) int32 triples) for one frame */
 int rmpe_debug_paf_points(const RmpeFrameDesc *frame_host, const float *paf_dev, int n,
                           const int32_t *cyx_dev, double *out_dev, void *stream);
+
+/* D5/D6 alone (eval...:364-415) on caller-made connection lists of one frame, all pointers DEVICE memory laid out as
+ * in RmpeDecodeBatch with batch = 1.  Test hook for RMPE_ST_FOUND_GT2: connection lists made by the library itself are
+ * one-to-one per limb and cannot produce the reference's IndexError. */
+int rmpe_debug_assemble(int max_peaks, int max_persons, const double *candidate_dev, const double *connections_dev,
+                        const int32_t *n_conn_dev, const int32_t *n_peaks_dev, double *subset_dev,
+                        int32_t *n_subset_dev, int32_t *status_dev, void *stream);
 
 /* ---------------------------------------------------------------------------------------- */
 /* U1  util.padRightDownCorner (util.py:57-77) on a device HWC u8 image                       */

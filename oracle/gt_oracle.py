@@ -286,9 +286,10 @@ def _py_round(v):
     return int(round(float(v)))  # python-3 round = half to even (py_rmpe_heatmapper.py:95-98)
 
 
-def create_heatmaps(joints, mask, sigma=SIGMA, thre=PAF_THRE, return_count=False):
+def create_heatmaps(joints, mask, sigma=SIGMA, thre=PAF_THRE, return_count=False, paf_average=False):
     """labels (57,46,46) f64.  count (19,46,46) int64 is the per-limb local `count` of
-    put_vector_maps (:71,:122), which the reference computes and discards."""
+    put_vector_maps (:71,:122), which the reference computes and discards.  paf_average=True is the NON-reference
+    variant spelt out in the reference's comments (:119-126): `+=` instead of `=` and `/= count` at the end."""
     joints = np.asarray(joints, dtype=np.float64)
     double_sigma2 = 2 * sigma * sigma
     grid = np.arange(GRID) * STRIDE + STRIDE / 2 - 0.5          # :22-23 cell centres
@@ -338,9 +339,17 @@ def create_heatmaps(joints, mask, sigma=SIGMA, thre=PAF_THRE, return_count=False
             dist = xD * (y1 - Y) - (x1 - X) * yD
             dist = dist / norm2
             on = np.abs(dist) <= thre
-            heat[2 * k][sl][on] = ux
-            heat[2 * k + 1][sl][on] = uy
+            if paf_average:
+                heat[2 * k][sl][on] += ux          # "# += dist * dx" (:120)
+                heat[2 * k + 1][sl][on] += uy
+            else:
+                heat[2 * k][sl][on] = ux
+                heat[2 * k + 1][sl][on] = uy
             counts[k][sl][on] += 1
+        if paf_average:                            # "# heatmaps[layerX, :, :][count > 0] /= count[count > 0]" (:125-126)
+            nz = counts[k] > 0
+            heat[2 * k][nz] /= counts[k][nz]
+            heat[2 * k + 1][nz] /= counts[k][nz]
     heat *= np.asarray(mask, dtype=np.float64)  # :42
     if return_count:
         return heat, counts

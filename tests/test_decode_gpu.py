@@ -104,9 +104,9 @@ def test_mixed_batch_and_device_plan(rmpe, decode_golden):
     for a, b in zip(res, res2):
         assert np.array_equal(a["candidate"], b["candidate"]) and np.array_equal(a["subset"], b["subset"])
     # small workspace forces chunking frame by frame
-    need1 = max(int(rmpe.lib.load().rmpe_decode_workspace_bytes(1, rmpe.batch.make_frames([f])[0].ctypes.data, 128, 1024))
+    need1 = max(int(rmpe.lib.load().rmpe_decode_workspace_bytes(1, rmpe.batch.make_frames([f])[0].ctypes.data, 128, 1024, 8))
                 for f in frames)
-    need_all = int(rmpe.lib.load().rmpe_decode_workspace_bytes(len(frames), plan.desc_host.ctypes.data, 128, 1024))
+    need_all = int(rmpe.lib.load().rmpe_decode_workspace_bytes(len(frames), plan.desc_host.ctypes.data, 128, 1024, 8))
     plan3 = rmpe.batch.DecodeDevicePlan(frames, workspace_bytes=min(need_all, need1 + (4 << 20)))
     plan3.run()
     for a, b in zip(res, plan3.results()):
@@ -125,6 +125,153 @@ def test_empty_and_capacity(rmpe):
     assert r["status"] & 0x2
     with pytest.raises(OverflowError):
         rmpe.decode._raise_status(r["status"])
+
+
+def _check_against_oracle(r, o):
+    assert r["status"] == 0
+    assert np.array_equal(r["candidate"], o["candidate"]), "peaks"
+    assert r["special_k"] == o["special_k"]
+    for k in range(19):
+        oc = np.array(o["limb_candidates"][k], dtype=np.float64).reshape(-1, 4)
+        assert np.array_equal(r["limb_candidates"][k], oc), "limb %d candidates" % k
+        if k not in o["special_k"]:
+            assert np.array_equal(r["connections"][k], np.asarray(o["connection_all"][k]).reshape(-1, 5)), "limb %d" % k
+    assert np.array_equal(r["subset"], o["subset"]), "persons"
+
+
+@pytest.mark.parametrize("thre1,thre2", [(0.05, 0.05), (0.2, 0.05), (0.1, 0.01), (0.1, 0.1), (0.3, 0.2)])
+@pytest.mark.parametrize("case", [DECODE_CASES[2], DECODE_CASES[3]], ids=["d2", "d3"])
+def test_decode_thresholds(rmpe, case, thre1, thre2):
+    """params['thre1'] / ['thre2'] other than the defaults: the screening bound of k_screen_plan and the exact test of
+    k_peak_verify both depend on thre1, the limb criterion on thre2 (eval...:101-111, :150-157)."""
+    name, H, W, P, seed, multi = case
+    blobs = decode_case_inputs(case)
+    o = do.single_scale(blobs[0][0], blobs[0][1], H, W, thre1=thre1, thre2=thre2, detail=True)
+    r = rmpe.batch.decode_batch_host([frames_of(case)], thre1=thre1, thre2=thre2, want_limb_candidates=True)[0]
+    _check_against_oracle(r, o)
+    if thre1 == 0.05:
+        assert len(o["candidate"]) > len(do.single_scale(blobs[0][0], blobs[0][1], H, W)[0])   # the threshold matters here
+
+
+def _multi_frame(rmpe, seed, H, W, P, scale_search):
+    S = rmpe.synth
+    _, _, persons = S.decode_blobs(seed, (H, W), (4, 4), P)
+    sc = []
+    for (Hs, Ws, pd, pr, hs, ws) in do.multi_scale_feed_shapes(H, W, scale_search):
+        paf, heat, _ = S.decode_blobs(seed + 1000 * len(sc), (H, W), (hs, ws), P, persons=persons, stride=8.0 * H / Hs)
+        sc.append((paf, heat, pd, pr))
+    return sc
+
+
+@pytest.mark.parametrize("scale_search,thre1", [((0.5, 1), 0.1), ((0.5, 1, 1.5), 0.1), ((1, 2, 1.5), 0.1), ((1, 1.5), 0.2),
+                                                 ((0.5, 1, 1.5, 2), 0.05)])
+def test_decode_two_and_three_scales(rmpe, scale_search, thre1):
+    """process_multi_scale with params['scale_search'] of 2 or 3 entries (RmpeFrameDesc.n_scales 2..4): the average
+    divides by len(multiplier) (eval...:91-92)."""
+    H, W = 200, 264
+    sc = _multi_frame(rmpe, 31, H, W, 2, scale_search)
+    o = do.multi_scale(sc, H, W, thre1=thre1, detail=True)
+    r = rmpe.batch.decode_batch_host([dict(H=H, W=W, scales=sc)], thre1=thre1, want_limb_candidates=True)[0]
+    _check_against_oracle(r, o)
+    assert len(o["subset"]) >= 1
+
+
+@pytest.mark.parametrize("multi", [False, True], ids=["single", "multi"])
+def test_dense_blobs_nothing_culled(rmpe, multi):
+    """Worst case of the screening: every (tile, part) pair is active, every part holds ~35 peaks, a saturated
+    plateau sits in the middle -- the lists must still be the reference's, element by element."""
+    H, W = 96, 120
+    rng = np.random.RandomState(5)
+
+    def blob(h, w):
+        heat = (0.3 + 0.15 * rng.normal(size=(h, w, 19))).astype(np.float32)
+        heat[h // 4:h // 2 + 1, w // 4:w // 2 + 2, :] = 0.75      # exact plateau in the blob
+        return (0.3 * rng.normal(size=(h, w, 38))).astype(np.float32), heat
+
+    if not multi:
+        paf, heat = blob(12, 15)
+        sc = [(paf, heat, 0, 0)]
+        o = do.single_scale(paf, heat, H, W, detail=True)
+    else:
+        sc = []
+        for (Hs, Ws, pd, pr, hs, ws) in do.multi_scale_feed_shapes(H, W, (0.5, 1)):
+            paf, heat = blob(hs, ws)
+            sc.append((paf, heat, pd, pr))
+        o = do.multi_scale(sc, H, W, detail=True)
+    assert min(len(p) for p in o["all_peaks"]) >= 5 and not o["overflow"]
+    r = rmpe.batch.decode_batch_host([dict(H=H, W=W, scales=sc)], max_peaks=256, max_cand=4096, max_persons=128,
+                                     want_limb_candidates=True)[0]
+    _check_against_oracle(r, o)
+
+
+def test_found_more_than_two_rows_raises_like_the_reference(rmpe):
+    """eval...:192-195: a connection whose A peak and B peak sit in three subset rows makes the reference index
+    subset_idx[2] -> IndexError.  Lists made by k_limbs are one-to-one and cannot get there, so the assembly kernel is fed
+    crafted lists: limb 14 (Reye->Rear) hands ONE ear to two persons, limb 17 (Rsho->Rear) then finds three rows."""
+    import torch
+    L = rmpe.lib
+    lib = L.load()
+    MP, MS = 8, 16
+    dev = torch.device("cuda", 0)
+    n_peaks = np.zeros(18, np.int32)
+    cand = np.zeros((18 * MP, 4))
+    conn = np.zeros((19, MP, 5))
+    n_conn = np.full(19, -1, np.int32)
+    # peaks: necks 0,1,2 | Rshos 3,4,5 | noses 6,7 | Reyes 8,9 | Rear 10   (ids consecutive over parts 0..17)
+    counts = {0: 2, 1: 3, 2: 3, 14: 2, 16: 1}
+    ids, nxt = {}, 0
+    for part in range(18):
+        n_peaks[part] = counts.get(part, 0)
+        ids[part] = list(range(nxt, nxt + n_peaks[part]))
+        for i in ids[part]:
+            cand[i] = [10 * i, 5 * i, 0.9, i]
+        nxt += n_peaks[part]
+
+    def put(k, rows):
+        n_conn[k] = len(rows)
+        for i, (a, b) in enumerate(rows):
+            conn[k, i] = [a, b, 0.8, 0, 0]
+
+    put(0, [(ids[1][0], ids[2][0]), (ids[1][1], ids[2][1]), (ids[1][2], ids[2][2])])   # neck -> Rsho: three persons
+    put(12, [(ids[1][0], ids[0][0]), (ids[1][1], ids[0][1])])                          # neck -> nose
+    put(13, [(ids[0][0], ids[14][0]), (ids[0][1], ids[14][1])])                        # nose -> Reye
+    # Reye -> Rear: the same ear twice.  Person 2 takes it first; person 1's connection then finds two rows (its own through
+    # the eye, person 2's through the ear), they overlap, so the FIRST row (person 1) gets the ear as well: one ear, two rows
+    put(14, [(ids[14][1], ids[16][0]), (ids[14][0], ids[16][0])])
+    put(17, [(ids[2][2], ids[16][0])])                                                 # Rsho of person 3 -> that ear
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_cand, d_conn, d_nc, d_np = t(cand), t(conn), t(n_conn), t(n_peaks)
+    sub = torch.zeros((MS, 20), dtype=torch.float64, device=dev)
+    nsub = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    L.check(lib.rmpe_debug_assemble(MP, MS, d_cand.data_ptr(), d_conn.data_ptr(), d_nc.data_ptr(), d_np.data_ptr(),
+                                    sub.data_ptr(), nsub.data_ptr(), st.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert int(st.item()) & L.ST_FOUND_GT2
+    with pytest.raises(IndexError):
+        rmpe.decode._raise_status(int(st.item()))
+    # the oracle's restatement of the same loop flags the same connection (and keeps the first two rows, like the kernel)
+    all_peaks = [[tuple(cand[i]) for i in ids[p]] for p in range(18)]
+    special = [k for k in range(19) if n_conn[k] < 0]
+    conn_all = [conn[k, :max(n_conn[k], 0)] for k in range(19)]
+    _, osub, overflow = do.assemble(all_peaks, conn_all, special)
+    assert overflow
+    assert np.array_equal(sub.cpu().numpy()[:int(nsub.item())], osub)
+    # without the duplicated ear nothing is flagged
+    put(14, [(ids[14][0], ids[16][0])])
+    L.check(lib.rmpe_debug_assemble(MP, MS, d_cand.data_ptr(), t(conn).data_ptr(), t(n_conn).data_ptr(), d_np.data_ptr(),
+                                    sub.data_ptr(), nsub.data_ptr(), st.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert int(st.item()) == 0
+
+
+def test_host_wrapper_rejects_descriptors_beyond_the_blobs(rmpe):
+    paf = np.zeros((12, 15, 38), np.float32)
+    heat = np.zeros((12, 15, 19), np.float32)
+    desc, hflat, pflat = rmpe.batch.make_frames([dict(H=96, W=120, scales=[(paf, heat, 0, 0)])])
+    desc[0]["heat_offset"][0] = 19       # one cell too far
+    with pytest.raises(rmpe.lib.RmpeError):
+        rmpe.batch.decode_batch_host_raw(desc, hflat, pflat)
 
 
 def test_process_single_and_multi_scale_drop_in(rmpe, decode_golden):
@@ -280,3 +427,21 @@ def test_full_size_decode_batch_properties(rmpe):
         f = frames[i]["scales"][0]
         cand, sub = do.single_scale(f[0], f[1], H, W)
         assert np.array_equal(res[i]["candidate"], cand) and np.array_equal(res[i]["subset"], sub)
+
+
+@pytest.mark.parametrize("backend", ["nccl", "gloo"])
+def test_decode_records_gather_across_ranks(rmpe, backend):
+    """The result tail of compute_keypoints (eval...:497-548) over ranks: frames i % world == rank are decoded on the rank's
+    GPU, turned into COCO keypoint records and gathered (all_gather_object).  NCCL with one rank per GPU when the box has
+    two GPUs (else a one-rank NCCL group); gloo with two ranks sharing GPU 0."""
+    import subprocess
+    import sys
+    import torch
+    n = min(2, torch.cuda.device_count()) if backend == "nccl" else 2
+    env = dict(os.environ, RMPE_TEST_BACKEND=backend)
+    port = 29600 + (os.getpid() % 300) + (0 if backend == "nccl" else 1)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(os.path.dirname(os.path.abspath(__file__)), "_gather_worker.py")]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "GATHER_OK" in out.stdout

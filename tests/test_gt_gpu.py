@@ -33,6 +33,8 @@ def test_gt_matches_reference_golden(rmpe, gt_golden, case, simple):
     assert sha(r["mask"][0]) == str(gt_golden[name + "_mask_sha"])
     if s["joints"].shape[0]:
         assert np.array_equal(r["joints"][0], gt_golden[name + "_joints"])
+    # 9 of the 12 golden cases store only the 57 plane sums of the reference's labels (a coarse check); what pins their
+    # values element by element is test_gt_matches_oracle below (oracle == reference: tests/test_oracle_pin.py)
     assert np.abs(r["labels"][0].sum(axis=(1, 2)) - gt_golden[name + "_labels_sum"]).max() < 1e-2
     if name in FULL_LABEL_CASES:
         assert np.abs(r["labels"][0] - gt_golden[name + "_labels_f32"].astype(np.float64)).max() <= LABEL_TOL + 1e-7
@@ -202,6 +204,129 @@ def test_crowded_20_persons(rmpe):
     assert np.abs(r["labels"][0] - olab).max() <= LABEL_TOL
 
 
+@pytest.mark.parametrize("P", [5, 12, 20, 33, 64])
+@pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
+def test_crowded_rasteriser_person_counts(rmpe, P, f64):
+    """k_raster_roles over its regimes: all 18 parts' tables resident (P <= 24), batched parts (33, 64 persons)."""
+    s = rmpe.synth.gt_sample(500 + P, P)
+    M, r = _run_case(rmpe, s, f64=f64)
+    _, omask, oj = go.transform(s["img"], s["mask"], s["joints"], M, s["aug"][0])
+    olab, ocnt = go.create_heatmaps(oj, omask, return_count=True)
+    assert r["status"][0] == 0
+    assert np.array_equal(r["count"][0], ocnt)
+    assert np.array_equal(r["joints"][0], oj)
+    assert np.abs(r["labels"][0] - olab).max() <= LABEL_TOL + (0 if f64 else 1e-7)
+
+
+@pytest.mark.parametrize("sigma,thre", [(5., 8.), (7., 6.5), (9.5, 12.), (3., 4.)])
+def test_heatmapper_sigma_thre(rmpe, sigma, thre):
+    """Heatmapper(sigma, thre) (py_rmpe_heatmapper.py:10-14) with non-default values: a non-power-of-two thre takes the
+    division in the band test, a power-of-two one the exact product form."""
+    s = rmpe.synth.gt_sample(61, 3, augment=False)
+    mask = np.ones((46, 46))
+    lab, cnt = rmpe.heatmapper.Heatmapper(sigma, thre).create_heatmaps(s["joints"], mask, return_count=True)
+    olab, ocnt = go.create_heatmaps(s["joints"], mask, sigma, thre, return_count=True)
+    assert np.array_equal(cnt, ocnt)
+    assert np.abs(lab - olab).max() <= LABEL_TOL
+    # tie-prone integer joints at this thre
+    rng = np.random.RandomState(9)
+    j = np.zeros((5, 18, 3))
+    j[..., 0] = rng.randint(0, 46, size=(5, 18)) * 8
+    j[..., 1] = rng.randint(0, 46, size=(5, 18)) * 8
+    lab, cnt = rmpe.heatmapper.Heatmapper(sigma, thre).create_heatmaps(j, mask, return_count=True)
+    olab, ocnt = go.create_heatmaps(j, mask, sigma, thre, return_count=True)
+    assert np.array_equal(cnt, ocnt) and np.abs(lab - olab).max() <= LABEL_TOL
+
+
+def test_paf_average_variant(rmpe):
+    """Non-default flag: the averaging the reference keeps commented out (py_rmpe_heatmapper.py:119-126)."""
+    s = rmpe.synth.gt_sample(77, 20, augment=False)
+    s["joints"][:, :, :2] += np.random.RandomState(1).normal(0, 15, size=(20, 18, 2))   # limbs of different directions
+    mask = np.ones((46, 46))
+    lab, cnt = rmpe.heatmapper.Heatmapper().create_heatmaps(s["joints"], mask, return_count=True, paf_average=True)
+    olab, ocnt = go.create_heatmaps(s["joints"], mask, return_count=True, paf_average=True)
+    assert (ocnt > 1).any()                     # crowded enough for bands to overlap
+    assert np.array_equal(cnt, ocnt) and np.abs(lab - olab).max() <= LABEL_TOL
+    ref = go.create_heatmaps(s["joints"], mask)
+    assert np.abs(ref - olab).max() > 1e-3      # and it is a different result from the reference's overwrite
+
+
+@pytest.mark.parametrize("P,f64", [(3, False), (3, True), (20, False), (20, True), (30, False)])
+def test_keras_tensors_from_the_rasteriser(rmpe, P, f64):
+    """RMPE NHWC outputs (training/ds_generators.py:52-63) written by the rasteriser itself == the planar labels
+    re-laid-out by the oracle; P = 30 takes the two-pass route (tables of 30 persons + a band do not fit one CTA)."""
+    b = rmpe.synth.gt_batch(3, n_persons=P, seed0=810)
+    flip = np.array([a[0] for a in b["augs"]], np.uint8)
+    M = rmpe.batch.aug_affine(flip, [a[1] for a in b["augs"]], [a[2] for a in b["augs"]], [a[3] for a in b["augs"]],
+                              b["centers"], b["scale_self"])
+    r = rmpe.batch.gt_batch_host(b["imgs"], b["masks"], b["joints"], b["n_persons"], M, flip, f64=f64, keras=True,
+                                 want_count=True)
+    r2 = rmpe.batch.gt_batch_host(b["imgs"], b["masks"], b["joints"], b["n_persons"], M, flip, f64=f64, keras=True,
+                                  want_labels=(P > 24), keras_weights=False)
+    ft = np.float64 if f64 else np.float32
+    for i in range(3):
+        _, omask, oj = go.transform(b["imgs"][i], b["masks"][i], b["joints"][i], M[i], bool(flip[i]))
+        olab, ocnt = go.create_heatmaps(oj, omask, return_count=True)
+        assert np.array_equal(r["count"][i], ocnt)
+        assert np.abs(r["labels"][i] - olab).max() <= LABEL_TOL + (0 if f64 else 1e-7)
+    x1, x2, y1, y2 = go.keras_batch(r["labels"], r["mask"])       # the same values, NHWC
+    for k, want in (("x1", x1), ("x2", x2), ("y1", y1), ("y2", y2)):
+        assert r[k].dtype == ft and np.array_equal(r[k], want), k
+    assert np.array_equal(r2["y1"], y1) and np.array_equal(r2["y2"], y2) and r2["x1"] is None
+
+
+def test_n_persons_beyond_the_person_stride_is_clamped_and_flagged(rmpe):
+    """Device entry: n_persons is caller data; a count above max_persons must not read the next sample's joints."""
+    import ctypes as C
+    import torch
+    L = rmpe.lib
+    plan = rmpe.batch.GtDevicePlan(2, 3)
+    b = rmpe.synth.gt_batch(2, n_persons=3, seed0=40)
+    flip = np.array([a[0] for a in b["augs"]], np.uint8)
+    M = rmpe.batch.aug_affine(flip, [a[1] for a in b["augs"]], [a[2] for a in b["augs"]], [a[3] for a in b["augs"]],
+                              b["centers"], b["scale_self"])
+    plan.upload(b["imgs"], b["masks"], b["joints"], np.array([7, -2], np.int32), M, flip)
+    plan.run()
+    torch.cuda.synchronize()
+    st = plan.status.cpu().numpy()
+    assert (st & L.ST_PERSONS_CLAMPED).all()
+    lab = plan.out_labels.cpu().numpy()
+    for i, n in enumerate((3, 0)):
+        _, omask, oj = go.transform(b["imgs"][i], b["masks"][i], b["joints"][i][:n], M[i], bool(flip[i]))
+        assert np.abs(lab[i] - go.create_heatmaps(oj, omask)).max() <= LABEL_TOL + 1e-7
+    # host entry: the same mistake is an argument error
+    with pytest.raises(L.RmpeError):
+        rmpe.batch.gt_batch_host(b["imgs"], b["masks"], b["joints"], [4, 1], M, flip)
+
+
+def test_host_calls_from_threads_do_not_serialise_or_mix(rmpe):
+    """Keras worker threads (ds_generators.py:209 under fit_generator): every thread has its own arena and streams."""
+    import threading
+    b = rmpe.synth.gt_batch(6, n_persons=2, seed0=70)
+    flip = np.array([a[0] for a in b["augs"]], np.uint8)
+    M = rmpe.batch.aug_affine(flip, [a[1] for a in b["augs"]], [a[2] for a in b["augs"]], [a[3] for a in b["augs"]],
+                              b["centers"], b["scale_self"])
+    want = rmpe.batch.gt_batch_host(b["imgs"], b["masks"], b["joints"], b["n_persons"], M, flip)
+    got, errs = {}, []
+
+    def work(t):
+        try:
+            for _ in range(5):
+                sl = slice(t, t + 3)
+                got[t] = rmpe.batch.gt_batch_host(b["imgs"][sl], b["masks"][sl], b["joints"][sl], b["n_persons"][sl],
+                                                  M[sl], flip[sl])
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for t in range(4):
+        for k in ("img", "mask", "labels", "joints"):
+            assert np.array_equal(got[t][k], want[k][t:t + 3]), (t, k)
+
+
 @pytest.mark.parametrize("seed", range(10))
 def test_random_geometry_sweep(rmpe, seed):
     """Fused warp+mask kernel against the oracle over odd source sizes (unaligned row pitches),
@@ -260,7 +385,7 @@ def test_fused_data_iterator_batches(rmpe):
         assert np.array_equal(x1[i], np.repeat(omask[:, :, None], 38, axis=2))
         assert np.abs(ys[0][i] - np.transpose(olab[:38], (1, 2, 0))).max() <= LABEL_TOL
         assert np.abs(ys[1][i] - np.transpose(olab[38:], (1, 2, 0))).max() <= LABEL_TOL
-        assert np.array_equal(it.keypoints[i], oj) or True
+        assert np.array_equal(it.keypoints[i], oj)          # transformed joints handed to the accuracy code
 
 
 class _FakeEntry:

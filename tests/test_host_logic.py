@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for name in sorted(declared):
         assert hasattr(lib, name), "missing export: " + name
     assert set(built_lib.lib.EXPORTS) <= declared
-    assert lib.rmpe_abi_version() == 1
+    assert lib.rmpe_abi_version() == 2
     assert lib.rmpe_device() == -1 or lib.rmpe_device() >= 0
 
 
@@ -29,8 +29,8 @@ def test_struct_layouts_match_header(built_lib):
     assert ctypes.sizeof(L.FrameDesc) == 144
     assert L.FRAME_DESC_DTYPE.itemsize == 144 and L.SRC_DESC_DTYPE.itemsize == 32
     # 6 int32 + 12 pointers
-    assert ctypes.sizeof(L.GtBatchHost) == 6 * 4 + 12 * 8
-    assert ctypes.sizeof(L.GtBatch) == 4 * 4 + 13 * 8
+    assert ctypes.sizeof(L.GtBatchHost) == 6 * 4 + 18 * 8
+    assert ctypes.sizeof(L.GtBatch) == 4 * 4 + 19 * 8
 
 
 def test_no_gpu_fails_loudly(built_lib):

@@ -183,3 +183,26 @@ def test_keras_batch_oracle_vs_reference_ds_generators():
     assert np.array_equal(x, np.transpose(imgs, (0, 2, 3, 1)))
     assert np.array_equal(x1, ox1) and np.array_equal(x2, ox2)
     assert np.array_equal(ys[0], oy1) and np.array_equal(ys[1], oy2) and len(ys) == 4
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not mounted (GPU box)")
+def test_draw_canvas_equals_the_references_drawing_tail(tmp_path):
+    """D7 (eval...:417-441) stays on cv2 and is outside the GPU path; the drop-in's own implementation must still paint the
+    same pixels.  The reference is run end to end on a synthetic frame; its (candidate, subset) feed draw_canvas."""
+    import cv2
+    import rmpe_b200
+    ref = ref_shim.load().eval
+    H, W = 240, 320
+    h, w = rmpe_b200.synth.single_scale_grid(H, W)
+    paf, heat, _ = rmpe_b200.synth.decode_blobs(3, (H, W), (h, w), 2)
+    img = np.random.RandomState(0).randint(0, 256, (H, W, 3)).astype(np.uint8)
+    path = str(tmp_path / "frame.png")
+    cv2.imwrite(path, img)
+    params = {'scale_search': [.5, 1, 1.5, 2], 'thre1': .1, 'thre2': .05}
+    mparams = {'boxsize': 368, 'stride': 8, 'padValue': 128}
+    canvas, cand, sub = ref.process_single_scale(path, ref_shim.FakeModel(lambda hh, ww, call: (paf, heat)), params, mparams)
+    assert len(sub) >= 1
+    o = do.single_scale(paf, heat, H, W, detail=True)
+    n_peaks = np.array([len(p) for p in o["all_peaks"]])
+    got = rmpe_b200.decode.draw_canvas(cv2.imread(path), cand, sub, n_peaks)
+    assert np.array_equal(got, canvas)
