@@ -331,6 +331,65 @@ def decode_batch_host_raw(desc, heat, paf, thre1=0.1, thre2=0.05, stride=8, max_
     return _unpack_decode(B, MP, MC, MS, cand, npk, conn, nconn, lc, nlc, sub, nsub, status)
 
 
+class DecodeHostPlan:
+    """rmpe_decode_batch_host over a fixed list of frames with every host buffer allocated once (pinned when torch is
+    importable): what a serving loop that re-uses its buffers calls, and what bench.py's decode `e2e` times.
+    `run()` = one C call: blobs host->device, the whole decode pipeline, the filled prefix of every table device->host."""
+
+    def __init__(self, frames, thre1=0.1, thre2=0.05, stride=8, max_peaks=128, max_cand=1024, max_persons=64, pinned=True):
+        self.lib = L.ensure_init()
+        desc, heat, paf = make_frames(frames)
+        B = self.B = len(desc)
+        self.MP, self.MC, self.MS = max_peaks, max_cand, max_persons
+        self._keep = []
+
+        def alloc(shape, dtype):
+            if pinned:
+                import torch
+                t = torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+                self._keep.append(t)
+                return t.numpy()
+            return np.empty(shape, dtype)
+
+        self.heat, self.paf = alloc(heat.shape, np.float32), alloc(paf.shape, np.float32)
+        self.heat[...] = heat
+        self.paf[...] = paf
+        self.desc = desc
+        self.cand = alloc((B, 18 * max_peaks, 4), np.float64)
+        self.npk = alloc((B, 18), np.int32)
+        self.conn = alloc((B, 19, max_peaks, 5), np.float64)
+        self.nconn = alloc((B, 19), np.int32)
+        self.nlc = alloc((B, 19), np.int32)
+        self.sub = alloc((B, max_persons, 20), np.float64)
+        self.nsub = alloc((B,), np.int32)
+        self.status = alloc((B,), np.int32)
+        h = L.DecodeBatchHost()
+        h.batch, h.max_peaks, h.max_cand, h.max_persons, h.stride, h.flags = B, max_peaks, max_cand, max_persons, stride, 0
+        h.thre1, h.thre2 = float(thre1), float(thre2)
+        h.heat, h.paf, h.heat_elems, h.paf_elems = L.ptr(self.heat), L.ptr(self.paf), heat.size, paf.size
+        h.frames = L.ptr(desc)
+        h.candidate, h.n_peaks, h.connections, h.n_conn = L.ptr(self.cand), L.ptr(self.npk), L.ptr(self.conn), L.ptr(self.nconn)
+        h.limb_cand, h.n_limb_cand = None, L.ptr(self.nlc)
+        h.subset, h.n_subset, h.status = L.ptr(self.sub), L.ptr(self.nsub), L.ptr(self.status)
+        self.h = h
+        self.h2d_bytes = int(heat.nbytes + paf.nbytes + desc.nbytes)
+
+    def run(self):
+        L.check(self.lib.rmpe_decode_batch_host(C.byref(self.h)))
+
+    def d2h_bytes(self):
+        """Bytes the last run() brought back: the count vectors and the filled prefix of every table (rmpe_host.cu)."""
+        B, MP, MS = self.B, self.MP, self.MS
+        rows = int(np.minimum(self.npk, MP).sum(axis=1).max()) if B else 0
+        mconn = int(np.clip(self.nconn, 0, MP).max()) if B else 0
+        msub = int(np.minimum(self.nsub, MS).max()) if B else 0
+        return int(B * (18 + 19 + 1 + 1) * 4 + B * rows * 32 + B * 19 * mconn * 40 + B * msub * 160)
+
+    def results(self):
+        return _unpack_decode(self.B, self.MP, self.MC, self.MS, self.cand, self.npk, self.conn, self.nconn, None,
+                              self.nlc, self.sub, self.nsub, self.status)
+
+
 class DecodeDevicePlan:
     """Device-resident decode of a fixed list of frames: blobs live in HBM, `run()` enqueues the
     whole pipeline on the current torch stream, `results()` reads back and unpacks."""

@@ -1456,7 +1456,7 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
             static std::once_flag roles_attr;
             static cudaError_t roles_attr_rc = cudaSuccess;
             std::call_once(roles_attr, [] {
-                const int mx = kMaxSmemOptin;
+                const int mx = 220 * 1024;      // = cap: the kernel also has a few bytes of static shared memory
                 cudaError_t e = cudaFuncSetAttribute(k_raster_roles<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(k_raster_roles<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(k_raster_roles<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
