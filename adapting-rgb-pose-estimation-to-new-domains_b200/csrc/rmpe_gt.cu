@@ -698,6 +698,7 @@ struct RasterArgs {
     int part_batch;            // parts whose exp tables are resident at once (18: one pass)
     int band_px;               // NHWC: pixels staged per pass (544, 272 or 136)
     int paf_average;           // RMPE_GT_PAF_AVERAGE
+    int batch;                 // k_raster_blocks: samples of the launch (1-D grid)
 };
 
 struct LimbRec {
@@ -791,33 +792,40 @@ __device__ __forceinline__ void raster_exp_entry(const double *j, int cidx, floa
 }
 
 // ---- H4 record of one (limb, person) (py_rmpe_heatmapper.py:69-114); returns true for a zero-length limb ----
-__device__ __forceinline__ bool raster_limb_rec(const double *jf, const double *jt, double thre, LimbRec &r) {
+// [row_lo, row_hi): the grid rows the calling CTA rasterises; a record whose box misses them is left empty and skips the
+// square root and the divisions (the zero-length test needs neither: sqrt(s) == 0 <=> s == 0)
+__device__ __forceinline__ bool raster_limb_rec(const double *jf, const double *jt, double thre, LimbRec &r,
+                                                int row_lo = 0, int row_hi = kGrid) {
     bool zero = false;
     r.minx = r.maxx = r.miny = r.maxy = 0;
     r.x1 = jf[0]; r.y1 = jf[1];
     const double x2 = jt[0], y2 = jt[1];
     r.xD = __dsub_rn(x2, r.x1); r.yD = __dsub_rn(y2, r.y1);
-    // distances(): sqrt(xD**2 + yD**2); put_vector_maps: sqrt(dx*dx + dy*dy) -- same value
-    r.norm2 = __dsqrt_rn(__dadd_rn(__dmul_rn(r.xD, r.xD), __dmul_rn(r.yD, r.yD)));
+    const double n2 = __dadd_rn(__dmul_rn(r.xD, r.xD), __dmul_rn(r.yD, r.yD));
+    r.norm2 = 0.0;
     r.ux = r.uy = 0.f;
     r.tn = r.en = 0.0;
     if (jf[2] < 2.0 && jt[2] < 2.0) {
-        if (r.norm2 == 0.0) {
+        if (n2 == 0.0) {
             zero = true;
         } else {
-            r.ux = (float)__ddiv_rn(r.xD, r.norm2);
-            r.uy = (float)__ddiv_rn(r.yD, r.norm2);
-            band_prepare(r, thre);
             const double mnx = r.x1 < x2 ? r.x1 : x2, mxx = r.x1 < x2 ? x2 : r.x1;
             const double mny = r.y1 < y2 ? r.y1 : y2, mxy = r.y1 < y2 ? y2 : r.y1;
-            const int a0 = py_round(__ddiv_rn(__dsub_rn(mnx, thre), 8.0));
-            const int b0 = py_round(__ddiv_rn(__dsub_rn(mny, thre), 8.0));
-            const int a1 = py_round(__ddiv_rn(__dadd_rn(mxx, thre), 8.0));
-            const int b1 = py_round(__ddiv_rn(__dadd_rn(mxy, thre), 8.0));
+            // round((v -+ thre) / 8): the division by the stride is an exact scaling, written as a multiplication
+            const int a0 = py_round(__dmul_rn(__dsub_rn(mnx, thre), 0.125));
+            const int b0 = py_round(__dmul_rn(__dsub_rn(mny, thre), 0.125));
+            const int a1 = py_round(__dmul_rn(__dadd_rn(mxx, thre), 0.125));
+            const int b1 = py_round(__dmul_rn(__dadd_rn(mxy, thre), 0.125));
             if (a1 >= 0 && b1 >= 0) {
-                r.minx = max(a0, 0); r.miny = max(b0, 0);
-                r.maxx = min(a1, kGrid); r.maxy = min(b1, kGrid);
-                if (r.maxy <= r.miny) r.maxx = r.minx;  // empty slice
+                const int minx = max(a0, 0), miny = max(b0, 0), maxx = min(a1, kGrid), maxy = min(b1, kGrid);
+                if (maxx > minx && maxy > miny && miny < row_hi && maxy > row_lo) {
+                    r.minx = minx; r.miny = miny; r.maxx = maxx; r.maxy = maxy;
+                    // distances(): sqrt(xD**2 + yD**2); put_vector_maps: sqrt(dx*dx + dy*dy) -- same value
+                    r.norm2 = __dsqrt_rn(n2);
+                    r.ux = (float)__ddiv_rn(r.xD, r.norm2);
+                    r.uy = (float)__ddiv_rn(r.yD, r.norm2);
+                    band_prepare(r, thre);
+                }
             }
         }
     }
@@ -1207,6 +1215,245 @@ __global__ void __launch_bounds__(kRrThreads) k_raster_roles(RasterArgs a) {
 }
 
 // ==========================================================================================
+// k_raster_blocks: crowded scenes (5..64 persons per sample), planar labels.
+// grid = (8, batch), 704 threads.  Crowded batches are small (64 samples per GPU in BASELINE configs[4]), so a sample is cut
+// into eight CTAs that give every SM warps to switch between: with one thread per 4-cell run and one CTA per (sample, role)
+// the slowest CTA's serial instruction stream set the kernel time (83 us per 64 samples at 20 persons).
+//   CTAs 0-3, heat: one quarter of the grid each (24 x 24 cells = 6 x 6 BLOCKS of 4x4 cells); a thread owns ONE (block,
+//     part) item.  max_p exp(-d_p^2 / 2 sigma^2) = exp(-min_p d_p^2 / 2 sigma^2) (exp is monotone, so this IS the
+//     reference's max merge, py_rmpe_heatmapper.py:59-62): the person loop is a min over separable squared distances --
+//     per person two LDS.128 (dx^2 of the block's 4 columns, dy^2 of its 4 rows) feed 16 FADD and, two persons at a time,
+//     16 three-input FMNMX -- and expf runs once per (part, cell) instead of twice per (part, person, column | row).  The
+//     tables hold no expf, so every tile builds its own (24 columns + 24 rows per part and person).  The background needs
+//     the max over all 18 parts: the part threads of a block meet through shared-memory atomicMax on the (non-negative)
+//     float bits.
+//   CTAs 4-7, limbs: five limbs each, whole grid.  SCATTER, then GATHER: a warp takes one (limb, person) record and walks its
+//     cell box in 4 x 8 patches, one cell per lane (dense: no lane waits for another lane's person); a cell inside the band
+//     sets bit p of the cell's 64-bit person mask in shared memory (atomicOr).  The reference overwrites in person order and
+//     counts hits (py_rmpe_heatmapper.py:116-126), so the winner of a cell is its HIGHEST set bit and the count the number
+//     of set bits.  The band test |dd| <= thre * norm is decided in float wherever the float value of the (linear) numerator
+//     is further from the limit than its rounding bound, and by the exact f64 test (band_on) otherwise.  The gather pass
+//     then writes the planes as coalesced 128-bit runs like k_raster_small.
+// ==========================================================================================
+constexpr int kRbTile = 6;                           // blocks per tile side (24 cells)
+constexpr int kRbBlocks = kRbTile * kRbTile;         // 36
+constexpr int kRbThreads = ((kRbBlocks * kLimbs + 31) / 32) * 32;    // 704
+constexpr int kRbTabW = 8 * kRbTile;                 // floats per (part, person): dx^2 of the tile's 24 columns, dy^2 of its 24 rows
+constexpr int kRbLimbsPerCta = 5;                    // 5 + 5 + 5 + 4
+
+static size_t raster_blocks_smem(int pm, int part_batch) {
+    const size_t sj = ((size_t)pm * kParts * 3 * 8 + 15) & ~(size_t)15;
+    const size_t heat = (size_t)part_batch * pm * kRbTabW * 4 + (size_t)kRbBlocks * 16 * 4;
+    const size_t limb = (size_t)kRbLimbsPerCta * pm * sizeof(LimbRec) + (size_t)kRbLimbsPerCta * kCells * 8;
+    return sj + std::max(heat, limb);
+}
+
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+#ifndef RMPE_RB_MINB
+#define RMPE_RB_MINB 2
+#endif
+template <typename T>
+__global__ void __launch_bounds__(kRbThreads, RMPE_RB_MINB) k_raster_blocks(RasterArgs a) {
+    // 1-D grid: the heat CTAs of all samples first, the (lighter) limb CTAs behind them fill the tail of the last wave
+    const int role = blockIdx.x >= 4 * a.batch ? 1 : 0;
+    const int id = blockIdx.x - role * 4 * a.batch;
+    const int b = id >> 2, sub = id & 3;
+    const int tid = threadIdx.x;
+    bool clamped;
+    const int P = raster_persons(a, b, kMaxPersonsGt, clamped);
+    const int PM = a.max_persons;
+    extern __shared__ __align__(16) uint8_t rb_smem[];
+    double *s_j = reinterpret_cast<double *>(rb_smem);                      // [PM][18][3]
+    uint8_t *rest = rb_smem + (((size_t)PM * kParts * 3 * 8 + 15) & ~(size_t)15);
+    __shared__ int s_zero;
+    if (tid == 0) s_zero = 0;
+    raster_joints(a, b, P, s_j, tid, kRbThreads);
+
+    if (role == 0) {
+        // ================= 18 Gaussian part maps + background: tile `sub` =================
+        const int tx0 = 24 * (sub & 1), ty0 = 24 * (sub >> 1);        // first cell column / row of the tile
+        const int slot = tid / kRbBlocks, blk = tid - slot * kRbBlocks;   // slot = part of this thread's item
+        const int by = blk / kRbTile, bx = blk - by * kRbTile;
+        const int x0 = tx0 + 4 * bx, y0 = ty0 + 4 * by;
+        // the block's cells: pairs (x0, x0+1), (x0+2, x0+3) of rows y0..y0+3; the last block column / row hangs over the grid
+        const bool pair1 = x0 + 2 < kGrid;
+        const int nrows = min(4, kGrid - y0);
+        const T *mk = reinterpret_cast<const T *>(a.mask) + (size_t)b * kCells + y0 * kGrid + x0;
+        T *lab = reinterpret_cast<T *>(a.labels) + (size_t)b * kLayers * kCells + y0 * kGrid + x0;
+        // v * mask of the block's cells -> plane (the mask comes through L1 every time: it would cost 16 registers to keep)
+        auto store_plane = [&](int plane, const float *v) {
+            T *o = lab + (size_t)plane * kCells;
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                if (r < nrows) {
+                    store_pair<T>(o + r * kGrid, (T)v[4 * r] * mk[r * kGrid], (T)v[4 * r + 1] * mk[r * kGrid + 1]);
+                    if (pair1) store_pair<T>(o + r * kGrid + 2, (T)v[4 * r + 2] * mk[r * kGrid + 2], (T)v[4 * r + 3] * mk[r * kGrid + 3]);
+                }
+        };
+        const int PB = a.part_batch;                                                 // parts resident at a time (18: one pass)
+        float *s_tab = reinterpret_cast<float *>(rest);                              // [PB][PM][kRbTabW]
+        int *s_bk = reinterpret_cast<int *>(s_tab + (size_t)PB * PM * kRbTabW);     // [16][36] float bits
+        for (int i = tid; i < kRbBlocks * 16; i += kRbThreads) s_bk[i] = 0;
+        const float inv2s2 = (float)(1.0 / (2.0 * a.sigma * a.sigma));
+        const float kInf = __int_as_float(0x7f800000);
+        __syncthreads();
+        for (int part0 = 0; part0 < kParts; part0 += PB) {
+            const int npb = min(PB, kParts - part0);
+            if (part0) __syncthreads();
+            // squared distances of the resident parts to the cell centres 8 i + 3.5 (py_rmpe_heatmapper.py:22-23, 51-57):
+            // f64 difference, rounded once to float, squared in float; +inf for a joint that is not there.  A thread
+            // fills one (part, column) of the table for every person.
+            for (int e = tid; e < npb * kRbTabW; e += kRbThreads) {
+                const int pl = e / kRbTabW, col = e - pl * kRbTabW;
+                const bool isx = col < 4 * kRbTile;
+                const double gpos = 8.0 * (isx ? tx0 + col : ty0 + col - 4 * kRbTile) + 3.5;
+                const double *j = s_j + (part0 + pl) * 3 + (isx ? 0 : 1);
+                float *t = s_tab + (size_t)pl * PM * kRbTabW + col;
+                for (int p = 0; p < P; p++, j += kParts * 3, t += kRbTabW) {
+                    const float d = (float)__dsub_rn(gpos, j[0]);
+                    *t = j[isx ? 2 : 1] < 2.0 ? d * d : kInf;
+                }
+            }
+            __syncthreads();
+            if (part0 == 0) {
+                // see k_raster_small: nothing above touches global memory that another kernel writes
+                pdl_wait();
+                if (sub == 0) {
+                    raster_joints_out(a, b, P, s_j, tid, kRbThreads);
+                    if (tid == 0 && clamped) atomicOr(a.status + b, RMPE_ST_PERSONS_CLAMPED);
+                }
+            }
+            if (slot < npb) {
+                float d2[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) d2[i] = kInf;
+                const float *tp = s_tab + (size_t)slot * PM * kRbTabW + 4 * bx;
+                const int yo = 4 * kRbTile + 4 * by - 4 * bx;
+                int p = 0;
+                for (; p + 1 < P; p += 2, tp += 2 * kRbTabW) {
+                    const float4 dxa = *reinterpret_cast<const float4 *>(tp), dya = *reinterpret_cast<const float4 *>(tp + yo);
+                    const float4 dxb = *reinterpret_cast<const float4 *>(tp + kRbTabW), dyb = *reinterpret_cast<const float4 *>(tp + kRbTabW + yo);
+                    const float xa[4] = {dxa.x, dxa.y, dxa.z, dxa.w}, ya[4] = {dya.x, dya.y, dya.z, dya.w};
+                    const float xb[4] = {dxb.x, dxb.y, dxb.z, dxb.w}, yb[4] = {dyb.x, dyb.y, dyb.z, dyb.w};
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+#pragma unroll
+                        for (int c = 0; c < 4; c++) d2[4 * r + c] = fmin3(d2[4 * r + c], xa[c] + ya[r], xb[c] + yb[r]);
+                }
+                if (p < P) {
+                    const float4 dxa = *reinterpret_cast<const float4 *>(tp), dya = *reinterpret_cast<const float4 *>(tp + yo);
+                    const float xa[4] = {dxa.x, dxa.y, dxa.z, dxa.w}, ya[4] = {dya.x, dya.y, dya.z, dya.w};
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+#pragma unroll
+                        for (int c = 0; c < 4; c++) d2[4 * r + c] = fminf(d2[4 * r + c], xa[c] + ya[r]);
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    d2[i] = expf(-d2[i] * inv2s2);
+                    // background = 1 - max over all 18 parts (py_rmpe_heatmapper.py:38): the part threads of a block meet here
+                    atomicMax(s_bk + i * kRbBlocks + blk, __float_as_int(d2[i]));
+                }
+                store_plane(38 + part0 + slot, d2);
+            }
+        }
+        __syncthreads();
+        if (slot == 0) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) v[i] = 1.f - __int_as_float(s_bk[i * kRbBlocks + blk]);
+            store_plane(56, v);
+        }
+        return;
+    }
+
+    // ================= part-affinity fields: limbs [k0, k0 + nl) =================
+    const int k0 = kRbLimbsPerCta * sub, nl = min(kRbLimbsPerCta, kLimbs - k0);
+    LimbRec *s_rec = reinterpret_cast<LimbRec *>(rest);                                                          // [nl][P]
+    unsigned long long *s_hit = reinterpret_cast<unsigned long long *>(s_rec + (size_t)kRbLimbsPerCta * PM);     // [nl][2116] person masks
+    for (int i = tid; i < nl * kCells; i += kRbThreads) s_hit[i] = 0ull;
+    __syncthreads();         // joints
+    const double thre = a.thre;
+    for (int i = tid; i < nl * P; i += kRbThreads) {
+        const int kl = i / P, p = i - kl * P;
+        LimbRec r;
+        if (raster_limb_rec(s_j + (p * kParts + c_limb_from[k0 + kl]) * 3, s_j + (p * kParts + c_limb_to[k0 + kl]) * 3, thre, r)) s_zero = 1;
+        s_rec[i] = r;
+    }
+    __syncthreads();
+    {
+        // ---- scatter: one warp per record, one cell per lane ----
+        const int warp = tid >> 5, lane = tid & 31;
+        const int lx = lane & 7, ly = lane >> 3;
+        for (int i = warp; i < nl * P; i += kRbThreads / 32) {
+            const LimbRec &r = s_rec[i];
+            const int4 box = *reinterpret_cast<const int4 *>(&r.minx);      // minx, maxx, miny, maxy
+            if (box.y <= box.x) continue;
+            const int kl = i / P, p = i - kl * P;
+            unsigned long long *hit = s_hit + (size_t)kl * kCells;
+            const unsigned long long bit = 1ull << p;
+            // numerator dd = xD (y1 - Y) - (x1 - X) yD at the cell corner (X, Y) = (8x, 8y), in float with its rounding bound
+            // E <= 2^-24 (|xD| |y1| + |yD| |x1| + 3 (|a| + |b|) + |dd|) <= 3e-5 (|xD| + |yD|) + 3e-7 (|a| + |b|) for Y, X <= 368
+            const float fxD = (float)r.xD, fyD = (float)r.yD, fx1 = (float)r.x1, fy1 = (float)r.y1;
+            const float tn_lo = (float)r.tn * 0.999999f, tn_hi = (float)r.tn * 1.000001f;
+            const float e0 = 0.5f + 3e-5f * (fabsf(fxD) + fabsf(fyD));
+            for (int px = box.x; px < box.y; px += 8) {
+                const int x = px + lx;
+                const float fb = (fx1 - (float)(8 * x)) * fyD;
+                for (int py = box.z; py < box.w; py += 4) {
+                    const int y = py + ly;
+                    if (x < box.y && y < box.w) {
+                        const float fa = fxD * (fy1 - (float)(8 * y));
+                        const float ad = fabsf(fa - fb);
+                        const float e = e0 + 1e-5f * (fabsf(fa) + fabsf(fb));
+                        bool in = ad < tn_lo - e;
+                        if (!in && !(ad > tn_hi + e)) in = band_on(r, raster_dd(r, x, y), thre);
+                        if (in) atomicOr(hit + y * kGrid + x, bit);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    pdl_wait();
+    if (sub == 0 && tid == 0 && s_zero) atomicOr(a.status + b, RMPE_ST_ZERO_LIMB);
+    // ---- gather: a thread owns float4 runs of cells; winner = highest person bit, count = number of bits ----
+    const T *mk = reinterpret_cast<const T *>(a.mask) + (size_t)b * kCells;
+    T *lab = reinterpret_cast<T *>(a.labels) + (size_t)b * kLayers * kCells;
+    for (int i = tid; i < nl * kCellVec; i += kRbThreads) {
+        const int kl = i / kCellVec, run = i - kl * kCellVec;
+        const int pix = 4 * run, k = k0 + kl;
+        const unsigned long long *h = s_hit + (size_t)kl * kCells + pix;
+        const ulonglong2 h01 = *reinterpret_cast<const ulonglong2 *>(h), h23 = *reinterpret_cast<const ulonglong2 *>(h + 2);
+        const unsigned long long hm[4] = {h01.x, h01.y, h23.x, h23.y};
+        T m[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) m[q] = mk[pix + q];
+        float vx[4], vy[4];
+        int cnt[4];
+        const LimbRec *rk = s_rec + kl * P;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            vx[q] = 0.f; vy[q] = 0.f;
+            cnt[q] = __popcll(hm[q]);
+            if (hm[q]) {
+                const LimbRec &w = rk[63 - __clzll((long long)hm[q])];
+                vx[q] = w.ux; vy[q] = w.uy;
+            }
+        }
+        store4<T>(lab + (size_t)(2 * k) * kCells + pix, vx[0], vx[1], vx[2], vx[3], m);
+        store4<T>(lab + (size_t)(2 * k + 1) * kCells + pix, vy[0], vy[1], vy[2], vy[3], m);
+        if (a.out_count)
+            *reinterpret_cast<int4 *>(a.out_count + ((size_t)b * kLimbs + k) * kCells + pix) = make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
+    }
+}
+
+// ==========================================================================================
 // k_keras_batch: DataIteratorBase.gen's per-sample transposes / repeats (training/ds_generators.py:47-63)
 // as one pass: a CTA takes two grid rows (92 pixels) of one sample, reads the 57 label planes as
 // coalesced row segments into shared memory and writes the four NHWC tensors as contiguous runs.
@@ -1400,7 +1647,8 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
         const int pm = b->max_persons;
         const size_t esz = ra.f64 ? 8 : 4;
         bool two_pass = false;       // NHWC for more persons than the one-pass kernel holds tables for
-        if (!nhwc && pm <= kRsMaxP && !simple && !ra.paf_average) {
+        static const int small_off = [] { const char *e = getenv("RMPE_RASTER_SMALL"); return (e && atoi(e) == 0) ? 1 : 0; }();   // A/B: k_raster_blocks for every person count
+        if (!nhwc && pm <= kRsMaxP && !ra.paf_average && !small_off) {       // RMPE_GT_SIMPLE_KERNELS selects the warp kernels only
             static const int groups = [] {
                 const char *e = getenv("RMPE_RASTER_GROUPS");
                 int v = e ? atoi(e) : kRsGroups;
@@ -1452,6 +1700,36 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
                 ra.part_batch = pb;
                 smem = sj + std::max(per_part * pb, recs);
                 ra.y1 = ra.y2 = ra.x1 = ra.x2 = nullptr;
+            }
+            static const int crowd_blocks = [] {
+                const char *e = getenv("RMPE_RASTER_CROWD");      // "roles": the previous crowded kernel, for A/B tests
+                return (e && strcmp(e, "roles") == 0) ? 0 : 1;
+            }();
+            if (!use_nhwc && !ra.paf_average && crowd_blocks && raster_blocks_smem(pm, 1) <= cap) {
+                // k_raster_blocks: 4x4-cell blocks, one (block, plane) item per thread.  All 18 parts' distance tables are
+                // resident when two CTAs still share an SM (up to ~27 persons); fewer parts at a time beyond that.
+                int pb = kParts;
+                while (pb > 1 && raster_blocks_smem(pm, pb) > (size_t)smem_target_kb * 1024) pb--;
+                if (raster_blocks_smem(pm, pb) > (size_t)smem_target_kb * 1024) { pb = kParts; while (pb > 1 && raster_blocks_smem(pm, pb) > cap) pb--; }
+                ra.part_batch = pb;
+                const size_t bsmem = raster_blocks_smem(pm, pb);
+                static std::once_flag blocks_attr;
+                static cudaError_t blocks_attr_rc = cudaSuccess;
+                std::call_once(blocks_attr, [] {
+                    const int mx = 220 * 1024;
+                    cudaError_t e = cudaFuncSetAttribute(k_raster_blocks<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+                    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_raster_blocks<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+                    blocks_attr_rc = e;
+                });
+                RMPE_CUDA_TRY(blocks_attr_rc);
+                dim3 bgrid(8 * b->batch);
+                ra.batch = b->batch;
+                ProfScope ps("k_raster", st);
+                if (ra.f64) RMPE_CUDA_TRY(launch_pdl(k_raster_blocks<double>, bgrid, dim3(kRbThreads), bsmem, st, ra));
+                else RMPE_CUDA_TRY(launch_pdl(k_raster_blocks<float>, bgrid, dim3(kRbThreads), bsmem, st, ra));
+                count_launch();
+                RMPE_CUDA_TRY(cudaGetLastError());
+                return RMPE_OK;
             }
             static std::once_flag roles_attr;
             static cudaError_t roles_attr_rc = cudaSuccess;

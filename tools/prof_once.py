@@ -13,10 +13,11 @@ import rmpe_b200  # noqa: E402
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     persons = int(sys.argv[2]) if len(sys.argv) > 2 else bench.PERSONS
+    batch = int(sys.argv[3]) if len(sys.argv) > 3 else bench.BATCH
     rmpe_b200.lib.ensure_init(0)
     if what in ("all", "gt"):
-        hb = bench.make_gt_inputs(rmpe_b200, 0, bench.BATCH, persons)
-        plan = rmpe_b200.batch.GtDevicePlan(bench.BATCH, persons, bench.SRC_HW)
+        hb = bench.make_gt_inputs(rmpe_b200, 0, batch, persons)
+        plan = rmpe_b200.batch.GtDevicePlan(batch, persons, bench.SRC_HW)
         plan.upload(hb["imgs"], hb["masks"], hb["joints"], hb["n_persons"], hb["M"], hb["flip"])
         for _ in range(2):
             plan.run()
