@@ -1,6 +1,8 @@
 """Drop-in for py_rmpe_server/py_rmpe_data_iterator.py (RawDataIterator :11-79): per-sample glue
 around Transformer.transform + Heatmapper.create_heatmaps, plus a batched transform_batch that
-runs the whole batch through one C-ABI call.  h5py is imported lazily (absent in this image)."""
+runs the whole batch through one C-ABI call.  The HDF5 file is opened with h5py when it is installed and with the
+package's own reader (h5lite.py: contiguous u8 datasets + the 'meta' string attribute, which is all the reference
+writes, training/generate_hdf5_coco2014.py:356-366) when it is not."""
 import json
 import random
 
@@ -19,8 +21,11 @@ class RawDataIterator:
         self.h5 = None
         self.datum = None
         if h5file is not None:
-            import h5py  # noqa: deferred, optional dependency
-            self.h5 = h5py.File(self.h5file, "r")
+            try:
+                import h5py as _h5  # noqa: optional dependency
+            except ImportError:
+                from . import h5lite as _h5
+            self.h5 = _h5.File(self.h5file, "r")
             self.datum = self.h5['datum']
         self.heatmapper = Heatmapper()
         self.augment = augment

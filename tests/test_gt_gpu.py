@@ -447,6 +447,33 @@ def test_raw_iterator_batched_equals_per_sample(rmpe):
     assert np.abs(many[0][2] - olab).max() <= LABEL_TOL
 
 
+def test_raw_data_iterator_from_an_hdf5_file(rmpe):
+    """RawDataIterator(h5file).gen() on the committed fixture (the reference's on-disk format, read without h5py): every
+    sample through the C ABI against the oracle run on what read_data returned (py_rmpe_data_iterator.py:22-41)."""
+    import os
+    import random
+    from cases import ROOT
+    path = os.path.join(ROOT, "tests", "golden", "datum_3samples.h5")
+    it = rmpe.data_iterator.RawDataIterator(path, shuffle=False, augment=True)
+    assert it.num_keys() == 3
+    random.seed(5)
+    got = [tuple(np.array(a, copy=True) for a in tpl) for tpl in it.gen()]
+    random.seed(5)
+    batched = [tuple(np.array(a, copy=True) for a in tpl) for tpl in it.gen_batched(2)]
+    random.seed(5)
+    for key, tpl, tplb in zip(sorted(it.datum.keys()), got, batched):
+        aug = rmpe.transformer.AugmentSelection.random()
+        img, mask, meta = it.read_data(key)
+        M = go.affine_closed_form(aug.flip, aug.degree, aug.crop, aug.scale, meta['objpos'][0], meta['scale_provided'][0])
+        oimg, omask, oj = go.transform(np.ascontiguousarray(img), np.ascontiguousarray(mask), meta['joints'], M, aug.flip)
+        olab = go.create_heatmaps(oj, omask)
+        assert np.array_equal(tpl[0], np.transpose(oimg, (2, 0, 1)))
+        assert np.array_equal(tpl[1], omask) and np.array_equal(tpl[3], oj)
+        assert np.abs(tpl[2] - olab).max() <= LABEL_TOL
+        for a, b in zip(tpl, tplb):
+            assert np.array_equal(a, b)
+
+
 _VARIANT_SCRIPT = r"""
 import hashlib, sys
 import numpy as np
