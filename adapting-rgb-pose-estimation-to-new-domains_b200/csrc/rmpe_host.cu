@@ -697,20 +697,52 @@ extern "C" int rmpe_decode_batch_host(const RmpeDecodeBatchHost *h) {
     int32_t *d_nsub = (int32_t *)A.take(B * 4);
     int32_t *d_st = (int32_t *)A.take(B * 4);
     void *d_ws = A.take(ws_bytes);
-    RMPE_HOST_TRY(cudaMemcpyAsync(d_heat, h->heat, h->heat_elems * 4, cudaMemcpyHostToDevice, st));
-    RMPE_HOST_TRY(cudaMemcpyAsync(d_paf, h->paf, h->paf_elems * 4, cudaMemcpyHostToDevice, st));
     RMPE_HOST_TRY(cudaMemcpyAsync(d_fr, h->frames, B * sizeof(RmpeFrameDesc), cudaMemcpyHostToDevice, st));
     RMPE_HOST_TRY(cudaMemsetAsync(d_npk, 0, npk_b, st));
-    RmpeDecodeBatch d;
-    memset(&d, 0, sizeof(d));
-    d.batch = B; d.max_peaks = MP; d.max_cand = MC; d.max_persons = MS; d.stride = h->stride; d.flags = h->flags;
-    d.thre1 = h->thre1; d.thre2 = h->thre2;
-    d.heat = d_heat; d.paf = d_paf; d.frames = d_fr; d.frames_host = h->frames;
-    d.candidate = d_cand; d.n_peaks = d_npk; d.connections = d_conn; d.n_conn = d_nconn;
-    d.limb_cand = d_lc; d.n_limb_cand = d_nlc; d.subset = d_sub; d.n_subset = d_nsub; d.status = d_st;
-    d.workspace = d_ws; d.workspace_bytes = ws_bytes;
-    rc = rmpe_decode_batch(&d, st);
-    if (rc != RMPE_OK) return host_fail(*ctx, rc);
+    // Chunks of up to 64 frames (rmpe_decode_batch's own chunk size): the blobs of chunk i + 1 cross the bus on the copy
+    // stream while chunk i is decoded on the main stream -- a 1000-frame multi-scale list is 4.6 GB of blobs, 85 ms of
+    // PCIe against 35 ms of kernels.  A chunk's blobs are the byte range its descriptors span (make_frames lays the
+    // blobs out in frame order; overlapping ranges are merely copied twice).
+    constexpr int kHostChunk = 64;
+    cudaStream_t cs = ctx->pipe[0];
+    cudaEvent_t ev_start, ev_copied[2];
+    RMPE_HOST_TRY(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) RMPE_HOST_TRY(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+    RMPE_HOST_TRY(cudaEventRecord(ev_start, st));
+    RMPE_HOST_TRY(cudaStreamWaitEvent(cs, ev_start, 0));        // the arena may still be in use by this thread's previous call
+    int rc_chunk = RMPE_OK;
+    for (int f0 = 0, ci = 0; f0 < B; f0 += kHostChunk, ci++) {
+        const int n = std::min(kHostChunk, B - f0);
+        size_t h_lo = (size_t)-1, h_hi = 0, p_lo = (size_t)-1, p_hi = 0;
+        for (int i = f0; i < f0 + n; i++) {
+            const RmpeFrameDesc &f = h->frames[i];
+            for (int s = 0; s < f.n_scales; s++) {
+                const size_t cells = (size_t)f.grid_h[s] * f.grid_w[s];
+                h_lo = std::min(h_lo, (size_t)f.heat_offset[s]); h_hi = std::max(h_hi, (size_t)f.heat_offset[s] + cells * 19);
+                p_lo = std::min(p_lo, (size_t)f.paf_offset[s]); p_hi = std::max(p_hi, (size_t)f.paf_offset[s] + cells * 38);
+            }
+        }
+        cudaError_t e = cudaMemcpyAsync(d_heat + h_lo, h->heat + h_lo, (h_hi - h_lo) * 4, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_paf + p_lo, h->paf + p_lo, (p_hi - p_lo) * 4, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_copied[ci & 1], cs);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev_copied[ci & 1], 0);
+        if (e != cudaSuccess) { set_error("decode host pipeline: %s", cudaGetErrorString(e)); rc_chunk = RMPE_E_CUDA; break; }
+        RmpeDecodeBatch d;
+        memset(&d, 0, sizeof(d));
+        d.batch = n; d.max_peaks = MP; d.max_cand = MC; d.max_persons = MS; d.stride = h->stride; d.flags = h->flags;
+        d.thre1 = h->thre1; d.thre2 = h->thre2;
+        d.heat = d_heat; d.paf = d_paf; d.frames = d_fr + f0; d.frames_host = h->frames + f0;
+        d.candidate = d_cand + (size_t)f0 * kParts * MP * 4; d.n_peaks = d_npk + (size_t)f0 * kParts;
+        d.connections = d_conn + (size_t)f0 * kLimbs * MP * 5; d.n_conn = d_nconn + (size_t)f0 * kLimbs;
+        d.limb_cand = d_lc ? d_lc + (size_t)f0 * kLimbs * MC * 4 : nullptr; d.n_limb_cand = d_nlc + (size_t)f0 * kLimbs;
+        d.subset = d_sub + (size_t)f0 * MS * 20; d.n_subset = d_nsub + f0; d.status = d_st + f0;
+        d.workspace = d_ws; d.workspace_bytes = ws_bytes;
+        rc_chunk = rmpe_decode_batch(&d, st);
+        if (rc_chunk != RMPE_OK) break;
+    }
+    cudaEventDestroy(ev_start);
+    for (int i = 0; i < 2; i++) cudaEventDestroy(ev_copied[i]);
+    if (rc_chunk != RMPE_OK) return host_fail(*ctx, rc_chunk);
     // Counts first; then only the filled prefix of every capacity-sized table comes back (a frame fills ~50 of its
     // 18 x max_peaks candidate rows): one strided copy per table, row = the largest prefix any frame / limb uses.
     std::vector<int32_t> npk((size_t)B * kParts), nconn((size_t)B * kLimbs), nlc((size_t)B * kLimbs), nsub(B);

@@ -133,6 +133,34 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Bind this process to the CPUs NVML reports as local to GPU `index` (its NUMA node / PCIe root), so that the pinned
+    host buffers allocated afterwards and the thread that drives the copies sit next to the GPU.  With several ranks
+    per box this keeps every rank's host<->device traffic on its own socket.  Returns the CPU count bound to, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = index
+        if vis:
+            try:
+                phys = int(vis.split(",")[index])
+            except (ValueError, IndexError):
+                phys = index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:  # noqa: BLE001  (no NVML, no permission, unknown topology: run unbound)
+        return None
+
+
 # --------------------------------------------------------------------------------------------
 # synthetic workloads (SURVEY.md 8d).  Frames are made by a fork pool BEFORE CUDA is initialised.
 # --------------------------------------------------------------------------------------------
@@ -384,6 +412,9 @@ def main():
             which = ["gt", "ss3"]
         cpu = cpu_baselines(arm, which)
         arm.close()
+
+    # every rank next to its GPU before anything is pinned (the CPU legs above ran on all cores)
+    numa_cpus = None if os.environ.get("RMPE_BENCH_NO_AFFINITY") else bind_to_gpu_numa_node(local)
 
     import torch
     import torch.distributed as dist
@@ -715,7 +746,7 @@ def main():
                    "parallelism": "samples sharded by rank, no collective"},
         "clocks": clocks, "e2e": gt["e2e"], "gpu_launches": int(gt["launches"]), "roofline": gt["roofline"],
         "cpu_baseline": cpu.get("gt"), "kernels": gt["kernels"], "decode": decode, "configs": configs,
-        "status_nonzero": gt["status_bad"], "host_cores": cores,
+        "status_nonzero": gt["status_bad"], "host_cores": cores, "numa_bound_cpus": numa_cpus,
     }
     print(json.dumps(line), flush=True)
 
