@@ -980,6 +980,7 @@ __global__ void __launch_bounds__(kVerThreads) k_peak_verify(const RmpeFrameDesc
 // ------------------------------------------------------------------------------------------
 struct FinalizeJobs {
     int W[kChunkFrames];
+    int frame[kChunkFrames];      // chunks are cut from the frames sorted by shape: a chunk's frames are not consecutive
 };
 __global__ void __launch_bounds__(256) k_peaks_finalize(const __grid_constant__ FinalizeJobs fj, int first_frame,
                                                         int max_peaks, const int32_t *__restrict__ raw_key,
@@ -990,7 +991,8 @@ __global__ void __launch_bounds__(256) k_peaks_finalize(const __grid_constant__ 
                                                         double *__restrict__ pk_s) {
     pdl_wait();
     pdl_trigger();
-    const int part = blockIdx.x, frame = first_frame + blockIdx.y;
+    const int part = blockIdx.x, frame = fj.frame[blockIdx.y];
+    (void)first_frame;
     const int W = fj.W[blockIdx.y];
     __shared__ int s_key[kMaxPeaksCap];
     __shared__ double s_sc[kMaxPeaksCap];
@@ -1736,6 +1738,18 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
     RMPE_CUDA_TRY(cudaMemsetAsync(b->status, 0, (size_t)B * 4, st));
     RMPE_CUDA_TRY(cudaMemsetAsync(cand_count, 0, 256, st));
 
+    // Frames are processed sorted by shape (outputs stay indexed by the caller's frame number): frames of one shape share
+    // their operator tables and their k_screen_pairs variant, so a chunk of 64 same-shaped frames builds 8 tables instead
+    // of ~240 and runs one plan / pairs launch instead of three (1000 COCO-val shapes: 45 -> 14 table launches per pass).
+    std::vector<int> order(B);
+    for (int i = 0; i < B; i++) order[i] = i;
+    if (B > kChunkFrames)
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+            const RmpeFrameDesc &fx = b->frames_host[x], &fy = b->frames_host[y];
+            if (fx.n_scales != fy.n_scales) return fx.n_scales < fy.n_scales;
+            if (fx.height != fy.height) return fx.height < fy.height;
+            return fx.width < fy.width;
+        });
     int f0 = 0;
     while (f0 < B) {
         // take frames while they fit
@@ -1746,7 +1760,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
         FramePlan plans[kChunkFrames];
         bool any_single = false, any_multi = false, any_screen = false;
         while (f0 + n < B && n < kChunkFrames) {
-            FramePlan p = plan_frame(b->frames_host[f0 + n], b->stride);
+            FramePlan p = plan_frame(b->frames_host[order[f0 + n]], b->stride);
             if (o + p.bytes > b->workspace_bytes) break;
             plans[n] = p;
             if (p.screen) {
@@ -1763,7 +1777,9 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
             n++;
         }
         RMPE_REQUIRE(n > 0, "workspace too small for one frame (see rmpe_decode_workspace_bytes)");
-        const RmpeFrameDesc *fr = b->frames_host + f0;
+        RmpeFrameDesc fr[kChunkFrames];          // the chunk's descriptors in processing order, fid[i] = caller's frame number
+        int fid[kChunkFrames];
+        for (int i = 0; i < n; i++) { fid[i] = order[f0 + i]; fr[i] = b->frames_host[fid[i]]; }
 
         if (any_screen) {
             // ---- screen in float32 straight from the blobs, decide exactly per surviving pixel ----
@@ -1832,7 +1848,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                     }
                     mj.sc[sI] = MsScale{b->heat + f.heat_offset[sI], Ky, Kx, loy, lox, h, w, p.kwy[sI], p.kwx[sI]};
                 }
-                mj.H = f.height; mj.W = f.width; mj.n_scales = f.n_scales; mj.frame = f0 + i;
+                mj.H = f.height; mj.W = f.width; mj.n_scales = f.n_scales; mj.frame = fid[i];
                 mj.tiles_x = (f.width + kScrTW - 1) / kScrTW;
                 mj.tiles = mj.tiles_x * ((f.height + kScrTH - 1) / kScrTH);
                 if (p.multi && p.big) { jobsB.j[nB++] = mj; tB = std::max(tB, mj.tiles); smB = std::max(smB, p.smem); }
@@ -1918,7 +1934,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
             for (int i = 0; i < n; i++) {
                 if (plans[i].screen || (fr[i].n_scales > 1) != multi) continue;
                 sj.j[m].U = u_ptr[i]; sj.j[m].H = fr[i].height; sj.j[m].W = fr[i].width;
-                sj.j[m].frame = f0 + i; sj.j[m].S_out = nullptr;
+                sj.j[m].frame = fid[i]; sj.j[m].S_out = nullptr;
                 int t = ((fr[i].height + kST - 1) / kST) * ((fr[i].width + kST - 1) / kST);
                 max_tiles = max(max_tiles, t);
                 m++;
@@ -1935,7 +1951,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
         }
         {
             FinalizeJobs fj{};
-            for (int i = 0; i < n; i++) fj.W[i] = fr[i].width;
+            for (int i = 0; i < n; i++) { fj.W[i] = fr[i].width; fj.frame[i] = fid[i]; }
             ProfScope ps("k_peaks_finalize", st);
             RMPE_CUDA_TRY(launch_pdl(k_peaks_finalize, dim3(kParts, n), dim3(256), 0, st, fj, f0, MP, raw_key, raw_score, raw_count,
                                      b->candidate, b->n_peaks, pk_x, pk_y, pk_s));
