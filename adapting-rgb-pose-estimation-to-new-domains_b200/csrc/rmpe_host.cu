@@ -699,11 +699,12 @@ extern "C" int rmpe_decode_batch_host(const RmpeDecodeBatchHost *h) {
     void *d_ws = A.take(ws_bytes);
     RMPE_HOST_TRY(cudaMemcpyAsync(d_fr, h->frames, B * sizeof(RmpeFrameDesc), cudaMemcpyHostToDevice, st));
     RMPE_HOST_TRY(cudaMemsetAsync(d_npk, 0, npk_b, st));
-    // Chunks of up to 64 frames (rmpe_decode_batch's own chunk size): the blobs of chunk i + 1 cross the bus on the copy
+    // Chunks of 16 or 64 frames (64 = rmpe_decode_batch's own chunk size): the blobs of chunk i + 1 cross the bus on the copy
     // stream while chunk i is decoded on the main stream -- a 1000-frame multi-scale list is 4.6 GB of blobs, 85 ms of
     // PCIe against 35 ms of kernels.  A chunk's blobs are the byte range its descriptors span (make_frames lays the
     // blobs out in frame order; overlapping ranges are merely copied twice).
-    constexpr int kHostChunk = 64;
+    // small batches are cut finer so that there is something to overlap at all (64 single-scale frames: 4 x 16)
+    const int kHostChunk = B < 256 ? 16 : 64;
     cudaStream_t cs = ctx->pipe[0];
     cudaEvent_t ev_start, ev_copied[2];
     RMPE_HOST_TRY(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
