@@ -207,7 +207,8 @@ def test_crowded_20_persons(rmpe):
 @pytest.mark.parametrize("P", [5, 12, 20, 33, 64])
 @pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
 def test_crowded_rasteriser_person_counts(rmpe, P, f64):
-    """k_raster_roles over its regimes: all 18 parts' tables resident (P <= 24), batched parts (33, 64 persons)."""
+    """The crowded rasteriser (k_raster_blocks) over its regimes: all 18 parts' distance tables resident (P <= 27),
+    parts in batches beyond that (33, 64 persons); person masks of up to 64 bits in the limb scatter."""
     s = rmpe.synth.gt_sample(500 + P, P)
     M, r = _run_case(rmpe, s, f64=f64)
     _, omask, oj = go.transform(s["img"], s["mask"], s["joints"], M, s["aug"][0])
@@ -216,6 +217,27 @@ def test_crowded_rasteriser_person_counts(rmpe, P, f64):
     assert np.array_equal(r["count"][0], ocnt)
     assert np.array_equal(r["joints"][0], oj)
     assert np.abs(r["labels"][0] - olab).max() <= LABEL_TOL + (0 if f64 else 1e-7)
+
+
+@pytest.mark.parametrize("thre", [8., 5.5])
+def test_crowded_limbs_far_outside_the_grid(rmpe, thre):
+    """k_raster_blocks decides the band test in float only where the float numerator is further from the limit than its
+    rounding bound: long limbs whose joints lie thousands of pixels outside the crop (large products, small margins
+    relative to them) and limbs that graze cell corners must still give the reference's counts bit for bit."""
+    rng = np.random.RandomState(23)
+    P = 9
+    j = np.zeros((P, 18, 3))
+    j[..., 0] = rng.uniform(-3000, 3300, size=(P, 18))
+    j[..., 1] = rng.uniform(-3000, 3300, size=(P, 18))
+    j[:3, :, :2] = rng.randint(-40, 90, size=(3, 18, 2)) * 8.0             # cell-corner lattice: dd lands exactly on the limit
+    j[3, :, :2] = rng.uniform(0, 368, size=(18, 2))
+    j[..., 2] = rng.choice([0., 1., 2.], size=(P, 18), p=[.2, .7, .1])
+    mask = np.ones((46, 46))
+    lab, cnt = rmpe.heatmapper.Heatmapper(7., thre).create_heatmaps(j, mask, return_count=True)
+    olab, ocnt = go.create_heatmaps(j, mask, 7., thre, return_count=True)
+    assert ocnt.sum() > 1000
+    assert np.array_equal(cnt, ocnt)
+    assert np.abs(lab - olab).max() <= LABEL_TOL
 
 
 @pytest.mark.parametrize("sigma,thre", [(5., 8.), (7., 6.5), (9.5, 12.), (3., 4.)])
