@@ -2,9 +2,9 @@
 // bicubic), fused 368->46 mask resize, keypoint transform and the 57-plane heat/PAF rasteriser.
 //
 // Reference path replaced (paths relative to the reference root):
-//   py_rmpe_server/py_rmpe_transformer.py:83-114  Transformer.transform      -> k_warp_fused / k_warp_simple,
-//                                                                               k_mask46, joints in k_raster
-//   py_rmpe_server/py_rmpe_heatmapper.py:32-138    Heatmapper.create_heatmaps -> k_raster
+//   py_rmpe_server/py_rmpe_transformer.py:83-114  Transformer.transform      -> k_warp_fused (k_warp_simple + k_mask46 with
+//                                                                               RMPE_GT_SIMPLE_KERNELS), joints in the rasterisers
+//   py_rmpe_server/py_rmpe_heatmapper.py:32-138    Heatmapper.create_heatmaps -> k_raster_small / k_raster_blocks / k_raster_roles
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) k_warp_simple(WarpArgs a) {
 // k_warp_fused: warpAffine(image, border 127) + warpAffine(mask, border 255) + the 368->46 mask
 // resize in ONE pass over the destination.
 //
-// A persistent CTA (one per SM) holds the 32 KB dp4a weight table once and runs NG independent
+// A persistent CTA (one per SM) holds OpenCV's 32 KB int16 weight table once and runs NG independent
 // groups of 128 threads; each group draws 32x32 destination tiles from a global counter (three
 // passes ahead), warp w owning the cell row (destination rows 8w..8w+7) so every warp does
 // identical work.  Per tile the group
@@ -120,9 +120,9 @@ __global__ void __launch_bounds__(256) k_warp_simple(WarpArgs a) {
 //      per source pixel (B,G,R,mask), out-of-image pixels already replaced by the border
 //      constants (127,127,127,255) -- the 16-tap loop needs no bounds test at all; 8-byte aligned
 //      sources are read with 64-bit loads, 8 pixels per thread (4-byte aligned: 32-bit, 4 pixels),
-//   3. evaluates the 16 taps of the channels with dp4a over hi/lo byte-split int16 weights
-//      (exact: identical to OpenCV's int32 accumulation): 4 LDS.32 + 8 PRMT + 8 IDP per tap row
-//      on the four rows that feed the mask, 4 + 7 + 6 on the others,
+//   3. evaluates the 16 taps of the channels with dp2a.lo / dp2a.hi: a pair of OpenCV's int16 weights times the low /
+//      high two pixel bytes of a word (exact: identical to OpenCV's int32 accumulation): 4 LDS.32 + 4 PRMT + 8 IDP.2A
+//      per tap row on the four rows that feed the mask, 4 + 4 + 6 on the others,
 //   4. reduces the warped mask to the 46x46 grid in registers/shuffles (cells are 8x8 destination
 //      pixels of which rows/cols 2..5 feed cv2.resize),
 //   5. packs B,G,R of 32 neighbouring pixels into 24 words with one shuffle and stores the row
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) k_warp_simple(WarpArgs a) {
 constexpr int kTile = 32;
 constexpr int kTilesX = (kOutW + kTile - 1) / kTile;  // 12
 constexpr int kTilesPerSample = kTilesX * kTilesX;    // 144
-constexpr int kTabBytes = 32 * 32 * 8 * 4;            // dp4a table
+constexpr int kTabBytes = 32 * 32 * 8 * 4;            // 1024 phases x 16 int16 weights
 constexpr int kGroupThreads = 128;
 constexpr int kGeoInts = 4 * kTile;                   // {X0,Y0}[32] then {ad,bd}[32], interleaved
 constexpr int kGroupFixedBytes = 4 * kGeoInts * 4;    // geometry ring: tile k, k+1 (bounding box), k+2 (being built); 4th slot: tile queue

@@ -183,3 +183,19 @@ def multi_scale_frame(seed, H, W, n_persons=3):
         sc.append((paf, heat, pd, pr))
     return dict(H=H, W=W, scales=sc)
 
+
+
+def dense_frame(seed, H, W, coarse=12):
+    """Worst case of the decoder's screening: a smooth random field around 0.3 in every heat channel and random PAFs --
+    every (tile, part) pair is above thre1 somewhere, nothing is culled, ~25 peaks per part on a ski.jpg-sized frame.
+    (Real network output sits between this and the sparse template frames of decode_blobs.)"""
+    import cv2
+    rng = np.random.RandomState(seed)
+    h, w = single_scale_grid(H, W)
+
+    def field(c, amp, base):
+        z = rng.normal(size=(h // coarse + 2, w // coarse + 2, c)).astype(np.float32)
+        z = cv2.resize(z, (w, h), interpolation=cv2.INTER_CUBIC)
+        return (base + amp * z.reshape(h, w, c)).astype(np.float32)
+
+    return dict(H=H, W=W, scales=[(field(38, 0.3, 0.0), field(19, 0.15, 0.3), 0, 0)])

@@ -183,6 +183,8 @@ def _synth_frame(task):
     kind, seed, H, W, persons = task
     if kind == "ms":
         return S.multi_scale_frame(seed, H, W, persons)
+    if kind == "dense":
+        return S.dense_frame(seed, H, W)
     h, w = S.single_scale_grid(H, W)
     paf, heat, _ = S.decode_blobs(seed, (H, W), (h, w), persons)
     return dict(H=H, W=W, scales=[(paf, heat, 0, 0)])
@@ -308,11 +310,13 @@ def prepare_frames(rank, world, want_secondary, workers):
     H, W = DEC_HW
     tasks = [("ss", 9000 + 100 * rank + i, H, W, PERSONS) for i in range(64 if want_secondary else DEC_FRAMES)]
     n_ss3 = len(tasks)
-    n_ss20 = n_ms = 0
+    n_ss20 = n_ms = n_dense = 0
     ms_idx = []
     if want_secondary:
         tasks += [("ss", 19000 + 100 * rank + i, H, W, CROWD_PERSONS) for i in range(32)]
         n_ss20 = 32
+        tasks += [("dense", 29000 + 100 * rank + i, H, W, 0) for i in range(DEC_FRAMES)]
+        n_dense = DEC_FRAMES
         shapes = ms_shape_list()
         ms_idx = [i for i in range(len(shapes)) if i % world == rank]
         tasks += [("ms", 700 + i, shapes[i][0], shapes[i][1], PERSONS) for i in ms_idx]
@@ -320,7 +324,8 @@ def prepare_frames(rank, world, want_secondary, workers):
     frames = synth_frames(tasks, workers)
     _FRAMES["ss3"] = frames[:n_ss3]
     _FRAMES["ss20"] = frames[n_ss3:n_ss3 + n_ss20]
-    _FRAMES["ms"] = frames[n_ss3 + n_ss20:n_ss3 + n_ss20 + n_ms]
+    _FRAMES["dense"] = frames[n_ss3 + n_ss20:n_ss3 + n_ss20 + n_dense]
+    _FRAMES["ms"] = frames[n_ss3 + n_ss20 + n_dense:n_ss3 + n_ss20 + n_dense + n_ms]
 
 
 def reference_arm(args):
@@ -604,6 +609,19 @@ def main():
                 dt64, d2h64 = e2e_variant(torch.float64, True)
                 e2e["f64_labels"] = {"value": world * batch / dt64, "unit": "samples/s", "ms_per_step": dt64 * 1e3,
                                      "d2h_bytes_per_step": d2h64}
+                # the same f32 call with ordinary (pageable) numpy buffers, as a caller that does not pin anything has them:
+                # the driver stages every copy through its own pinned buffers and the chunk pipeline serialises
+                pg_out = {"img": np.empty((batch, 368, 368, 3), np.uint8), "mask": np.empty((batch, 46, 46), np.float32),
+                          "labels": np.empty((batch, 57, 46, 46), np.float32), "joints": np.empty((batch, persons, 18, 3))}
+
+                def pageable_step(i):
+                    M = rmpe_b200.batch.aug_affine(hb["flip"], hb["degree"], hb["crop"], hb["scale"], hb["centers"],
+                                                   hb["scale_self"])
+                    rmpe_b200.batch.gt_batch_host(hb["imgs"], hb["masks"], hb["joints"], hb["n_persons"], M, hb["flip"],
+                                                  out=pg_out)
+
+                dtp = host_timed(pageable_step, 3, 1)
+                e2e["pageable_buffers"] = {"value": world * batch / dtp, "unit": "samples/s", "ms_per_step": dtp * 1e3}
                 # what the interconnect alone takes for the f32 step's bytes: the same pinned buffers copied in and out
                 # on two streams at once, no kernels (explains e2e against the device-resident value)
                 big_in = [keep[0], keep[1]]                       # imgs, masks
@@ -729,6 +747,12 @@ def main():
                             "frames_per_gpu": DEC_FRAMES, "l2": "flushed before every timed step", "scaling": "weak"}
             lg["cpu_baseline"] = cpu.get("ss20")
             configs["configs4_crowded_decode"] = lg
+            # not a BASELINE config: the screening's worst case (nothing culled), to bracket real network output
+            lg = decode_leg(_FRAMES["dense"], sec_steps, flushed=True, caps=dict(max_persons=128), with_e2e=False)
+            lg["config"] = {"workload": "single-scale decode of DENSE ski-shaped blobs: smooth random fields, every (tile, part) "
+                                        "pair active, ~25 peaks per part (worst case of the screening; not a BASELINE config)",
+                            "frames_per_gpu": DEC_FRAMES, "l2": "flushed before every timed step", "scaling": "weak"}
+            configs["extra_dense_blobs_worst_case"] = lg
 
     clocks = sampler.finish()
     if world > 1:

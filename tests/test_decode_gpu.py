@@ -216,6 +216,17 @@ def test_dense_blobs_nothing_culled(rmpe, multi):
     _check_against_oracle(r, o)
 
 
+def test_dense_full_size_frame(rmpe):
+    """A ski.jpg-sized frame of dense blobs (bench.py's worst-case leg): every tile of every part is screened, ~25 peaks
+    per part, thousands of limb pairs -- peaks, limb candidates, connections and persons equal the oracle's."""
+    f = rmpe.synth.dense_frame(29000, 674, 712)
+    paf, heat, _, _ = f["scales"][0]
+    o = do.single_scale(paf, heat, 674, 712, detail=True)
+    assert min(len(p) for p in o["all_peaks"]) >= 10 and not o["overflow"]
+    r = rmpe.batch.decode_batch_host([f], max_peaks=128, max_cand=1024, max_persons=128, want_limb_candidates=True)[0]
+    _check_against_oracle(r, o)
+
+
 def test_found_more_than_two_rows_raises_like_the_reference(rmpe):
     """eval...:192-195: a connection whose A peak and B peak sit in three subset rows makes the reference index
     subset_idx[2] -> IndexError.  Lists made by k_limbs are one-to-one and cannot get there, so the assembly kernel is fed
