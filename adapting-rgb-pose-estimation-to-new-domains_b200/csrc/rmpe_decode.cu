@@ -1268,6 +1268,12 @@ __global__ void __launch_bounds__(kLimbThreads) k_limbs(const RmpeFrameDesc *__r
 constexpr int kAsmConnRows = 1024;   // connection rows of a frame held in shared memory (more: read from global)
 constexpr int kAsmRowCap = kMaxSubsetCap + 1;
 
+__host__ __device__ inline bool asm_use_map(int max_peaks) { return max_peaks <= 256; }
+static size_t assemble_smem_bytes(int max_peaks) {
+    return ((size_t)kAsmRowCap * 2 + (size_t)kAsmConnRows * 3 + (size_t)kParts * max_peaks) * 8 + (size_t)kParts * kAsmRowCap * 4 +
+           (asm_use_map(max_peaks) ? (size_t)kParts * max_peaks * 4 : 0);
+}
+
 // Working copy of `subset` in shared memory, column-major: ids as int32 (they are small exact integers in the
 // reference's float64 rows; -1 = no part), total score and part count as float64 with the reference's addition order.
 // Column-major turns the row search of every connection into conflict-free loads and a row deletion into one pass.
@@ -1285,6 +1291,11 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
     double *s_conn = s_ct + kAsmRowCap;                           // [kAsmConnRows][3]: idA, idB, score
     double *s_score = s_conn + kAsmConnRows * 3;                  // [18 * max_peaks] peak scores
     int *s_id = reinterpret_cast<int *>(s_score + kParts * max_peaks);   // [18][kAsmRowCap] subset[:, 0:18]
+    // row that holds candidate id (or -1; entries may go stale and are checked on use): replaces the scan over the rows
+    // while every id sits in at most one row (asm_use_map: kept for max_peaks <= 256)
+    int *s_row = s_id + kParts * kAsmRowCap;                             // [18 * max_peaks]
+    const bool use_map = asm_use_map(max_peaks);
+    bool map_ok = use_map;
     __shared__ int s_off[kLimbs + 1];
     __shared__ int s_nc[kLimbs];
     const double *cand = candidate + (size_t)frame * kParts * max_peaks * 4;
@@ -1303,6 +1314,7 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
     if (lane == kLimbs - 1) s_off[kLimbs] = incl;
     __syncwarp();
     for (int i = lane; i < ntot; i += 32) s_score[i] = cand[(size_t)i * 4 + 2];
+    if (use_map) for (int i = lane; i < ntot; i += 32) s_row[i] = -1;
     {
         const int rows_all = min(s_off[kLimbs], kAsmConnRows);
         for (int i = lane; i < rows_all * 3; i += 32) {
@@ -1337,9 +1349,19 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
                 pA = (int)row[0]; pB = (int)row[1]; sc = row[2];
             }
             int found = 0, j1 = -1;
-            for (int j = 0; j < nrows; j++) {
-                const bool hit = (lane < n_chunk) && (colA[j] == pA || colB[j] == pB);
-                if (hit) { if (found == 0) j1 = j; found++; }
+            if (map_ok) {
+                if (lane < n_chunk) {
+                    int ra = s_row[pA], rb = s_row[pB];
+                    if (ra >= 0 && colA[ra] != pA) ra = -1;          // the peak was overwritten in that row since
+                    if (rb >= 0 && colB[rb] != pB) rb = -1;
+                    if (ra >= 0 && rb >= 0 && ra != rb) { found = 2; j1 = min(ra, rb); }
+                    else if (ra >= 0 || rb >= 0) { found = 1; j1 = ra >= 0 ? ra : rb; }
+                }
+            } else {
+                for (int j = 0; j < nrows; j++) {
+                    const bool hit = (lane < n_chunk) && (colA[j] == pA || colB[j] == pB);
+                    if (hit) { if (found == 0) j1 = j; found++; }
+                }
             }
             bool bad = found >= 2;
             const unsigned one_m = __ballot_sync(0xffffffffu, found == 1);
@@ -1351,6 +1373,7 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
                 if (found == 1) {
                     if (colB[j1] != pB) {
                         colB[j1] = pB;
+                        if (use_map) s_row[pB] = j1;
                         s_ct[j1] = __dadd_rn(s_ct[j1], 1.0);
                         s_sc[j1] = __dadd_rn(s_sc[j1], __dadd_rn(s_score[pB], sc));
                     }
@@ -1358,6 +1381,7 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
                     const int r = nrows + __popc(new_m & ((1u << lane) - 1));
 #pragma unroll
                     for (int c = 0; c < kParts; c++) s_id[c * kAsmRowCap + r] = (c == ia) ? pA : ((c == ib) ? pB : -1);
+                    if (use_map) { s_row[pA] = r; s_row[pB] = r; }
                     s_sc[r] = __dadd_rn(__dadd_rn(__dadd_rn(0.0, s_score[pA]), s_score[pB]), sc);
                     s_ct[r] = 2.0;
                 }
@@ -1416,10 +1440,13 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
                         __syncwarp();
                     }
                     nrows--;
-                } else if (lane == 0) {
-                    colB[j1] = pB;
-                    s_ct[j1] = __dadd_rn(s_ct[j1], 1.0);
-                    s_sc[j1] = __dadd_rn(s_sc[j1], __dadd_rn(s_score[pB], sc));
+                } else {
+                    map_ok = false;        // the B peak now sits in two rows: only the scan finds both from here on
+                    if (lane == 0) {
+                        colB[j1] = pB;
+                        s_ct[j1] = __dadd_rn(s_ct[j1], 1.0);
+                        s_sc[j1] = __dadd_rn(s_sc[j1], __dadd_rn(s_score[pB], sc));
+                    }
                 }
             } else if (found == 0 && k < 17) {
                 if (nrows < max_persons && nrows < kMaxSubsetCap) {
@@ -1434,6 +1461,15 @@ __global__ void __launch_bounds__(32) k_assemble(int first_frame, int max_peaks,
                     st |= RMPE_ST_PERSON_OVERFLOW;
                 }
             }
+            __syncwarp();
+        }
+        if (map_ok) {
+            // the sequential path moved rows around (merges) or filled them without the map: rebuild it from the columns
+            for (int c = 0; c < kParts; c++)
+                for (int r = lane; r < nrows; r += 32) {
+                    const int id = s_id[c * kAsmRowCap + r];
+                    if (id >= 0) s_row[id] = r;
+                }
             __syncwarp();
         }
         }
@@ -1665,7 +1701,7 @@ static int ensure_smooth_attr() {
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_limbs, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kMaxCandCap * 12 + 2 * kMaxPeaksCap));
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)((kAsmRowCap * 2 + kAsmConnRows * 3 + kParts * kMaxPeaksCap) * 8 + kParts * kAsmRowCap * 4)));
+                                       (int)std::max(assemble_smem_bytes(kMaxPeaksCap), assemble_smem_bytes(256))));
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_screen_pairs<10, kScrMaxSrcRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_screen_pairs<kScrMaxKW, kScrMaxSrcRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     RMPE_CUDA_TRY(cudaFuncSetAttribute(k_screen_pairs<kMsKW, kMsMaxRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -1970,7 +2006,7 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
         }
         {
             ProfScope ps("k_assemble", st);
-            const size_t asm_smem = ((size_t)kAsmRowCap * 2 + (size_t)kAsmConnRows * 3 + (size_t)kParts * MP) * 8 + (size_t)kParts * kAsmRowCap * 4;
+            const size_t asm_smem = assemble_smem_bytes(MP);
             RMPE_CUDA_TRY(launch_pdl(k_assemble, dim3(B), dim3(32), asm_smem, st, 0, MP, b->max_persons, b->candidate,
                                      b->connections, b->n_conn, b->n_peaks, b->subset, b->n_subset, b->status));
         }
@@ -2040,7 +2076,7 @@ extern "C" int rmpe_debug_assemble(int max_peaks, int max_persons, const double 
     if (rc != RMPE_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream_;
     RMPE_CUDA_TRY(cudaMemsetAsync(status_dev, 0, sizeof(int32_t), st));
-    const size_t asm_smem = ((size_t)kAsmRowCap * 2 + (size_t)kAsmConnRows * 3 + (size_t)kParts * max_peaks) * 8 + (size_t)kParts * kAsmRowCap * 4;
+    const size_t asm_smem = assemble_smem_bytes(max_peaks);
     k_assemble<<<1, 32, asm_smem, st>>>(0, max_peaks, max_persons, candidate_dev, connections_dev, n_conn_dev, n_peaks_dev,
                                         subset_dev, n_subset_dev, status_dev);
     count_launch();
