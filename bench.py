@@ -622,6 +622,21 @@ def main():
 
                 dtp = host_timed(pageable_step, 3, 1)
                 e2e["pageable_buffers"] = {"value": world * batch / dtp, "unit": "samples/s", "ms_per_step": dtp * 1e3}
+                # the reference's own calling pattern, one sample at a time through the drop-in class
+                # (RawDataIterator.transform_data = AugmentSelection.random + one fused C call; py_rmpe_data_iterator.py:68-74)
+                import random as _random
+                it = rmpe_b200.data_iterator.RawDataIterator(None, shuffle=False, augment=True)
+                _random.seed(1234)
+
+                def drop_in_step(i):
+                    k = i % batch
+                    meta = {"joints": hb["joints"][k].copy(), "objpos": [list(hb["centers"][k])],
+                            "scale_provided": [float(hb["scale_self"][k])]}
+                    it.transform_data(hb["imgs"][k], hb["masks"][k], meta)
+
+                dts = host_timed(drop_in_step, 64, 4)
+                e2e["drop_in_per_sample"] = {"value": world / dts, "unit": "samples/s", "ms_per_sample": dts * 1e3,
+                                             "api": "RawDataIterator.transform_data (reference signature, f64 labels, one call per sample)"}
                 # what the interconnect alone takes for the f32 step's bytes: the same pinned buffers copied in and out
                 # on two streams at once, no kernels (explains e2e against the device-resident value)
                 big_in = [keep[0], keep[1]]                       # imgs, masks
