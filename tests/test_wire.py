@@ -127,3 +127,32 @@ def test_server_process_feeds_client_batches(built_lib):
         server.process.terminate()
         server.process.join(5)
         client.socket.close(0)
+
+
+def test_comparator_metrics_are_the_references():
+    """rmpe_server_comparator's L1 / L2 / exact-match metrics (reference :19-111) on two synthetic sample streams, and
+    the weights.tsv layout (6 + 57 * 3 columns)."""
+    import rmpe_b200
+    cmpm = rmpe_b200.sub("py_rmpe_server.rmpe_server_comparator")
+    rng = np.random.RandomState(3)
+    img = rng.randint(0, 256, size=(3, 368, 368)).astype(np.uint8)
+    mask = rng.randint(0, 256, size=(46, 46)) / 255.0
+    lab = rng.uniform(-1, 1, size=(57, 46, 46))
+    img2 = img.copy(); img2[0, 0, :4] ^= 1
+    mask2 = mask.copy(); mask2[1, 1] += 1 / 255.0
+    lab2 = lab.copy(); lab2[5] += 2 / 255.0
+    rows = cmpm.step(0, {"a": (img, mask, lab), "b": (img2, mask2, lab2), "c": (img, mask, lab)})
+    assert len(rows) == 3 and all(len(r) == 6 + 57 * 3 for r in rows)
+    ab, ac, bc = rows
+    assert ac[:6] == [0.0, 0.0, 1.0, 0.0, 0.0, 1.0] and all(v == 1.0 for v in ac[8::3])
+    n = img.size
+    assert abs(ab[0] - 4.0 / n) < 1e-12 and abs(ab[2] - (1 - 4.0 / n)) < 1e-12            # four pixels differ by one
+    assert abs(ab[3] - 1.0 / 2116) < 1e-9 and abs(ab[5] - (1 - 1.0 / 2116)) < 1e-12        # one mask cell by 1/255
+    cols = cmpm.columns()
+    assert abs(ab[cols.index("Layer5L1")] - 2.0) < 1e-9 and ab[cols.index("Layer5AC")] == 0.0
+    assert ab[cols.index("Layer6L1")] == 0.0 and ab == bc
+    import tempfile, os
+    p = os.path.join(tempfile.mkdtemp(), "weights.tsv")
+    cmpm.write_tsv(rows, p)
+    lines = open(p).read().splitlines()
+    assert len(lines) == 4 and lines[0].split("\t")[1:] == cols and len(lines[1].split("\t")) == 1 + len(cols)
