@@ -108,3 +108,33 @@ def test_raw_data_iterator_opens_the_fixture_like_the_reference():
             sys.modules.pop("h5py", None)
         else:
             sys.modules["h5py"] = had
+
+
+def test_round_trip_property(tmp_path):
+    """hypothesis: any set of keys, array shapes and (unicode, long, empty) meta strings survives write -> read."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    key_st = st.text(alphabet="0123456789abcdefXYZ_-", min_size=1, max_size=12)
+    sample_st = st.tuples(st.integers(1, 6), st.integers(1, 9), st.integers(1, 11), st.integers(0, 2 ** 31 - 1),
+                          st.text(max_size=300))
+    counter = [0]
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(st.dictionaries(key_st, sample_st, min_size=1, max_size=40))
+    def run(spec):
+        samples = {}
+        for k, (c, h, w, seed, text) in spec.items():
+            arr = np.random.RandomState(seed).randint(0, 256, size=(c, h, w)).astype(np.uint8)
+            samples[k] = (arr, json.dumps({"t": text, "n": seed}))
+        counter[0] += 1
+        path = str(tmp_path / ("p%d.h5" % counter[0]))
+        h5lite.write_datum_file(path, samples)
+        with h5lite.File(path) as f:
+            g = f["datum"]
+            assert g.keys() == sorted(samples, key=lambda s: s.encode("utf-8")) or sorted(g.keys()) == sorted(samples)
+            for k, (arr, meta) in samples.items():
+                d = g[k]
+                assert d.shape == arr.shape and np.array_equal(d[()], arr)
+                assert d.attrs["meta"] == meta
+
+    run()
