@@ -1235,10 +1235,15 @@ __global__ void __launch_bounds__(kRrThreads) k_raster_roles(RasterArgs a) {
 //     is further from the limit than its rounding bound, and by the exact f64 test (band_on) otherwise.  The gather pass
 //     then writes the planes as coalesced 128-bit runs like k_raster_small.
 // ==========================================================================================
-constexpr int kRbTile = 6;                           // blocks per tile side (24 cells)
-constexpr int kRbBlocks = kRbTile * kRbTile;         // 36
+#ifndef RMPE_RB_TILE_Y
+#define RMPE_RB_TILE_Y 6
+#endif
+constexpr int kRbTile = 6;                           // blocks per tile row (24 cells)
+constexpr int kRbTileY = RMPE_RB_TILE_Y;             // block rows per heat tile (6: four tiles per sample, 3: eight)
+constexpr int kRbHeatTiles = 2 * (12 / kRbTileY);
+constexpr int kRbBlocks = kRbTile * kRbTileY;        // 36
 constexpr int kRbThreads = ((kRbBlocks * kLimbs + 31) / 32) * 32;    // 704
-constexpr int kRbTabW = 8 * kRbTile;                 // floats per (part, person): dx^2 of the tile's 24 columns, dy^2 of its 24 rows
+constexpr int kRbTabW = 4 * kRbTile + 4 * kRbTileY;  // floats per (part, person): dx^2 of the tile's 24 columns, dy^2 of its rows
 constexpr int kRbLimbsPerCta = 5;                    // 5 + 5 + 5 + 4
 
 static size_t raster_blocks_smem(int pm, int part_batch) {
@@ -1260,9 +1265,9 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
 template <typename T>
 __global__ void __launch_bounds__(kRbThreads, RMPE_RB_MINB) k_raster_blocks(RasterArgs a) {
     // 1-D grid: the heat CTAs of all samples first, the (lighter) limb CTAs behind them fill the tail of the last wave
-    const int role = blockIdx.x >= 4 * a.batch ? 1 : 0;
-    const int id = blockIdx.x - role * 4 * a.batch;
-    const int b = id >> 2, sub = id & 3;
+    const int role = blockIdx.x >= kRbHeatTiles * a.batch ? 1 : 0;
+    const int id = blockIdx.x - role * kRbHeatTiles * a.batch;
+    const int b = role ? id >> 2 : id / kRbHeatTiles, sub = role ? id & 3 : id - b * kRbHeatTiles;
     const int tid = threadIdx.x;
     bool clamped;
     const int P = raster_persons(a, b, kMaxPersonsGt, clamped);
@@ -1276,7 +1281,7 @@ __global__ void __launch_bounds__(kRbThreads, RMPE_RB_MINB) k_raster_blocks(Rast
 
     if (role == 0) {
         // ================= 18 Gaussian part maps + background: tile `sub` =================
-        const int tx0 = 24 * (sub & 1), ty0 = 24 * (sub >> 1);        // first cell column / row of the tile
+        const int tx0 = 24 * (sub & 1), ty0 = 4 * kRbTileY * (sub >> 1);      // first cell column / row of the tile
         const int slot = tid / kRbBlocks, blk = tid - slot * kRbBlocks;   // slot = part of this thread's item
         const int by = blk / kRbTile, bx = blk - by * kRbTile;
         const int x0 = tx0 + 4 * bx, y0 = ty0 + 4 * by;
@@ -1311,7 +1316,7 @@ __global__ void __launch_bounds__(kRbThreads, RMPE_RB_MINB) k_raster_blocks(Rast
             for (int e = tid; e < npb * kRbTabW; e += kRbThreads) {
                 const int pl = e / kRbTabW, col = e - pl * kRbTabW;
                 const bool isx = col < 4 * kRbTile;
-                const double gpos = 8.0 * (isx ? tx0 + col : ty0 + col - 4 * kRbTile) + 3.5;
+                const double gpos = 8.0 * (isx ? tx0 + col : ty0 + col - 4 * kRbTile) + 3.5;   // columns first, then the tile's rows
                 const double *j = s_j + (part0 + pl) * 3 + (isx ? 0 : 1);
                 float *t = s_tab + (size_t)pl * PM * kRbTabW + col;
                 for (int p = 0; p < P; p++, j += kParts * 3, t += kRbTabW) {
@@ -1722,7 +1727,7 @@ extern "C" int rmpe_gt_batch(const RmpeGtBatch *b, void *stream_) {
                     blocks_attr_rc = e;
                 });
                 RMPE_CUDA_TRY(blocks_attr_rc);
-                dim3 bgrid(8 * b->batch);
+                dim3 bgrid((kRbHeatTiles + 4) * b->batch);
                 ra.batch = b->batch;
                 ProfScope ps("k_raster", st);
                 if (ra.f64) RMPE_CUDA_TRY(launch_pdl(k_raster_blocks<double>, bgrid, dim3(kRbThreads), bsmem, st, ra));
