@@ -260,6 +260,51 @@ def test_heatmapper_sigma_thre(rmpe, sigma, thre):
     assert np.array_equal(cnt, ocnt) and np.abs(lab - olab).max() <= LABEL_TOL
 
 
+def test_heatmapper_building_blocks(rmpe):
+    """put_joints / put_gaussian_maps / put_limbs / put_vector_maps (py_rmpe_heatmapper.py:47-138), the reference's
+    in-place building blocks: composed like create_heatmaps (:32-44) they give create_heatmaps; on a stack that already
+    holds values the Gaussian layers merge by max and the PAF layers are overwritten only inside a band."""
+    G = rmpe.config.RmpeGlobalConfig
+    s = rmpe.synth.gt_sample(88, 6, augment=False)
+    joints = s["joints"]
+    mask = np.random.RandomState(4).randint(0, 256, size=(46, 46)) / 255.0
+    hm = rmpe.heatmapper.Heatmapper()
+    want = hm.create_heatmaps(joints, mask)
+    got = np.zeros(G.parts_shape)
+    hm.put_joints(got, joints)
+    sl = slice(G.heat_start, G.heat_start + G.heat_layers)
+    got[G.bkg_start] = 1. - np.amax(got[sl], axis=0)
+    hm.put_limbs(got, joints)
+    got *= mask
+    # identical except the background, which the kernel forms as 1 - max in float32 and this composition in float64
+    assert np.array_equal(got[:G.bkg_start], want[:G.bkg_start]) and np.abs(got[G.bkg_start] - want[G.bkg_start]).max() <= 1e-7
+    olab = go.create_heatmaps(joints, mask)
+    assert np.abs(got - olab).max() <= LABEL_TOL
+    # layer by layer, on a pre-filled stack
+    pre = np.full(G.parts_shape, 0.25)
+    hm.put_gaussian_maps(pre, 3, joints[joints[:, 3, 2] < 2][:, 3, 0:2])
+    ref = np.maximum(0.25, go.create_heatmaps(joints, np.ones((46, 46)))[G.heat_start + 3])
+    assert np.abs(pre[G.heat_start + 3] - ref).max() <= LABEL_TOL and np.all(pre[:G.heat_start] == 0.25)
+    fr, to = G.limbs_conn[4]
+    vis = (joints[:, fr, 2] < 2) & (joints[:, to, 2] < 2)
+    pre = np.full(G.parts_shape, 0.25)
+    hm.put_vector_maps(pre, 10, 11, joints[vis, fr, 0:2], joints[vis, to, 0:2])
+    full, cnt = go.create_heatmaps(joints, np.ones((46, 46)), return_count=True)
+    hit = cnt[4] > 0
+    assert hit.any() and np.all(pre[10][~hit] == 0.25) and np.all(pre[11][~hit] == 0.25)
+    assert np.abs(pre[10][hit] - full[G.paf_start + 8][hit]).max() <= LABEL_TOL
+    assert np.abs(pre[11][hit] - full[G.paf_start + 9][hit]).max() <= LABEL_TOL
+    # more pairs than one rasteriser call holds (64): later pairs still win
+    rng = np.random.RandomState(6)
+    jf = rng.uniform(0, 368, size=(70, 2)); jt = jf + rng.uniform(-60, 60, size=(70, 2))
+    a = np.zeros(G.parts_shape); hm.put_vector_maps(a, 0, 1, jf, jt)
+    persons = np.zeros((70, 18, 3)); persons[:, :, 2] = 2.0
+    f0, t0 = G.limbs_conn[0]
+    persons[:, f0, 0:2] = jf; persons[:, t0, 0:2] = jt; persons[:, f0, 2] = persons[:, t0, 2] = 1.0
+    ref70 = go.create_heatmaps(persons, np.ones((46, 46)))
+    assert np.abs(a[0] - ref70[0]).max() <= LABEL_TOL and np.abs(a[1] - ref70[1]).max() <= LABEL_TOL
+
+
 def test_paf_average_variant(rmpe):
     """Non-default flag: the averaging the reference keeps commented out (py_rmpe_heatmapper.py:119-126)."""
     s = rmpe.synth.gt_sample(77, 20, augment=False)
