@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_const
         float *sTall = sBall + 2 * s_boff[NS];                            // [sc][nrows][128]
         float *sS = sTall + s_toff[NS];                                   // [34][128]
         float *sKyAll = sS + kScrRows * kScrCols;                         // [NS][34][MAXROWS] dense over staged rows
-        float *sKxAll = sKyAll + NS * kScrRows * MAXROWS;                 // [NS][128][KWX]
+        float *sKxAll = sKyAll + NS * kScrRows * MAXROWS;                 // [NS][KWX][128]: tap-major, a warp's 32 columns in 32 banks
         bool bad = false;
         for (int sc = 0; sc < NS; sc++) bad = bad || (s_rng[sc][1] - s_rng[sc][0] + 1 > MAXROWS);
         if (bad) {   // host sized the launch for this never to happen
@@ -699,8 +699,8 @@ __global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_const
                 sKy[i] = (k >= 0 && k < S.kwy) ? S.Ky[(size_t)y * S.kwy + k] : 0.f;
             }
             if (half == 0) {
-                float *kx = sKxAll + ((size_t)sc * kScrCols + col) * KWX;
-                for (int j = 0; j < KWX; j++) kx[j] = (j < S.kwx) ? S.Kx[(size_t)xg * S.kwx + j] : 0.f;
+                float *kx = sKxAll + (size_t)sc * KWX * kScrCols + col;
+                for (int j = 0; j < KWX; j++) kx[j * kScrCols] = (j < S.kwx) ? S.Kx[(size_t)xg * S.kwx + j] : 0.f;
             }
         }
         const int x = x0 + col - 1;
@@ -736,10 +736,10 @@ __global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_const
             const int nrows = s_rng[sc][1] - s_rng[sc][0] + 1, ncols = s_rng[sc][3] - c0 + 1;
             const float *sB = sBall + buf * s_boff[NS] + s_boff[sc];
             float *sT = sTall + s_toff[sc];
-            const float *kx = sKxAll + ((size_t)sc * kScrCols + col) * KWX;
+            const float *kx = sKxAll + (size_t)sc * KWX * kScrCols + col;
             float kxw[KWX];
 #pragma unroll
-            for (int j = 0; j < KWX; j++) kxw[j] = kx[j];
+            for (int j = 0; j < KWX; j++) kxw[j] = kx[j * kScrCols];
             const int off = mylox[sc] - c0, bp = ncols + KWX;
             for (int i = half; i < nrows; i += 2) {
                 const float *b = sB + i * bp + off;
