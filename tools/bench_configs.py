@@ -1,6 +1,6 @@
 """Device-side throughput of the BASELINE.json configs that are not bench.py's headline (configs[2..4]),
-one rank's share of each, CUDA-event timed.  Prints one JSON line per config.  Development / evidence
-tool (profiles/README.md); the driver's contract is bench.py.
+one rank's share of each, CUDA-event timed.  Prints one JSON line per config.  Round-1 development tool: since round 2
+bench.py itself carries these workloads as the `configs.*` legs of its one JSON line (with cpu_baseline and e2e each).
 
   config 2: single-scale decode, ski.jpg-shaped frames, batch 64 over 8 GPUs  -> 8 frames per GPU
   config 3: multi-scale (4 scales) decode over 1k COCO2014-Val-shaped images  -> shapes drawn from
