@@ -347,6 +347,7 @@ constexpr int kMsKW = 12;            // multi scale: non-zeros per row of Kx_s
 constexpr int kMsMaxRows = 24;       // multi scale: staged blob rows per scale and tile
 constexpr int kMsKWBig = 16;         // small frames (scale 2 of a 240-row image is up-sampled by only 2.6): wider variant
 constexpr int kMsMaxRowsBig = 32;
+constexpr int kCullCols = 64;        // staged columns (+ padding) per scale that the tight column-group bound of k_screen_pairs holds
 
 struct AxisJob {
     int dst, src, kw;
@@ -583,15 +584,16 @@ __device__ __forceinline__ void cp_async4(float *smem_dst, const float *gmem_src
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int NR, int MAXROWS>
-__device__ __forceinline__ void ms_vertical(const float *__restrict__ sT, const float *__restrict__ sKy, int col, int half,
-                                            int nrows, float acc[kScrRows / 2]) {
+// vertical pass of R tile rows (row0 ..; rows beyond the tile repeat its last row) over NR staged rows
+template <int NR, int MAXROWS, int R>
+__device__ __forceinline__ void ms_vertical(const float *__restrict__ sT, const float *__restrict__ sKy, int col, int row0,
+                                            int nrows, float acc[R]) {
     float tcol[NR];
 #pragma unroll
     for (int i = 0; i < NR; i++) tcol[i] = (i < nrows) ? sT[i * kScrCols + col] : 0.f;
 #pragma unroll
-    for (int q = 0; q < kScrRows / 2; q++) {
-        const float4 *ky = reinterpret_cast<const float4 *>(sKy + (half * (kScrRows / 2) + q) * MAXROWS);
+    for (int q = 0; q < R; q++) {
+        const float4 *ky = reinterpret_cast<const float4 *>(sKy + min(row0 + q, kScrRows - 1) * MAXROWS);
         float a = acc[q];
 #pragma unroll
         for (int i4 = 0; i4 < NR / 4; i4++) {
@@ -607,16 +609,41 @@ __device__ __forceinline__ void ms_vertical(const float *__restrict__ sT, const 
 
 // ms_vertical over the staged rows [i0, end) only, NR of them (a multiple of four, >= end - i0); the window is moved down
 // if it would leave the MAXROWS-wide rows of Ky
-template <int NR, int MAXROWS>
+template <int NR, int MAXROWS, int R>
 __device__ __forceinline__ void band_vertical(const float *__restrict__ sT, const float *__restrict__ sKy, int i0, int end,
-                                              int col, int half, float acc[kScrRows / 2]) {
+                                              int col, int row0, float acc[R]) {
     static_assert(NR <= MAXROWS && NR % 4 == 0 && MAXROWS % 4 == 0, "float4 rows of Ky");
     i0 = min(i0, MAXROWS - NR);
-    ms_vertical<NR, MAXROWS>(sT + i0 * kScrCols, sKy + i0, col, half, end - i0, acc);
+    ms_vertical<NR, MAXROWS, R>(sT + i0 * kScrCols, sKy + i0, col, row0, end - i0, acc);
+}
+
+// S of R tile rows of one column, accumulated over the scales, -> sS
+template <int MAXROWS, int R>
+__device__ __forceinline__ void slice_vertical(const float *__restrict__ sTall, const int *__restrict__ s_toff,
+                                               const float *__restrict__ sKyAll, int (*s_slab)[14][2], int slab, int NS,
+                                               int col, int row0, float *__restrict__ sS) {
+    float acc[R];
+#pragma unroll
+    for (int q = 0; q < R; q++) acc[q] = 0.f;
+    for (int sc = 0; sc < NS; sc++) {
+        const float *sT = sTall + s_toff[sc];
+        const float *sKy = sKyAll + sc * kScrRows * MAXROWS;
+        // only the band of staged rows these tile rows touch (the rest of Ky is zero: same sums)
+        const int i0 = s_slab[sc][slab][0], end = s_slab[sc][slab][1], len = end - i0;
+        if (len <= 8) band_vertical<8, MAXROWS, R>(sT, sKy, i0, end, col, row0, acc);
+        else if (len <= 12) band_vertical<12, MAXROWS, R>(sT, sKy, i0, end, col, row0, acc);
+        else if (MAXROWS <= 16 || len <= 16) band_vertical<16, MAXROWS, R>(sT, sKy, i0, end, col, row0, acc);
+        else if (len <= 20) band_vertical<(MAXROWS >= 20 ? 20 : MAXROWS), MAXROWS, R>(sT, sKy, i0, end, col, row0, acc);
+        else if (MAXROWS <= 24 || len <= 24) band_vertical<(MAXROWS >= 24 ? 24 : MAXROWS), MAXROWS, R>(sT, sKy, i0, end, col, row0, acc);
+        else band_vertical<MAXROWS, MAXROWS, R>(sT, sKy, i0, end, col, row0, acc);
+    }
+#pragma unroll
+    for (int q = 0; q < R; q++)
+        if (row0 + q < kScrRows) sS[(row0 + q) * kScrCols + col] = acc[q];
 }
 
 template <int KWX, int MAXROWS>
-__global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_constant__ MsJobs jobs, float thre1, int act_cap,
+__global__ void __launch_bounds__(kScrThreads, MAXROWS <= 16 ? 3 : 2) k_screen_pairs(const __grid_constant__ MsJobs jobs, float thre1, int act_cap,
                                                               const ActEntry *__restrict__ act,
                                                               const float *__restrict__ act_A,
                                                               const int32_t *__restrict__ act_count,
@@ -624,16 +651,22 @@ __global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_const
                                                               int32_t *__restrict__ cand_key,
                                                               int32_t *__restrict__ cand_fp,
                                                               int32_t *__restrict__ cand_count,
-                                                              int32_t *__restrict__ status) {
+                                                              int32_t *__restrict__ status, int cull) {
     pdl_wait();
     pdl_trigger();
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int col = tid & (kScrCols - 1), half = tid >> 7;   // 128 columns x 2 row halves
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int col = tid & (kScrCols - 1), half = tid >> 7;   // set-up of an item: 128 columns x 2
     extern __shared__ __align__(16) uint8_t sm_raw[];
     __shared__ int s_rng[RMPE_MAX_SCALES][4];
     __shared__ int s_loy[RMPE_MAX_SCALES][kScrRows];
     __shared__ int s_boff[RMPE_MAX_SCALES + 1], s_toff[RMPE_MAX_SCALES + 1];
-    __shared__ int s_band[RMPE_MAX_SCALES][2][2];   // staged rows [first, end) that the 17 tile rows of a half touch
+    // staged rows [first, end) that a slice of the 34 tile rows touches, for 2 / 4 / 8 slices (entries 0-1, 2-5, 6-13)
+    __shared__ int s_slab[RMPE_MAX_SCALES][14][2];
+    __shared__ int s_gcol[RMPE_MAX_SCALES][4][2];   // staged columns {first, count} that a column group of 32 (+-1) depends on
+    __shared__ float s_ym[RMPE_MAX_SCALES][2];      // largest positive / negative row mass of Ky
+    __shared__ short s_loff[RMPE_MAX_SCALES][kScrCols];        // first staged column of every tile column
+    __shared__ float s_zw[kScrThreads / 32][kCullCols];        // per warp: bound on |sum_i Ky[r][i] B[i][c]| of a staged column
+    __shared__ float s_cb[2][kScrCols];                        // bound on S per tile column (two halves of the scales)
     __shared__ int s_item;
     const int n_act = min(*act_count, act_cap);
 
@@ -663,16 +696,37 @@ __global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_const
             }
             s_boff[NS] = bo; s_toff[NS] = to;
         }
-        if (tid >= 32 && tid < 32 + 2 * NS) {
-            // Ky is zero outside [loy[r], loy[r] + kwy) of its row: the vertical pass of a half only needs that band
-            const int sc = (tid - 32) >> 1, hf = (tid - 32) & 1, r0 = s_rng[sc][0];
+        if (tid >= 32 && tid < 32 + 14 * NS) {
+            // Ky is zero outside [loy[r], loy[r] + kwy) of its row: the vertical pass of a slice only needs that band
+            const int sc = (tid - 32) / 14, e = (tid - 32) - 14 * sc, r0 = s_rng[sc][0];
+            const int ns = e < 2 ? 2 : (e < 6 ? 4 : 8), k = e < 2 ? e : (e < 6 ? e - 2 : e - 6);
+            const int R = (kScrRows + ns - 1) / ns;
             int lo = INT_MAX, hi = 0;
-            for (int r = hf * (kScrRows / 2); r < (hf + 1) * (kScrRows / 2); r++) {
+            for (int r = k * R; r < min((k + 1) * R, kScrRows); r++) {
                 lo = min(lo, s_loy[sc][r] - r0);
                 hi = max(hi, s_loy[sc][r] - r0 + J.sc[sc].kwy);
             }
-            s_band[sc][hf][0] = max(lo, 0) & ~3;        // Ky rows are read as float4
-            s_band[sc][hf][1] = min(hi, s_rng[sc][1] - r0 + 1);
+            if (lo == INT_MAX) lo = 0;                  // a slice beyond the tile (the eighth of eight)
+            s_slab[sc][e][0] = max(lo, 0) & ~3;         // Ky rows are read as float4
+            s_slab[sc][e][1] = max(min(hi, s_rng[sc][1] - r0 + 1), s_slab[sc][e][0]);
+        }
+        if (tid >= 16 && tid < 16 + NS) {
+            const MsScale &S = J.sc[tid - 16];
+            s_ym[tid - 16][0] = __int_as_float(S.loy[H]);
+            s_ym[tid - 16][1] = __int_as_float(S.loy[H + 1]);
+        }
+        if (half == 0) {
+            // staged columns the 32 tile columns of a group read
+            for (int sc = 0; sc < NS; sc++) {
+                s_loff[sc][col] = (short)(mylox[sc] - s_rng[sc][2]);
+                const int lo = __reduce_min_sync(0xffffffffu, mylox[sc]);
+                const int hi = __reduce_max_sync(0xffffffffu, mylox[sc]);
+                if (lane == 0) {
+                    const int c0 = s_rng[sc][2], bp = s_rng[sc][3] - c0 + 1 + KWX;
+                    s_gcol[sc][warp][0] = lo - c0;
+                    s_gcol[sc][warp][1] = min(hi + KWX - c0, bp) - (lo - c0);
+                }
+            }
         }
         __syncthreads();
         float *sBall = reinterpret_cast<float *>(sm_raw);                 // 2 x [sc][nrows][ncols + KWX]: this part / next part
@@ -680,8 +734,11 @@ __global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_const
         float *sS = sTall + s_toff[NS];                                   // [34][128]
         float *sKyAll = sS + kScrRows * kScrCols;                         // [NS][34][MAXROWS] dense over staged rows
         float *sKxAll = sKyAll + NS * kScrRows * MAXROWS;                 // [NS][KWX][128]: tap-major, a warp's 32 columns in 32 banks
-        bool bad = false;
-        for (int sc = 0; sc < NS; sc++) bad = bad || (s_rng[sc][1] - s_rng[sc][0] + 1 > MAXROWS);
+        bool bad = false, tight = (cull != 0);
+        for (int sc = 0; sc < NS; sc++) {
+            bad = bad || (s_rng[sc][1] - s_rng[sc][0] + 1 > MAXROWS);
+            for (int g = 0; g < 4; g++) tight = tight && (s_gcol[sc][g][1] <= kCullCols);
+        }
         if (bad) {   // host sized the launch for this never to happen
             if (tid == 0) atomicOr(status + J.frame, RMPE_ST_PEAK_OVERFLOW);
             continue;
@@ -703,8 +760,6 @@ __global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_const
                 for (int j = 0; j < KWX; j++) kx[j * kScrCols] = (j < S.kwx) ? S.Kx[(size_t)xg * S.kwx + j] : 0.f;
             }
         }
-        const int x = x0 + col - 1;
-        const bool col_ok = col >= 1 && col <= kScrTW && x < W;
         // blob values of one part -> shared memory with cp.async (4-byte gathers out of the NHWC blob): the copy
         // of the NEXT part is in flight while this part is screened
         for (int i = tid; i < 2 * s_boff[NS]; i += kScrThreads) sBall[i] = 0.f;   // incl. the zero padding of every row
@@ -715,9 +770,10 @@ __global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_const
                 const int nrows = s_rng[sc][1] - r0 + 1, ncols = s_rng[sc][3] - c0 + 1;
                 float *sB = sBall + buf * s_boff[NS] + s_boff[sc];
                 const int bp = ncols + KWX;
-                for (int i = tid; i < nrows * ncols; i += kScrThreads) {
-                    const int r = i / ncols, c = i - r * ncols;
-                    cp_async4(sB + r * bp + c, S.heat + ((size_t)(r0 + r) * S.w + c0 + c) * kHeatC + part);
+                for (int r = warp; r < nrows; r += kScrThreads / 32) {       // a staged row per warp: no index division
+                    const float *src = S.heat + ((size_t)(r0 + r) * S.w + c0) * kHeatC + part;
+                    float *dst = sB + r * bp;
+                    for (int c = lane; c < ncols; c += 32) cp_async4(dst + c, src + c * kHeatC);
                 }
             }
         };
@@ -730,64 +786,107 @@ __global__ void __launch_bounds__(kScrThreads) k_screen_pairs(const __grid_const
         cp_async_wait_all();
         __syncthreads();                                        // this part's blob values landed; previous sT / sS are free
         if (pm & (pm - 1)) stage_part(__ffs(pm & (pm - 1)) - 1, buf ^ 1);
+        // ---- which column groups can hold a peak.  |S[r][col]| <= sum_s sum_j |Kx_s[col][j]| z_s[lox + j] with
+        //      z[c] = max(yp B+ + yn B-, yn B+ + yp B-), B+- = the staged column's largest positive / negative blob value
+        //      and yp / yn = the row masses of Ky.  A group of 32 tile columns whose bound (over its columns and their
+        //      two neighbours) is <= thre1 holds no peak and no neighbour of one: it is skipped, its part of sS stays
+        //      stale and is never compared with a pixel that can be a peak; the work of the remaining groups is spread over all
+        //      eight warps (2, 4 or 8 row slices per group).  Warp w bounds group w & 3 for the scales of parity w >> 2.
+        unsigned live = 0xFu;
+        if (tight) {
+            const int g = warp & 3, cg = 32 * g + lane;
+            float b = 0.f;
+            for (int sc = warp >> 2; sc < NS; sc += 2) {
+                const int nrows = s_rng[sc][1] - s_rng[sc][0] + 1, bp = s_rng[sc][3] - s_rng[sc][2] + 1 + KWX;
+                const int first = s_gcol[sc][g][0], cnt = s_gcol[sc][g][1];
+                const float *sB = sBall + buf * s_boff[NS] + s_boff[sc] + first;
+                const float yp = s_ym[sc][0], yn = s_ym[sc][1];
+                __syncwarp();
+                for (int c = lane; c < cnt; c += 32) {
+                    float vp = 0.f, vn = 0.f;
+                    for (int r = 0; r < nrows; r++) {
+                        const float v = sB[r * bp + c];
+                        vp = fmaxf(vp, v); vn = fmaxf(vn, -v);
+                    }
+                    s_zw[warp][c] = fmaxf(yp * vp + yn * vn, yn * vp + yp * vn);
+                }
+                __syncwarp();
+                auto col_bound = [&](int cc) {
+                    const float *kx = sKxAll + (size_t)sc * KWX * kScrCols + cc;
+                    const float *z = s_zw[warp] + ((int)s_loff[sc][cc] - first);
+                    float s = 0.f;
+#pragma unroll
+                    for (int j = 0; j < KWX; j++) s = fmaf(fabsf(kx[j * kScrCols]), z[j], s);
+                    return s;
+                };
+                b += col_bound(cg);
+            }
+            s_cb[warp >> 2][cg] = b;
+            __syncthreads();
+            const float lim_b = thre1 - kScreenDelta * A;
+            live = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                float bq = s_cb[0][32 * q + lane] + s_cb[1][32 * q + lane];
+                // a hot pixel in the first or last column of a group compares with a value of the next group
+                if (lane == 0 && q > 0) bq = fmaxf(bq, s_cb[0][32 * q - 1] + s_cb[1][32 * q - 1]);
+                if (lane == 31 && q < 3) bq = fmaxf(bq, s_cb[0][32 * q + 32] + s_cb[1][32 * q + 32]);
+                if (__any_sync(0xffffffffu, bq * 1.0001f > lim_b)) live |= 1u << q;
+            }
+            if (!live) continue;                                // (uniform over the CTA) nothing of this part can be a peak
+        }
+        const int n_live = __popc(live);
+        const int ns = n_live == 1 ? 8 : (n_live == 2 ? 4 : 2);       // row slices per group
+        const int slab0 = ns == 2 ? 0 : (ns == 4 ? 2 : 6);
+        const int gi = warp / ns, k = warp - gi * ns;
+        const bool on = gi < n_live;
+        const int cg = 32 * (on ? __fns(live, 0, gi + 1) : 0) + lane;  // this warp's tile columns
         // ---- horizontal passes: T_s[i][col] = sum_j Kx_s[col][j] * B_s[i][lox+j] ----
+        if (on)
         for (int sc = 0; sc < NS; sc++) {
-            const int c0 = s_rng[sc][2];
-            const int nrows = s_rng[sc][1] - s_rng[sc][0] + 1, ncols = s_rng[sc][3] - c0 + 1;
-            const float *sB = sBall + buf * s_boff[NS] + s_boff[sc];
+            const int nrows = s_rng[sc][1] - s_rng[sc][0] + 1, bp = s_rng[sc][3] - s_rng[sc][2] + 1 + KWX;
+            const float *sB = sBall + buf * s_boff[NS] + s_boff[sc] + s_loff[sc][cg];
             float *sT = sTall + s_toff[sc];
-            const float *kx = sKxAll + (size_t)sc * KWX * kScrCols + col;
+            const float *kx = sKxAll + (size_t)sc * KWX * kScrCols + cg;
             float kxw[KWX];
 #pragma unroll
             for (int j = 0; j < KWX; j++) kxw[j] = kx[j * kScrCols];
-            const int off = mylox[sc] - c0, bp = ncols + KWX;
-            for (int i = half; i < nrows; i += 2) {
-                const float *b = sB + i * bp + off;
+            for (int i = k; i < nrows; i += ns) {
+                const float *b = sB + i * bp;
                 float acc = 0.f;
 #pragma unroll
                 for (int j = 0; j < KWX; j++) acc = fmaf(kxw[j], b[j], acc);   // beyond the region: zero x zero padding
-                sT[i * kScrCols + col] = acc;
+                sT[i * kScrCols + cg] = acc;
             }
         }
         __syncthreads();
         // ---- vertical passes, accumulated over the scales: S[r][col] = sum_s sum_i Ky_s[r][i] * T_s[i][col] ----
-        {
-            float acc[kScrRows / 2];
-#pragma unroll
-            for (int q = 0; q < kScrRows / 2; q++) acc[q] = 0.f;
-            for (int sc = 0; sc < NS; sc++) {
-                const float *sT = sTall + s_toff[sc];
-                const float *sKy = sKyAll + sc * kScrRows * MAXROWS;
-                // only the band of staged rows this half's 17 tile rows touch (the rest of Ky is zero: same sums)
-                const int i0 = s_band[sc][half][0], end = s_band[sc][half][1], len = end - i0;
-                if (len <= 8) band_vertical<8, MAXROWS>(sT, sKy, i0, end, col, half, acc);
-                else if (len <= 12) band_vertical<12, MAXROWS>(sT, sKy, i0, end, col, half, acc);
-                else if (MAXROWS <= 16 || len <= 16) band_vertical<16, MAXROWS>(sT, sKy, i0, end, col, half, acc);
-                else if (len <= 20) band_vertical<(MAXROWS >= 20 ? 20 : MAXROWS), MAXROWS>(sT, sKy, i0, end, col, half, acc);
-                else if (MAXROWS <= 24 || len <= 24) band_vertical<(MAXROWS >= 24 ? 24 : MAXROWS), MAXROWS>(sT, sKy, i0, end, col, half, acc);
-                else band_vertical<MAXROWS, MAXROWS>(sT, sKy, i0, end, col, half, acc);
-            }
-#pragma unroll
-            for (int q = 0; q < kScrRows / 2; q++) sS[(half * (kScrRows / 2) + q) * kScrCols + col] = acc[q];
+        if (on) {
+            if (ns == 2) slice_vertical<MAXROWS, 17>(sTall, s_toff, sKyAll, s_slab, slab0 + k, NS, cg, 17 * k, sS);
+            else if (ns == 4) slice_vertical<MAXROWS, 9>(sTall, s_toff, sKyAll, s_slab, slab0 + k, NS, cg, 9 * k, sS);
+            else slice_vertical<MAXROWS, 5>(sTall, s_toff, sKyAll, s_slab, slab0 + k, NS, cg, 5 * k, sS);
         }
         __syncthreads();
         // ---- conservative 4-neighbour test on the interior (most rows of a tile hold nothing above thre1:
         //      one shared-memory read, one compare and one vote per row then) ----
         const float delta = kScreenDelta * A;
         const float lim = thre1 - delta, d2 = 2.f * delta;
+        const int x = x0 + cg - 1;
+        const bool col_ok = cg >= 1 && cg <= kScrTW && x < W;
+        const int rt_n = kScrTH / ns;                           // 16, 8 or 4 interior rows per slice
 #pragma unroll 1
-        for (int q = 0; q < kScrTH / 2; q++) {
-            const int r = 1 + half * (kScrTH / 2) + q;
+        for (int q = 0; on && q < rt_n; q++) {
+            const int r = 1 + k * rt_n + q;
             const int y = y0 + r - 1;
-            const float sv = sS[r * kScrCols + col];
+            const float sv = sS[r * kScrCols + cg];
             const bool hot = col_ok && y < H && sv > lim;
             if (!__any_sync(0xffffffffu, hot)) continue;
             bool cand = false;
             if (hot) {
-                const float up = (y > 0) ? sS[(r - 1) * kScrCols + col] : 0.f;
-                const float dn = (y < H - 1) ? sS[(r + 1) * kScrCols + col] : 0.f;
-                const float lf = (x > 0) ? sS[r * kScrCols + col - 1] : 0.f;
-                const float rt = (x < W - 1) ? sS[r * kScrCols + col + 1] : 0.f;
+                const float up = (y > 0) ? sS[(r - 1) * kScrCols + cg] : 0.f;
+                const float dn = (y < H - 1) ? sS[(r + 1) * kScrCols + cg] : 0.f;
+                const float lf = (x > 0) ? sS[r * kScrCols + cg - 1] : 0.f;
+                const float rt = (x < W - 1) ? sS[r * kScrCols + cg + 1] : 0.f;
                 cand = (sv >= up - d2) && (sv >= dn - d2) && (sv >= lf - d2) && (sv >= rt - d2);
             }
             const unsigned bal = __ballot_sync(0xffffffffu, cand);
@@ -1587,7 +1686,7 @@ static FramePlan plan_frame(const RmpeFrameDesc &f, int stride, bool allow_scree
 }
 
 // resident CTAs of k_screen_pairs per SM for a dynamic shared-memory need (+ static shared memory / reserve)
-static int ctas_per_sm(size_t smem) { return std::max(1, std::min(6, (int)((224 * 1024) / (std::max<size_t>(smem, 1) + 2048)))); }
+static int ctas_per_sm(size_t smem) { return std::max(1, std::min(6, (int)((224 * 1024) / (std::max<size_t>(smem, 1) + 6144)))); }
 
 static size_t fixed_ws_bytes(int batch, int max_peaks, int max_cand) {
     size_t per_list = (size_t)batch * kParts * max_peaks;
@@ -1916,6 +2015,8 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                     return (v >= 1 && v <= kParts) ? v : 3;
                 }();
                 const int group = (variant >= 2) ? ms_group : ss_group;
+                // column-group culling inside k_screen_pairs (RMPE_SCREEN_CULL=0: every group of an active tile is evaluated)
+                static const int cull = [] { const char *e = getenv("RMPE_SCREEN_CULL"); return (e && atoi(e) == 0) ? 0 : 1; }();
                 {
                     ProfScope ps("k_screen_plan", st);
                     k_screen_plan<<<dim3(mt, nj), kPlanThreads, 0, st>>>(jobs, (float)b->thre1, act_cap, group, lst, lstA, cnt, tab_err,
@@ -1928,16 +2029,16 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                     const int grid = sms * per_sm;
                     if (variant == 0)
                         RMPE_CUDA_TRY(launch_pdl(k_screen_pairs<10, kScrMaxSrcRows>, dim3(grid), dim3(kScrThreads), smem, st,
-                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, nxt, cand_cap, cand_key, cand_fp, cand_count, b->status));
+                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, nxt, cand_cap, cand_key, cand_fp, cand_count, b->status, cull));
                     else if (variant == 1)
                         RMPE_CUDA_TRY(launch_pdl(k_screen_pairs<kScrMaxKW, kScrMaxSrcRows>, dim3(grid), dim3(kScrThreads), smem, st,
-                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, nxt, cand_cap, cand_key, cand_fp, cand_count, b->status));
+                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, nxt, cand_cap, cand_key, cand_fp, cand_count, b->status, cull));
                     else if (variant == 2)
                         RMPE_CUDA_TRY(launch_pdl(k_screen_pairs<kMsKW, kMsMaxRows>, dim3(grid), dim3(kScrThreads), smem, st,
-                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, nxt, cand_cap, cand_key, cand_fp, cand_count, b->status));
+                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, nxt, cand_cap, cand_key, cand_fp, cand_count, b->status, cull));
                     else
                         RMPE_CUDA_TRY(launch_pdl(k_screen_pairs<kMsKWBig, kMsMaxRowsBig>, dim3(grid), dim3(kScrThreads), smem, st,
-                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, nxt, cand_cap, cand_key, cand_fp, cand_count, b->status));
+                            jobs, (float)b->thre1, act_cap, lst, lstA, cnt, nxt, cand_cap, cand_key, cand_fp, cand_count, b->status, cull));
                 }
                 count_launch(2);
                 return RMPE_OK;
