@@ -667,6 +667,7 @@ __global__ void __launch_bounds__(kScrThreads, MAXROWS <= 16 ? 3 : 2) k_screen_p
     __shared__ short s_loff[RMPE_MAX_SCALES][kScrCols];        // first staged column of every tile column
     __shared__ float s_zw[kScrThreads / 32][kCullCols];        // per warp: bound on |sum_i Ky[r][i] B[i][c]| of a staged column
     __shared__ float s_cb[2][kScrCols];                        // bound on S per tile column (two halves of the scales)
+    __shared__ float s_A[kParts];                              // the item's bounds on the partial sums (rounding allowance)
     __shared__ int s_item;
     const int n_act = min(*act_count, act_cap);
 
@@ -710,6 +711,7 @@ __global__ void __launch_bounds__(kScrThreads, MAXROWS <= 16 ? 3 : 2) k_screen_p
             s_slab[sc][e][0] = max(lo, 0) & ~3;         // Ky rows are read as float4
             s_slab[sc][e][1] = max(min(hi, s_rng[sc][1] - r0 + 1), s_slab[sc][e][0]);
         }
+        if (tid >= 128 && tid < 128 + kParts) s_A[tid - 128] = act_A[(size_t)E.slot * kParts + tid - 128];
         if (tid >= 16 && tid < 16 + NS) {
             const MsScale &S = J.sc[tid - 16];
             s_ym[tid - 16][0] = __int_as_float(S.loy[H]);
@@ -782,7 +784,7 @@ __global__ void __launch_bounds__(kScrThreads, MAXROWS <= 16 ? 3 : 2) k_screen_p
         int buf = 0;
       for (unsigned pm = E.parts; pm; pm &= pm - 1, buf ^= 1) {
         const int part = __ffs(pm) - 1;
-        const float A = act_A[(size_t)E.slot * kParts + part];
+        const float A = s_A[part];
         cp_async_wait_all();
         __syncthreads();                                        // this part's blob values landed; previous sT / sS are free
         if (pm & (pm - 1)) stage_part(__ffs(pm & (pm - 1)) - 1, buf ^ 1);
@@ -831,7 +833,7 @@ __global__ void __launch_bounds__(kScrThreads, MAXROWS <= 16 ? 3 : 2) k_screen_p
                 // a hot pixel in the first or last column of a group compares with a value of the next group
                 if (lane == 0 && q > 0) bq = fmaxf(bq, s_cb[0][32 * q - 1] + s_cb[1][32 * q - 1]);
                 if (lane == 31 && q < 3) bq = fmaxf(bq, s_cb[0][32 * q + 32] + s_cb[1][32 * q + 32]);
-                if (__any_sync(0xffffffffu, bq * 1.0001f > lim_b)) live |= 1u << q;
+                if (__any_sync(0xffffffffu, !(bq * 1.0001f <= lim_b))) live |= 1u << q;     // NaN / Inf keep the group
             }
             if (!live) continue;                                // (uniform over the CTA) nothing of this part can be a peak
         }
@@ -2004,17 +2006,18 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                 float *lstA = act_A + (size_t)slot * act_cap * kParts;
                 // parts per work item (measured): single-scale items are cheap to set up (three parts), multi-scale items
                 // stage the operators of four scales (amortise them over up to six active parts of the tile)
-                static const int ms_group = [] {      // measured on 512 COCO-val-shaped frames: 18 parts per item 18.1 k frames/s, 9: 19.3 k, 6: 19.4 k
+                static const int ms_group = [] {      // 256 COCO-val-shaped frames with the culling kernel: 6 parts per item 7.23 ms, 9: 7.09, 12: 7.13, 18: 7.23
                     const char *e = getenv("RMPE_MS_GROUP");
-                    int v = e ? atoi(e) : 6;
-                    return (v >= 1 && v <= kParts) ? v : 6;
+                    int v = e ? atoi(e) : 9;
+                    return (v >= 1 && v <= kParts) ? v : 9;
                 }();
-                static const int ss_group = [] {      // 8 ski-shaped frames: 1 part per item 0.115 ms, 2: 0.109, 3: 0.107, 4: 0.111
+                static const int ss_group = [] {      // 8 ski-shaped frames: 3 parts per item 0.109 ms, 6: 0.111; 64 frames: 3: 0.402, 6: 0.388, 9: 0.388
                     const char *e = getenv("RMPE_SS_GROUP");
-                    int v = e ? atoi(e) : 3;
-                    return (v >= 1 && v <= kParts) ? v : 3;
+                    int v = e ? atoi(e) : 0;
+                    return (v >= 1 && v <= kParts) ? v : 0;
                 }();
-                const int group = (variant >= 2) ? ms_group : ss_group;
+                // few frames: small items spread better over the SMs; many: larger items amortise the set-up of a tile
+                const int group = (variant >= 2) ? ms_group : (ss_group ? ss_group : (nj > 16 ? 6 : 3));
                 // column-group culling inside k_screen_pairs (RMPE_SCREEN_CULL=0: every group of an active tile is evaluated)
                 static const int cull = [] { const char *e = getenv("RMPE_SCREEN_CULL"); return (e && atoi(e) == 0) ? 0 : 1; }();
                 {
