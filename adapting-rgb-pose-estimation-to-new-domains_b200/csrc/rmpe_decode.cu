@@ -347,7 +347,8 @@ constexpr int kMsKW = 12;            // multi scale: non-zeros per row of Kx_s
 constexpr int kMsMaxRows = 24;       // multi scale: staged blob rows per scale and tile
 constexpr int kMsKWBig = 16;         // small frames (scale 2 of a 240-row image is up-sampled by only 2.6): wider variant
 constexpr int kMsMaxRowsBig = 32;
-constexpr int kCullCols = 64;        // staged columns (+ padding) per scale that the tight column-group bound of k_screen_pairs holds
+constexpr int kPlanSlots = 4;        // parts of a tile refined together by k_screen_plan
+constexpr int kPlanMaxCols = 96;     // staged columns + padding per scale that the refinement holds
 
 struct AxisJob {
     int dst, src, kw;
@@ -450,10 +451,11 @@ struct MsJob {
 struct MsJobs {
     MsJob j[kMsJobsPerLaunch];
 };
-struct ActEntry {          // one work item of k_screen_pairs: up to `group` active parts of one tile
+struct ActEntry {          // one work item of k_screen_pairs: up to `group` (<= 16) active parts of one tile
     int job, tile;
     unsigned parts;         // bit p = part p is screened by this item
     int slot;               // index of its 18 bounds in act_A
+    unsigned long long live;   // nibble k = column groups (32 tile columns each) of the item's k-th part that can hold a peak
 };
 
 // blob region of every scale that a tile's 34 x 128 smoothed values depend on: s_rng[sc] = {r0, r1, c0, c1};
@@ -488,7 +490,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_screen_plan(const __grid_const
                                                               int group, ActEntry *__restrict__ act,
                                                               float *__restrict__ act_A, int32_t *__restrict__ act_count,
                                                               const int32_t *__restrict__ tab_err,
-                                                              int32_t *__restrict__ status) {
+                                                              int32_t *__restrict__ status, int refine) {
     pdl_trigger();
     const MsJob &J = jobs.j[blockIdx.y];
     if ((int)blockIdx.x >= J.tiles) return;
@@ -498,82 +500,230 @@ __global__ void __launch_bounds__(kPlanThreads) k_screen_plan(const __grid_const
     }
     const int NS = J.n_scales;
     const int ty = blockIdx.x / J.tiles_x, tx = blockIdx.x - ty * J.tiles_x;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int y0 = ty * kScrTH, x0 = tx * kScrTW;
     __shared__ int s_rng[RMPE_MAX_SCALES][4];
     __shared__ int s_loy[RMPE_MAX_SCALES][kScrRows];
     __shared__ int s_bpos[RMPE_MAX_SCALES][kHeatC + 1], s_bneg[RMPE_MAX_SCALES][kHeatC + 1];
+    // largest positive / negative value of every staged row, per channel (bits of non-negative floats)
+    __shared__ int s_rp[RMPE_MAX_SCALES][kMsMaxRowsBig][kHeatC + 1], s_rn[RMPE_MAX_SCALES][kMsMaxRowsBig][kHeatC + 1];
     int mylox[RMPE_MAX_SCALES];
     if (tid < RMPE_MAX_SCALES * (kHeatC + 1)) { (&s_bpos[0][0])[tid] = 0; (&s_bneg[0][0])[tid] = 0; }
-    tile_ranges(J, ty * kScrTH, tx * kScrTW, tid, tid & (kScrCols - 1), tid >> 7, s_rng, s_loy, mylox);
+    for (int i = tid; i < RMPE_MAX_SCALES * kMsMaxRowsBig * (kHeatC + 1); i += kPlanThreads) { (&s_rp[0][0][0])[i] = 0; (&s_rn[0][0][0])[i] = 0; }
+    tile_ranges(J, y0, x0, tid, tid & (kScrCols - 1), tid >> 7, s_rng, s_loy, mylox);
     for (int sc = 0; sc < NS; sc++) {
         const MsScale &S = J.sc[sc];
         const int r0 = s_rng[sc][0], c0 = s_rng[sc][2];
         const int nrows = s_rng[sc][1] - r0 + 1, rowlen = (s_rng[sc][3] - c0 + 1) * kHeatC;
         // coalesced row segments of the NHWC blob; element e of a segment belongs to channel e % 19.  13 x 19 = 247
         // threads walk a segment with stride 247, so a thread stays on ONE channel and keeps its maxima in registers;
-        // the 13 threads of a channel meet in shared memory once per scale.
+        // the 13 threads of a channel meet in shared memory once per staged row (row maxima) and once per scale.
         float vpos = 0.f, vneg = 0.f;
         if (tid < kPlanStride) {
+            const int ch = tid % kHeatC;
             const float *base = S.heat + ((size_t)r0 * S.w + c0) * kHeatC;
             const size_t rstride = (size_t)S.w * kHeatC;
             int r = 0;
             for (; r + 1 < nrows; r += 2) {                       // two rows in flight
                 const float *row0 = base + (size_t)r * rstride, *row1 = row0 + rstride;
+                float p0 = 0.f, n0 = 0.f, p1 = 0.f, n1 = 0.f;
                 for (int e = tid; e < rowlen; e += kPlanStride) {
                     const float v0 = row0[e], v1 = row1[e];
-                    vpos = fmaxf(vpos, fmaxf(v0, v1));
-                    vneg = fmaxf(vneg, fmaxf(-v0, -v1));
+                    p0 = fmaxf(p0, v0); n0 = fmaxf(n0, -v0);
+                    p1 = fmaxf(p1, v1); n1 = fmaxf(n1, -v1);
                 }
+                if (r + 1 < kMsMaxRowsBig) {
+                    if (p0 > 0.f) atomicMax(&s_rp[sc][r][ch], __float_as_int(p0));
+                    if (n0 > 0.f) atomicMax(&s_rn[sc][r][ch], __float_as_int(n0));
+                    if (p1 > 0.f) atomicMax(&s_rp[sc][r + 1][ch], __float_as_int(p1));
+                    if (n1 > 0.f) atomicMax(&s_rn[sc][r + 1][ch], __float_as_int(n1));
+                }
+                vpos = fmaxf(vpos, fmaxf(p0, p1));
+                vneg = fmaxf(vneg, fmaxf(n0, n1));
             }
             if (r < nrows) {
                 const float *row0 = base + (size_t)r * rstride;
+                float p0 = 0.f, n0 = 0.f;
                 for (int e = tid; e < rowlen; e += kPlanStride) {
                     const float v0 = row0[e];
-                    vpos = fmaxf(vpos, v0);
-                    vneg = fmaxf(vneg, -v0);
+                    p0 = fmaxf(p0, v0); n0 = fmaxf(n0, -v0);
                 }
+                if (r < kMsMaxRowsBig) {
+                    if (p0 > 0.f) atomicMax(&s_rp[sc][r][ch], __float_as_int(p0));
+                    if (n0 > 0.f) atomicMax(&s_rn[sc][r][ch], __float_as_int(n0));
+                }
+                vpos = fmaxf(vpos, p0);
+                vneg = fmaxf(vneg, n0);
             }
-            if (vpos > 0.f) atomicMax(&s_bpos[sc][tid % kHeatC], __float_as_int(vpos));
-            if (vneg > 0.f) atomicMax(&s_bneg[sc][tid % kHeatC], __float_as_int(vneg));
+            if (vpos > 0.f) atomicMax(&s_bpos[sc][ch], __float_as_int(vpos));
+            if (vneg > 0.f) atomicMax(&s_bneg[sc][ch], __float_as_int(vneg));
         }
     }
     __syncthreads();
     // S = sum_s sum_ij Ky_s[i] Kx_s[j] B_s[i][j]: the positive entries of Ky (x) Kx weigh max(B,0), the negative ones
     // max(-B,0); P = Py+ Px+ + Py- Px-, N = Py+ Px- + Py- Px+ with the row masses k_axis_tables left behind the tables
     __shared__ float s_A[kParts];
-    __shared__ int s_on[kParts];
-    if (tid < kParts) {
-        float bound = 0.f, atot = 0.f;
-        for (int sc = 0; sc < NS; sc++) {
-            const MsScale &S = J.sc[sc];
-            const float yp = __int_as_float(S.loy[J.H]), yn = __int_as_float(S.loy[J.H + 1]);
-            const float xp = __int_as_float(S.lox[J.W]), xn = __int_as_float(S.lox[J.W + 1]);
-            const float P = yp * xp + yn * xn, N = yp * xn + yn * xp;
-            const float bp = __int_as_float(s_bpos[sc][tid]), bn = __int_as_float(s_bneg[sc][tid]);
-            bound += P * bp + N * bn;
-            atot += (P + N) * fmaxf(bp, bn);
+    __shared__ int s_parts[kParts], s_nact;      // parts still active, compacted
+    __shared__ unsigned char s_live[kParts];     // their live column groups
+    __shared__ int s_rb[kParts];
+    if (tid < 32) {
+        bool on = false;
+        if (tid < kParts) {
+            float bound = 0.f, atot = 0.f;
+            for (int sc = 0; sc < NS; sc++) {
+                const MsScale &S = J.sc[sc];
+                const float yp = __int_as_float(S.loy[J.H]), yn = __int_as_float(S.loy[J.H + 1]);
+                const float xp = __int_as_float(S.lox[J.W]), xn = __int_as_float(S.lox[J.W + 1]);
+                const float P = yp * xp + yn * xn, N = yp * xn + yn * xp;
+                const float bp = __int_as_float(s_bpos[sc][tid]), bn = __int_as_float(s_bneg[sc][tid]);
+                bound += P * bp + N * bn;
+                atot += (P + N) * fmaxf(bp, bn);
+            }
+            bound *= 1.0001f; atot *= 1.0001f;      // atot bounds every partial sum: scales the rounding allowance
+            s_A[tid] = atot;
+            on = bound + kScreenDelta * atot > thre1;
+            s_live[tid] = on ? 0xF : 0;
+            s_rb[tid] = 0;
         }
-        bound *= 1.0001f; atot *= 1.0001f;      // atot bounds every partial sum: scales the rounding allowance
-        s_A[tid] = atot;
-        s_on[tid] = (bound + kScreenDelta * atot > thre1) ? 1 : 0;
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        if (on) s_parts[__popc(m & ((1u << tid) - 1))] = tid;
+        if (tid == 0) s_nact = __popc(m);
     }
     __syncthreads();
+    int n_on = s_nact;
+    if (n_on == 0) return;
+    // ---- refinement of the parts that passed.  The bound above lets a peak switch on every tile within the reach of
+    //      the operators (+-45 pixels: ~10 tiles per peak where ~2.6 hold values above thre1).  Two one-dimensional
+    //      bounds from the same blob values follow:
+    //        rows:    |S[r][c]| <= sum_s sum_i |Ky_s[r][i]| zy_s[i],  zy_s[i] = max(xp B+ + xn B-, xn B+ + xp B-) over staged row i
+    //        columns: |S[r][c]| <= sum_s sum_j |Kx_s[c][j]| zx_s[j],  zx_s[j] likewise over staged column j with the masses of Ky
+    //      (B+- = largest positive / negative blob value, xp / xn, yp / yn = largest row masses of the operators).
+    //      A part stays active if some row bound and some column bound exceed thre1; the column bounds also say WHICH
+    //      groups of 32 tile columns (with their two neighbour columns) can hold a peak: k_screen_pairs evaluates those only.
+    bool can_refine = refine != 0;
+    for (int sc = 0; sc < NS; sc++)
+        can_refine = can_refine && (s_rng[sc][1] - s_rng[sc][0] + 1 <= kMsMaxRowsBig) &&
+                     (s_rng[sc][3] - s_rng[sc][2] + 1 + kMsKWBig <= kPlanMaxCols) && J.sc[sc].kwx <= kMsKWBig;
+    if (can_refine) {
+        __shared__ float s_zx[kPlanSlots][RMPE_MAX_SCALES][kPlanMaxCols];
+        __shared__ float s_cbp[kPlanSlots][kScrCols];
+        // (1) row bounds of every active part: one thread per (part, tile row)
+        for (int task = tid; task < n_on * kScrRows; task += kPlanThreads) {
+            const int slot = task / kScrRows, t = task - slot * kScrRows;
+            const int part = s_parts[slot];
+            const int y = clampi(y0 - 1 + t, 0, J.H - 1);
+            float rb = 0.f;
+            for (int sc = 0; sc < NS; sc++) {
+                const MsScale &S = J.sc[sc];
+                const float xp = __int_as_float(S.lox[J.W]), xn = __int_as_float(S.lox[J.W + 1]);
+                const int lo = s_loy[sc][t] - s_rng[sc][0], nrows = s_rng[sc][1] - s_rng[sc][0] + 1;
+                const float *ky = S.Ky + (size_t)y * S.kwy;
+                for (int k = 0; k < S.kwy; k++)
+                    if (lo + k < nrows) {
+                        const float bp = __int_as_float(s_rp[sc][lo + k][part]), bn = __int_as_float(s_rn[sc][lo + k][part]);
+                        rb = fmaf(fabsf(ky[k]), fmaxf(xp * bp + xn * bn, xn * bp + xp * bn), rb);
+                    }
+            }
+            atomicMax(&s_rb[part], __float_as_int(rb));
+        }
+        __syncthreads();
+        if (tid < 32) {                             // parts whose rows reach thre1, compacted again
+            bool on = false;
+            int part = 0;
+            if (tid < n_on) {
+                part = s_parts[tid];
+                on = !(__int_as_float(s_rb[part]) * 1.0001f + kScreenDelta * s_A[part] <= thre1);
+                if (!on) s_live[part] = 0;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            __syncwarp();
+            if (on) s_parts[__popc(m & ((1u << tid) - 1))] = part;
+            if (tid == 0) s_nact = __popc(m);
+        }
+        __syncthreads();
+        n_on = s_nact;
+        for (int b0 = 0; b0 < n_on; b0 += kPlanSlots) {
+            const int nb = min(kPlanSlots, n_on - b0);
+            __syncthreads();                       // the previous batch is done with the tables
+            // (2) staged columns: one thread per (part, scale, column); the lines were read by the scan above
+            for (int sc = 0; sc < NS; sc++) {
+                const MsScale &S = J.sc[sc];
+                const int r0 = s_rng[sc][0], c0 = s_rng[sc][2];
+                const int nrows = s_rng[sc][1] - r0 + 1, ncols = s_rng[sc][3] - c0 + 1, np = ncols + kMsKWBig;
+                const float yp = __int_as_float(S.loy[J.H]), yn = __int_as_float(S.loy[J.H + 1]);
+                const size_t rstride = (size_t)S.w * kHeatC;
+                for (int task = tid; task < nb * np; task += kPlanThreads) {
+                    const int slot = task / np, j = task - slot * np;
+                    float z = 0.f;
+                    if (j < ncols) {
+                        const float *base = S.heat + ((size_t)r0 * S.w + c0 + j) * kHeatC + s_parts[b0 + slot];
+                        float vp = 0.f, vn = 0.f;
+                        for (int i = 0; i < nrows; i++) {
+                            const float v = base[i * rstride];
+                            vp = fmaxf(vp, v); vn = fmaxf(vn, -v);
+                        }
+                        z = fmaxf(yp * vp + yn * vn, yn * vp + yp * vn);
+                    }
+                    s_zx[slot][sc][j] = z;          // zero beyond the region: the taps there weigh nothing
+                }
+            }
+            __syncthreads();
+            // (3) column bounds: thread = (tile column, parity of the part's slot)
+            {
+                const int c = tid & (kScrCols - 1), par = tid >> 7;
+                const int xg = clampi(x0 - 1 + c, 0, J.W - 1);
+                float cb[kPlanSlots / 2];
+#pragma unroll
+                for (int q = 0; q < kPlanSlots / 2; q++) cb[q] = 0.f;
+                if (par < nb)
+                    for (int sc = 0; sc < NS; sc++) {
+                        const MsScale &S = J.sc[sc];
+                        const float *kx = S.Kx + (size_t)xg * S.kwx;
+                        const int off = mylox[sc] - s_rng[sc][2];
+                        for (int j = 0; j < S.kwx; j++) {
+                            const float w = fabsf(kx[j]);
+#pragma unroll
+                            for (int q = 0; q < kPlanSlots / 2; q++) cb[q] = fmaf(w, s_zx[2 * q + par][sc][off + j], cb[q]);
+                        }
+                    }
+#pragma unroll
+                for (int q = 0; q < kPlanSlots / 2; q++) s_cbp[2 * q + par][c] = cb[q];
+            }
+            __syncthreads();
+            // (4) live column groups of a part: one warp per part
+            if (warp < nb) {
+                const int part = s_parts[b0 + warp];
+                const float lim_b = thre1 - kScreenDelta * s_A[part];
+                unsigned live = 0;
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    float v = s_cbp[warp][32 * g + lane];
+                    if (lane == 0 && g > 0) v = fmaxf(v, s_cbp[warp][32 * g - 1]);     // a hot pixel in the first or last column
+                    if (lane == 31 && g < 3) v = fmaxf(v, s_cbp[warp][32 * g + 32]);   // compares with a value of the next group
+                    if (__any_sync(0xffffffffu, !(v * 1.0001f <= lim_b))) live |= 1u << g;   // NaN / Inf keep the group
+                }
+                if (lane == 0) s_live[part] = (unsigned char)live;
+            }
+        }
+        __syncthreads();
+    }
     if (tid == 0) {
         // active parts (a peak needs S > thre1), cut into work items of at most `group` parts
         unsigned m = 0;
+        unsigned long long lv = 0;
         int n = 0;
         for (int p = 0; p <= kParts; p++) {
-            const bool on = p < kParts && s_on[p];
-            if (on) { m |= 1u << p; n++; }
+            const bool on = p < kParts && s_live[p];
+            if (on) { m |= 1u << p; lv |= (unsigned long long)s_live[p] << (4 * n); n++; }
             if ((n == group || p == kParts) && m) {
                 const int slot = atomicAdd(act_count, 1);
                 if (slot < act_cap) {
-                    act[slot] = ActEntry{(int)blockIdx.y, (int)blockIdx.x, m, slot};
+                    act[slot] = ActEntry{(int)blockIdx.y, (int)blockIdx.x, m, slot, lv};
                     for (int q = 0; q < kParts; q++) act_A[(size_t)slot * kParts + q] = s_A[q];
                 } else {
                     atomicOr(status + J.frame, RMPE_ST_PEAK_OVERFLOW);
                 }
-                m = 0; n = 0;
+                m = 0; lv = 0; n = 0;
             }
         }
     }
@@ -662,11 +812,7 @@ __global__ void __launch_bounds__(kScrThreads, MAXROWS <= 16 ? 3 : 2) k_screen_p
     __shared__ int s_boff[RMPE_MAX_SCALES + 1], s_toff[RMPE_MAX_SCALES + 1];
     // staged rows [first, end) that a slice of the 34 tile rows touches, for 2 / 4 / 8 slices (entries 0-1, 2-5, 6-13)
     __shared__ int s_slab[RMPE_MAX_SCALES][14][2];
-    __shared__ int s_gcol[RMPE_MAX_SCALES][4][2];   // staged columns {first, count} that a column group of 32 (+-1) depends on
-    __shared__ float s_ym[RMPE_MAX_SCALES][2];      // largest positive / negative row mass of Ky
     __shared__ short s_loff[RMPE_MAX_SCALES][kScrCols];        // first staged column of every tile column
-    __shared__ float s_zw[kScrThreads / 32][kCullCols];        // per warp: bound on |sum_i Ky[r][i] B[i][c]| of a staged column
-    __shared__ float s_cb[2][kScrCols];                        // bound on S per tile column (two halves of the scales)
     __shared__ float s_A[kParts];                              // the item's bounds on the partial sums (rounding allowance)
     __shared__ int s_item;
     const int n_act = min(*act_count, act_cap);
@@ -712,35 +858,16 @@ __global__ void __launch_bounds__(kScrThreads, MAXROWS <= 16 ? 3 : 2) k_screen_p
             s_slab[sc][e][1] = max(min(hi, s_rng[sc][1] - r0 + 1), s_slab[sc][e][0]);
         }
         if (tid >= 128 && tid < 128 + kParts) s_A[tid - 128] = act_A[(size_t)E.slot * kParts + tid - 128];
-        if (tid >= 16 && tid < 16 + NS) {
-            const MsScale &S = J.sc[tid - 16];
-            s_ym[tid - 16][0] = __int_as_float(S.loy[H]);
-            s_ym[tid - 16][1] = __int_as_float(S.loy[H + 1]);
-        }
-        if (half == 0) {
-            // staged columns the 32 tile columns of a group read
-            for (int sc = 0; sc < NS; sc++) {
-                s_loff[sc][col] = (short)(mylox[sc] - s_rng[sc][2]);
-                const int lo = __reduce_min_sync(0xffffffffu, mylox[sc]);
-                const int hi = __reduce_max_sync(0xffffffffu, mylox[sc]);
-                if (lane == 0) {
-                    const int c0 = s_rng[sc][2], bp = s_rng[sc][3] - c0 + 1 + KWX;
-                    s_gcol[sc][warp][0] = lo - c0;
-                    s_gcol[sc][warp][1] = min(hi + KWX - c0, bp) - (lo - c0);
-                }
-            }
-        }
+        if (half == 0)
+            for (int sc = 0; sc < NS; sc++) s_loff[sc][col] = (short)(mylox[sc] - s_rng[sc][2]);
         __syncthreads();
         float *sBall = reinterpret_cast<float *>(sm_raw);                 // 2 x [sc][nrows][ncols + KWX]: this part / next part
         float *sTall = sBall + 2 * s_boff[NS];                            // [sc][nrows][128]
         float *sS = sTall + s_toff[NS];                                   // [34][128]
         float *sKyAll = sS + kScrRows * kScrCols;                         // [NS][34][MAXROWS] dense over staged rows
         float *sKxAll = sKyAll + NS * kScrRows * MAXROWS;                 // [NS][KWX][128]: tap-major, a warp's 32 columns in 32 banks
-        bool bad = false, tight = (cull != 0);
-        for (int sc = 0; sc < NS; sc++) {
-            bad = bad || (s_rng[sc][1] - s_rng[sc][0] + 1 > MAXROWS);
-            for (int g = 0; g < 4; g++) tight = tight && (s_gcol[sc][g][1] <= kCullCols);
-        }
+        bool bad = false;
+        for (int sc = 0; sc < NS; sc++) bad = bad || (s_rng[sc][1] - s_rng[sc][0] + 1 > MAXROWS);
         if (bad) {   // host sized the launch for this never to happen
             if (tid == 0) atomicOr(status + J.frame, RMPE_ST_PEAK_OVERFLOW);
             continue;
@@ -781,62 +908,20 @@ __global__ void __launch_bounds__(kScrThreads, MAXROWS <= 16 ? 3 : 2) k_screen_p
         };
         __syncthreads();                                        // zero fill done before the first copies land
         stage_part(__ffs(E.parts) - 1, 0);
-        int buf = 0;
+        int buf = 0, part_k = 0;
       for (unsigned pm = E.parts; pm; pm &= pm - 1, buf ^= 1) {
         const int part = __ffs(pm) - 1;
         const float A = s_A[part];
         cp_async_wait_all();
         __syncthreads();                                        // this part's blob values landed; previous sT / sS are free
         if (pm & (pm - 1)) stage_part(__ffs(pm & (pm - 1)) - 1, buf ^ 1);
-        // ---- which column groups can hold a peak.  |S[r][col]| <= sum_s sum_j |Kx_s[col][j]| z_s[lox + j] with
-        //      z[c] = max(yp B+ + yn B-, yn B+ + yp B-), B+- = the staged column's largest positive / negative blob value
-        //      and yp / yn = the row masses of Ky.  A group of 32 tile columns whose bound (over its columns and their
-        //      two neighbours) is <= thre1 holds no peak and no neighbour of one: it is skipped, its part of sS stays
-        //      stale and is never compared with a pixel that can be a peak; the work of the remaining groups is spread over all
-        //      eight warps (2, 4 or 8 row slices per group).  Warp w bounds group w & 3 for the scales of parity w >> 2.
-        unsigned live = 0xFu;
-        if (tight) {
-            const int g = warp & 3, cg = 32 * g + lane;
-            float b = 0.f;
-            for (int sc = warp >> 2; sc < NS; sc += 2) {
-                const int nrows = s_rng[sc][1] - s_rng[sc][0] + 1, bp = s_rng[sc][3] - s_rng[sc][2] + 1 + KWX;
-                const int first = s_gcol[sc][g][0], cnt = s_gcol[sc][g][1];
-                const float *sB = sBall + buf * s_boff[NS] + s_boff[sc] + first;
-                const float yp = s_ym[sc][0], yn = s_ym[sc][1];
-                __syncwarp();
-                for (int c = lane; c < cnt; c += 32) {
-                    float vp = 0.f, vn = 0.f;
-                    for (int r = 0; r < nrows; r++) {
-                        const float v = sB[r * bp + c];
-                        vp = fmaxf(vp, v); vn = fmaxf(vn, -v);
-                    }
-                    s_zw[warp][c] = fmaxf(yp * vp + yn * vn, yn * vp + yp * vn);
-                }
-                __syncwarp();
-                auto col_bound = [&](int cc) {
-                    const float *kx = sKxAll + (size_t)sc * KWX * kScrCols + cc;
-                    const float *z = s_zw[warp] + ((int)s_loff[sc][cc] - first);
-                    float s = 0.f;
-#pragma unroll
-                    for (int j = 0; j < KWX; j++) s = fmaf(fabsf(kx[j * kScrCols]), z[j], s);
-                    return s;
-                };
-                b += col_bound(cg);
-            }
-            s_cb[warp >> 2][cg] = b;
-            __syncthreads();
-            const float lim_b = thre1 - kScreenDelta * A;
-            live = 0;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                float bq = s_cb[0][32 * q + lane] + s_cb[1][32 * q + lane];
-                // a hot pixel in the first or last column of a group compares with a value of the next group
-                if (lane == 0 && q > 0) bq = fmaxf(bq, s_cb[0][32 * q - 1] + s_cb[1][32 * q - 1]);
-                if (lane == 31 && q < 3) bq = fmaxf(bq, s_cb[0][32 * q + 32] + s_cb[1][32 * q + 32]);
-                if (__any_sync(0xffffffffu, !(bq * 1.0001f <= lim_b))) live |= 1u << q;     // NaN / Inf keep the group
-            }
-            if (!live) continue;                                // (uniform over the CTA) nothing of this part can be a peak
-        }
+        // ---- the column groups (32 tile columns each) of this part that can hold a peak come with the item
+        //      (k_screen_plan's column bounds); their work is spread over all eight warps: 1 / 2 / 3-4 live groups ->
+        //      8 / 4 / 2 row slices per group.  A skipped group's part of sS stays stale and is never compared with a
+        //      pixel that can be a peak.
+        const unsigned live = cull ? (unsigned)(E.live >> (4 * part_k)) & 0xFu : 0xFu;
+        part_k++;
+        if (!live) continue;                                    // (uniform over the CTA)
         const int n_live = __popc(live);
         const int ns = n_live == 1 ? 8 : (n_live == 2 ? 4 : 2);       // row slices per group
         const int slab0 = ns == 2 ? 0 : (ns == 4 ? 2 : 6);
@@ -1688,7 +1773,7 @@ static FramePlan plan_frame(const RmpeFrameDesc &f, int stride, bool allow_scree
 }
 
 // resident CTAs of k_screen_pairs per SM for a dynamic shared-memory need (+ static shared memory / reserve)
-static int ctas_per_sm(size_t smem) { return std::max(1, std::min(6, (int)((224 * 1024) / (std::max<size_t>(smem, 1) + 6144)))); }
+static int ctas_per_sm(size_t smem) { return std::max(1, std::min(6, (int)((224 * 1024) / (std::max<size_t>(smem, 1) + 4096)))); }
 
 static size_t fixed_ws_bytes(int batch, int max_peaks, int max_cand) {
     size_t per_list = (size_t)batch * kParts * max_peaks;
@@ -2017,13 +2102,13 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                     return (v >= 1 && v <= kParts) ? v : 0;
                 }();
                 // few frames: small items spread better over the SMs; many: larger items amortise the set-up of a tile
-                const int group = (variant >= 2) ? ms_group : (ss_group ? ss_group : (nj > 16 ? 6 : 3));
+                const int group = std::min(16, (variant >= 2) ? ms_group : (ss_group ? ss_group : (nj > 16 ? 6 : 3)));   // 16 nibbles of ActEntry::live
                 // column-group culling inside k_screen_pairs (RMPE_SCREEN_CULL=0: every group of an active tile is evaluated)
                 static const int cull = [] { const char *e = getenv("RMPE_SCREEN_CULL"); return (e && atoi(e) == 0) ? 0 : 1; }();
                 {
                     ProfScope ps("k_screen_plan", st);
                     k_screen_plan<<<dim3(mt, nj), kPlanThreads, 0, st>>>(jobs, (float)b->thre1, act_cap, group, lst, lstA, cnt, tab_err,
-                                                                       b->status);
+                                                                       b->status, cull);
                     RMPE_CUDA_TRY(cudaGetLastError());
                 }
                 {
