@@ -348,6 +348,7 @@ constexpr int kMsMaxRows = 24;       // multi scale: staged blob rows per scale 
 constexpr int kMsKWBig = 16;         // small frames (scale 2 of a 240-row image is up-sampled by only 2.6): wider variant
 constexpr int kMsMaxRowsBig = 32;
 constexpr int kPlanSlots = 4;        // parts of a tile refined together by k_screen_plan
+constexpr int kPlanMaxRefined = 8;   // more surviving parts than this in a tile: no column bounds (all groups stay live)
 constexpr int kPlanMaxCols = 96;     // staged columns + padding per scale that the refinement holds
 
 struct AxisJob {
@@ -642,6 +643,9 @@ __global__ void __launch_bounds__(kPlanThreads) k_screen_plan(const __grid_const
         }
         __syncthreads();
         n_on = s_nact;
+        // a tile where most parts survive is dense (or crowded): its column groups are all live more often than not and
+        // the column bounds would cost a batch of four parts each
+        if (n_on > kPlanMaxRefined) n_on = 0;
         for (int b0 = 0; b0 < n_on; b0 += kPlanSlots) {
             const int nb = min(kPlanSlots, n_on - b0);
             __syncthreads();                       // the previous batch is done with the tables
