@@ -131,12 +131,14 @@ __global__ void __launch_bounds__(128) k_resize_v(const __grid_constant__ RJobs 
 // PAF value at an integer point of the up-sampled (single) / scale-averaged (multi) field,
 // evaluated on the fly from the blob(s) with the exact per-pixel arithmetic of cv2.resize.
 // ------------------------------------------------------------------------------------------
-// one bicubic resize (src h x w, NHWC with C channels) evaluated at destination (y, x), channel c
-__device__ inline float resize_point_blob(const float *__restrict__ blob, int h, int w, int C, int c, int y, int x,
-                                          int H, int W, double inv_f) {
+// one bicubic resize (src h x w, NHWC with C channels) evaluated at destination (y, x), channel c.  scl_x / scl_y are
+// resize_scale() of the two axes: two f64 divisions each, a constant of the frame -- the kernels that evaluate many
+// points of one frame compute them once (PtScales) instead of per point.
+__device__ inline float resize_point_blob_s(const float *__restrict__ blob, int h, int w, int C, int c, int y, int x,
+                                            int W, double scl_x, double scl_y) {
     float a[4], b[4];
-    int sx = resize_axis(x, resize_scale(W, w, inv_f), a);
-    int sy = resize_axis(y, resize_scale(H, h, inv_f), b);
+    int sx = resize_axis(x, scl_x, a);
+    int sy = resize_axis(y, scl_y, b);
     float hp[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -146,13 +148,18 @@ __device__ inline float resize_point_blob(const float *__restrict__ blob, int h,
     }
     return in_row_tail(x, c, W, C) ? tap_ltr(hp[0], hp[1], hp[2], hp[3], b) : tap_rtl(hp[0], hp[1], hp[2], hp[3], b);
 }
+__device__ inline float resize_point_blob(const float *__restrict__ blob, int h, int w, int C, int c, int y, int x,
+                                          int H, int W, double inv_f) {
+    return resize_point_blob_s(blob, h, w, C, c, y, x, W, resize_scale(W, w, inv_f), resize_scale(H, h, inv_f));
+}
 
-// multi-scale chain for one scale: blob -> x stride (fx=fy=stride) -> crop (Hc,Wc) -> (H,W)
-__device__ inline float resize_chain_point(const float *__restrict__ blob, int hs, int ws, int C, int c, int y, int x,
-                                           int H, int W, int Hc, int Wc, int stride) {
+// multi-scale chain for one scale: blob -> x stride (fx=fy=stride) -> crop (Hc,Wc) -> (H,W).  s2x / s2y: scales of the
+// second resize, s1: scale of the first (1 / stride)
+__device__ inline float resize_chain_point_s(const float *__restrict__ blob, int hs, int ws, int C, int c, int y, int x,
+                                             int W, int Hc, int Wc, int stride, double s2x, double s2y, double s1) {
     float a[4], b[4];
-    int sx = resize_axis(x, resize_scale(W, Wc, 0.0), a);
-    int sy = resize_axis(y, resize_scale(H, Hc, 0.0), b);
+    int sx = resize_axis(x, s2x, a);
+    int sy = resize_axis(y, s2y, b);
     float hp[4];
 #pragma unroll 1
     for (int j = 0; j < 4; j++) {
@@ -161,26 +168,55 @@ __device__ inline float resize_chain_point(const float *__restrict__ blob, int h
 #pragma unroll 1
         for (int k = 0; k < 4; k++) {
             int q = clampi(sx - 1 + k, 0, Wc - 1);
-            t[k] = resize_point_blob(blob, hs, ws, C, c, r, q, hs * stride, ws * stride, (double)stride);
+            t[k] = resize_point_blob_s(blob, hs, ws, C, c, r, q, ws * stride, s1, s1);
         }
         hp[j] = tap_ltr(t[0], t[1], t[2], t[3], a);
     }
     return in_row_tail(x, c, W, C) ? tap_ltr(hp[0], hp[1], hp[2], hp[3], b) : tap_rtl(hp[0], hp[1], hp[2], hp[3], b);
 }
+__device__ inline float resize_chain_point(const float *__restrict__ blob, int hs, int ws, int C, int c, int y, int x,
+                                           int H, int W, int Hc, int Wc, int stride) {
+    return resize_chain_point_s(blob, hs, ws, C, c, y, x, W, Hc, Wc, stride, resize_scale(W, Wc, 0.0), resize_scale(H, Hc, 0.0),
+                                resize_scale(ws * stride, ws, (double)stride));
+}
 
-__device__ inline double paf_point(const RmpeFrameDesc &f, const float *__restrict__ paf, int stride, int c, int y,
-                                   int x) {
+// resize scales of a frame: per scale the (second) resize to (H, W); s1 = the x stride up-sampling of the chain
+struct PtScales {
+    double sy[RMPE_MAX_SCALES], sx[RMPE_MAX_SCALES], s1;
+};
+__device__ inline void pt_scales_one(PtScales &ps, const RmpeFrameDesc &f, int stride, int s) {
+    if (f.n_scales == 1) {
+        ps.sy[0] = resize_scale(f.height, f.grid_h[0], 0.0);
+        ps.sx[0] = resize_scale(f.width, f.grid_w[0], 0.0);
+    } else {
+        ps.sy[s] = resize_scale(f.height, f.grid_h[s] * stride - f.pad_down[s], 0.0);
+        ps.sx[s] = resize_scale(f.width, f.grid_w[s] * stride - f.pad_right[s], 0.0);
+    }
+    if (s == 0) ps.s1 = resize_scale(0, 1, (double)stride);
+}
+
+__device__ inline double blob_point_s(const RmpeFrameDesc &f, const float *__restrict__ blobs, const int64_t *off, int C,
+                                      int stride, int c, int y, int x, const PtScales &ps) {
     if (f.n_scales == 1)
-        return (double)resize_point_blob(paf + f.paf_offset[0], f.grid_h[0], f.grid_w[0], kPafC, c, y, x, f.height,
-                                         f.width, 0.0);
+        return (double)resize_point_blob_s(blobs + off[0], f.grid_h[0], f.grid_w[0], C, c, y, x, f.width, ps.sx[0], ps.sy[0]);
     double acc = 0.0;
     for (int s = 0; s < f.n_scales; s++) {
         int Hc = f.grid_h[s] * stride - f.pad_down[s], Wc = f.grid_w[s] * stride - f.pad_right[s];
-        float v = resize_chain_point(paf + f.paf_offset[s], f.grid_h[s], f.grid_w[s], kPafC, c, y, x, f.height,
-                                     f.width, Hc, Wc, stride);
+        float v = resize_chain_point_s(blobs + off[s], f.grid_h[s], f.grid_w[s], C, c, y, x, f.width, Hc, Wc, stride,
+                                       ps.sx[s], ps.sy[s], ps.s1);
         acc = __dadd_rn(acc, (double)__fdiv_rn(v, (float)f.n_scales));
     }
     return acc;
+}
+__device__ inline double paf_point_s(const RmpeFrameDesc &f, const float *__restrict__ paf, int stride, int c, int y, int x,
+                                     const PtScales &ps) {
+    return blob_point_s(f, paf, f.paf_offset, kPafC, stride, c, y, x, ps);
+}
+__device__ inline double paf_point(const RmpeFrameDesc &f, const float *__restrict__ paf, int stride, int c, int y,
+                                   int x) {
+    PtScales ps;
+    for (int s = 0; s < f.n_scales; s++) pt_scales_one(ps, f, stride, s);
+    return paf_point_s(f, paf, stride, c, y, x, ps);
 }
 
 __global__ void k_paf_points(RmpeFrameDesc f, const float *paf, int stride, int n, const int32_t *cyx, double *out) {
@@ -327,9 +363,12 @@ __global__ void __launch_bounds__(kSmoothThreads) k_smooth_peaks(const __grid_co
 // both linear and separable, so the smoothed map is  S = Ky * blob * Kx^T  with composite
 // per-axis operators  K = G * R  that have ~(24 h/H + 5) non-zeros per row.
 //   k_axis_tables  builds K (f64 accumulation, stored f32) and the first source index per row.
-//   k_screen_plan / k_screen_pairs  evaluate S~ = Ky * blob * Kx^T straight from the NHWC blob
-//                  (the 57x larger up-sampled map is never written) and emit every pixel that could
-//                  be a peak once a rigorous bound delta on |S~ - S| is allowed for:
+//   k_screen_plan  decides from bounds on S which (32 x 126 tile, part) pairs can hold a peak at all
+//                  (tile bound from the largest blob values, then per-row and per-column bounds) and
+//                  which 32-column groups of such a tile; the survivors become work items.
+//   k_screen_pairs  evaluates S~ = Ky * blob * Kx^T for the live column groups of an item straight
+//                  from the NHWC blob (the 57x larger up-sampled map is never written) and emits every
+//                  pixel that could be a peak once a rigorous bound delta on |S~ - S| is allowed for:
 //                  S~ > thre1 - delta and S~ >= neighbour~ - 2 delta for the four neighbours.
 //   k_peak_verify  re-evaluates each such pixel and its four neighbours EXACTLY -- cv2's float32
 //                  tap order, scipy's f64 accumulation order and per-axis float32 store -- and
@@ -1007,22 +1046,12 @@ constexpr int kVerN = 2 * kSR + 3;   // 27: the pixel +-1, +-12
 constexpr int kVerI1Cap = 64 * 64;   // cached x-stride rectangle (floats); larger ones are evaluated point by point
 
 // heat value of the (scale-averaged) up-sampled map at an integer point, the reference's arithmetic
-__device__ inline double heat_point(const RmpeFrameDesc &f, const float *__restrict__ heat, int stride, int c, int y,
-                                    int x) {
-    if (f.n_scales == 1)
-        return (double)resize_point_blob(heat + f.heat_offset[0], f.grid_h[0], f.grid_w[0], kHeatC, c, y, x, f.height,
-                                         f.width, 0.0);
-    double acc = 0.0;
-    for (int s = 0; s < f.n_scales; s++) {
-        int Hc = f.grid_h[s] * stride - f.pad_down[s], Wc = f.grid_w[s] * stride - f.pad_right[s];
-        float v = resize_chain_point(heat + f.heat_offset[s], f.grid_h[s], f.grid_w[s], kHeatC, c, y, x, f.height,
-                                     f.width, Hc, Wc, stride);
-        acc = __dadd_rn(acc, (double)__fdiv_rn(v, (float)f.n_scales));
-    }
-    return acc;
+__device__ inline double heat_point_s(const RmpeFrameDesc &f, const float *__restrict__ heat, int stride, int c, int y, int x,
+                                      const PtScales &ps) {
+    return blob_point_s(f, heat, f.heat_offset, kHeatC, stride, c, y, x, ps);
 }
 
-__global__ void __launch_bounds__(kVerThreads) k_peak_verify(const RmpeFrameDesc *__restrict__ frames,
+__global__ void __launch_bounds__(kVerThreads, 6) k_peak_verify(const RmpeFrameDesc *__restrict__ frames,
                                                             const float *__restrict__ heat, int stride, double thre1,
                                                             int cand_cap, const int32_t *__restrict__ cand_key,
                                                             const int32_t *__restrict__ cand_fp,
@@ -1040,12 +1069,19 @@ __global__ void __launch_bounds__(kVerThreads) k_peak_verify(const RmpeFrameDesc
     __shared__ int s_tap0[2][kVerN];               // first tap of the second resize per row / column
     __shared__ float s_tapc[2][kVerN][4];          // its coefficients
     __shared__ int s_box[4];
+    __shared__ PtScales s_ps;                      // resize scales of the candidate's frame (f64 divisions: once per frame)
+    int ps_frame = -1;
     const int total = min(*cand_count, cand_cap);
     const int tid = threadIdx.x;
     for (int ci = blockIdx.x; ci < total; ci += gridDim.x) {
         const int fp = cand_fp[ci], key = cand_key[ci];
         const int frame = fp / kParts, part = fp - frame * kParts;
         const RmpeFrameDesc f = frames[frame];
+        if (frame != ps_frame) {                   // (uniform; the previous candidate ended behind a barrier)
+            if (tid < f.n_scales) pt_scales_one(s_ps, f, stride, tid);
+            ps_frame = frame;
+            __syncthreads();
+        }
         const int H = f.height, W = f.width;
         const int y = key / W, x = key - y * W;
         const bool f32map = f.n_scales == 1;
@@ -1053,7 +1089,7 @@ __global__ void __launch_bounds__(kVerThreads) k_peak_verify(const RmpeFrameDesc
         if (f32map) {
             for (int i = tid; i < kVerN * kVerN; i += kVerThreads) {
                 const int a = i / kVerN, b = i - a * kVerN;
-                sU[a][b] = heat_point(f, heat, stride, part, reflect_idx(y - kSR - 1 + a, H), reflect_idx(x - kSR - 1 + b, W));
+                sU[a][b] = heat_point_s(f, heat, stride, part, reflect_idx(y - kSR - 1 + a, H), reflect_idx(x - kSR - 1 + b, W), s_ps);
             }
         } else {
             // multi scale: U = sum_s f64(chain_s / n).  The 729 points of one scale share the x-stride map they are
@@ -1070,7 +1106,7 @@ __global__ void __launch_bounds__(kVerThreads) k_peak_verify(const RmpeFrameDesc
                     const int a = isrow ? tid : tid - kVerN;
                     float co[4];
                     const int g = isrow ? reflect_idx(y - kSR - 1 + a, H) : reflect_idx(x - kSR - 1 + a, W);
-                    const int s0 = isrow ? resize_axis(g, resize_scale(H, Hc, 0.0), co) : resize_axis(g, resize_scale(W, Wc, 0.0), co);
+                    const int s0 = resize_axis(g, isrow ? s_ps.sy[sI] : s_ps.sx[sI], co);
                     s_tap0[isrow ? 0 : 1][a] = s0;
 #pragma unroll
                     for (int k = 0; k < 4; k++) s_tapc[isrow ? 0 : 1][a][k] = co[k];
@@ -1091,7 +1127,7 @@ __global__ void __launch_bounds__(kVerThreads) k_peak_verify(const RmpeFrameDesc
                 if (cached)
                     for (int i = tid; i < nr * nq; i += kVerThreads) {
                         const int r = i / nq, q = i - r * nq;
-                        sI1[i] = resize_point_blob(blob, hs, ws, kHeatC, part, r0 + r, q0 + q, hs * stride, ws * stride, (double)stride);
+                        sI1[i] = resize_point_blob_s(blob, hs, ws, kHeatC, part, r0 + r, q0 + q, ws * stride, s_ps.s1, s_ps.s1);
                     }
                 __syncthreads();
                 for (int i = tid; i < kVerN * kVerN; i += kVerThreads) {
@@ -1110,8 +1146,8 @@ __global__ void __launch_bounds__(kVerThreads) k_peak_verify(const RmpeFrameDesc
                         v = in_row_tail(xg, part, W, kHeatC) ? tap_ltr(hp[0], hp[1], hp[2], hp[3], s_tapc[0][a])
                                                              : tap_rtl(hp[0], hp[1], hp[2], hp[3], s_tapc[0][a]);
                     } else {
-                        v = resize_chain_point(blob, hs, ws, kHeatC, part, reflect_idx(y - kSR - 1 + a, H),
-                                               reflect_idx(x - kSR - 1 + b, W), H, W, Hc, Wc, stride);
+                        v = resize_chain_point_s(blob, hs, ws, kHeatC, part, reflect_idx(y - kSR - 1 + a, H),
+                                                 reflect_idx(x - kSR - 1 + b, W), W, Hc, Wc, stride, s_ps.sx[sI], s_ps.sy[sI], s_ps.s1);
                     }
                     sU[a][b] = __dadd_rn(sU[a][b], (double)__fdiv_rn(v, (float)f.n_scales));
                 }
@@ -1263,6 +1299,8 @@ __global__ void __launch_bounds__(kLimbThreads) k_limbs(const RmpeFrameDesc *__r
     int *s_seq = reinterpret_cast<int *>(s_score + max_cand);       // [npow]
     uint8_t *s_usedA = reinterpret_cast<uint8_t *>(s_seq + max_cand);
     uint8_t *s_usedB = s_usedA + kMaxPeaksCap;
+    __shared__ PtScales s_ps;                      // resize scales of the frame (f64 divisions: once per CTA, not per point)
+    if (tid < f.n_scales) pt_scales_one(s_ps, f, stride, tid);
     if (tid == 0) s_total = 0;
     __syncthreads();
 
@@ -1290,7 +1328,7 @@ __global__ void __launch_bounds__(kLimbThreads) k_limbs(const RmpeFrameDesc *__r
                     const double px = (I == 9) ? (double)bx : __dadd_rn(__dmul_rn((double)I, stepx), (double)ax);
                     const double py = (I == 9) ? (double)by : __dadd_rn(__dmul_rn((double)I, stepy), (double)ay);
                     const int xi = __double2int_rn(px), yi = __double2int_rn(py);   // round half to even
-                    v = paf_point(f, paf, stride, pc + ch, yi, xi);
+                    v = paf_point_s(f, paf, stride, pc + ch, yi, xi, s_ps);
                 }
                 s_val[p][I][ch] = v;
             }
@@ -1363,8 +1401,8 @@ __global__ void __launch_bounds__(kLimbThreads) k_limbs(const RmpeFrameDesc *__r
                     double px = (I == 9) ? (double)bx : __dadd_rn(__dmul_rn((double)I, stepx), (double)ax);
                     double py = (I == 9) ? (double)by : __dadd_rn(__dmul_rn((double)I, stepy), (double)ay);
                     int xi = __double2int_rn(px), yi = __double2int_rn(py);   // round half to even
-                    double vxp = paf_point(f, paf, stride, pc, yi, xi);
-                    double vyp = paf_point(f, paf, stride, pc + 1, yi, xi);
+                    double vxp = paf_point_s(f, paf, stride, pc, yi, xi, s_ps);
+                    double vyp = paf_point_s(f, paf, stride, pc + 1, yi, xi, s_ps);
                     double s = __dadd_rn(__dmul_rn(vxp, ux), __dmul_rn(vyp, uy));
                     sum = __dadd_rn(sum, s);
                     nok += (s > thre2) ? 1 : 0;
@@ -2143,6 +2181,8 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
             if ((rc = screen(jobsH, nH, tH, smH, 2, 4)) != RMPE_OK) return rc;
             {
                 ProfScope ps("k_peak_verify", st);
+                // one candidate per CTA and round.  Resident CTAs per SM do not decide (4 / 6 / 8 by register cap measured
+                // 0.99 / 0.98 / 1.02 ms per 256 multi-scale frames): the kernel waits for instruction fetches (ncu: no_instruction)
                 const int grid = std::min(cand_cap, 8 * sms);
                 RMPE_CUDA_TRY(launch_pdl(k_peak_verify, dim3(grid), dim3(kVerThreads), 0, st, b->frames, b->heat, b->stride, b->thre1,
                                          cand_cap, cand_key, cand_fp, cand_count, MP, raw_key, raw_score, raw_count, b->status));
