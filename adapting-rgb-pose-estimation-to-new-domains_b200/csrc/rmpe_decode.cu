@@ -545,11 +545,8 @@ __global__ void __launch_bounds__(kPlanThreads) k_screen_plan(const __grid_const
     __shared__ int s_rng[RMPE_MAX_SCALES][4];
     __shared__ int s_loy[RMPE_MAX_SCALES][kScrRows];
     __shared__ int s_bpos[RMPE_MAX_SCALES][kHeatC + 1], s_bneg[RMPE_MAX_SCALES][kHeatC + 1];
-    // largest positive / negative value of every staged row, per channel (bits of non-negative floats)
-    __shared__ int s_rp[RMPE_MAX_SCALES][kMsMaxRowsBig][kHeatC + 1], s_rn[RMPE_MAX_SCALES][kMsMaxRowsBig][kHeatC + 1];
     int mylox[RMPE_MAX_SCALES];
     if (tid < RMPE_MAX_SCALES * (kHeatC + 1)) { (&s_bpos[0][0])[tid] = 0; (&s_bneg[0][0])[tid] = 0; }
-    for (int i = tid; i < RMPE_MAX_SCALES * kMsMaxRowsBig * (kHeatC + 1); i += kPlanThreads) { (&s_rp[0][0][0])[i] = 0; (&s_rn[0][0][0])[i] = 0; }
     tile_ranges(J, y0, x0, tid, tid & (kScrCols - 1), tid >> 7, s_rng, s_loy, mylox);
     for (int sc = 0; sc < NS; sc++) {
         const MsScale &S = J.sc[sc];
@@ -557,7 +554,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_screen_plan(const __grid_const
         const int nrows = s_rng[sc][1] - r0 + 1, rowlen = (s_rng[sc][3] - c0 + 1) * kHeatC;
         // coalesced row segments of the NHWC blob; element e of a segment belongs to channel e % 19.  13 x 19 = 247
         // threads walk a segment with stride 247, so a thread stays on ONE channel and keeps its maxima in registers;
-        // the 13 threads of a channel meet in shared memory once per staged row (row maxima) and once per scale.
+        // the 13 threads of a channel meet in shared memory once per scale.
         float vpos = 0.f, vneg = 0.f;
         if (tid < kPlanStride) {
             const int ch = tid % kHeatC;
@@ -566,34 +563,19 @@ __global__ void __launch_bounds__(kPlanThreads) k_screen_plan(const __grid_const
             int r = 0;
             for (; r + 1 < nrows; r += 2) {                       // two rows in flight
                 const float *row0 = base + (size_t)r * rstride, *row1 = row0 + rstride;
-                float p0 = 0.f, n0 = 0.f, p1 = 0.f, n1 = 0.f;
                 for (int e = tid; e < rowlen; e += kPlanStride) {
                     const float v0 = row0[e], v1 = row1[e];
-                    p0 = fmaxf(p0, v0); n0 = fmaxf(n0, -v0);
-                    p1 = fmaxf(p1, v1); n1 = fmaxf(n1, -v1);
+                    vpos = fmaxf(vpos, fmaxf(v0, v1));
+                    vneg = fmaxf(vneg, fmaxf(-v0, -v1));
                 }
-                if (r + 1 < kMsMaxRowsBig) {
-                    if (p0 > 0.f) atomicMax(&s_rp[sc][r][ch], __float_as_int(p0));
-                    if (n0 > 0.f) atomicMax(&s_rn[sc][r][ch], __float_as_int(n0));
-                    if (p1 > 0.f) atomicMax(&s_rp[sc][r + 1][ch], __float_as_int(p1));
-                    if (n1 > 0.f) atomicMax(&s_rn[sc][r + 1][ch], __float_as_int(n1));
-                }
-                vpos = fmaxf(vpos, fmaxf(p0, p1));
-                vneg = fmaxf(vneg, fmaxf(n0, n1));
             }
             if (r < nrows) {
                 const float *row0 = base + (size_t)r * rstride;
-                float p0 = 0.f, n0 = 0.f;
                 for (int e = tid; e < rowlen; e += kPlanStride) {
                     const float v0 = row0[e];
-                    p0 = fmaxf(p0, v0); n0 = fmaxf(n0, -v0);
+                    vpos = fmaxf(vpos, v0);
+                    vneg = fmaxf(vneg, -v0);
                 }
-                if (r < kMsMaxRowsBig) {
-                    if (p0 > 0.f) atomicMax(&s_rp[sc][r][ch], __float_as_int(p0));
-                    if (n0 > 0.f) atomicMax(&s_rn[sc][r][ch], __float_as_int(n0));
-                }
-                vpos = fmaxf(vpos, p0);
-                vneg = fmaxf(vneg, n0);
             }
             if (vpos > 0.f) atomicMax(&s_bpos[sc][ch], __float_as_int(vpos));
             if (vneg > 0.f) atomicMax(&s_bneg[sc][ch], __float_as_int(vneg));
@@ -647,6 +629,25 @@ __global__ void __launch_bounds__(kPlanThreads) k_screen_plan(const __grid_const
     if (can_refine) {
         __shared__ float s_zx[kPlanSlots][RMPE_MAX_SCALES][kPlanMaxCols];
         __shared__ float s_cbp[kPlanSlots][kScrCols];
+        __shared__ float s_zy[kParts][RMPE_MAX_SCALES][kMsMaxRowsBig];
+        // (0) staged rows of the active parts: zy of one (part, scale, row) per thread; the lines were read by the scan above
+        for (int sc = 0; sc < NS; sc++) {
+            const MsScale &S = J.sc[sc];
+            const int r0 = s_rng[sc][0], c0 = s_rng[sc][2];
+            const int nrows = s_rng[sc][1] - r0 + 1, ncols = s_rng[sc][3] - c0 + 1;
+            const float xp = __int_as_float(S.lox[J.W]), xn = __int_as_float(S.lox[J.W + 1]);
+            for (int task = tid; task < n_on * nrows; task += kPlanThreads) {
+                const int slot = task / nrows, i = task - slot * nrows;
+                const float *base = S.heat + ((size_t)(r0 + i) * S.w + c0) * kHeatC + s_parts[slot];
+                float vp = 0.f, vn = 0.f;
+                for (int j = 0; j < ncols; j++) {
+                    const float v = base[j * kHeatC];
+                    vp = fmaxf(vp, v); vn = fmaxf(vn, -v);
+                }
+                s_zy[slot][sc][i] = fmaxf(xp * vp + xn * vn, xn * vp + xp * vn);
+            }
+        }
+        __syncthreads();
         // (1) row bounds of every active part: one thread per (part, tile row)
         for (int task = tid; task < n_on * kScrRows; task += kPlanThreads) {
             const int slot = task / kScrRows, t = task - slot * kScrRows;
@@ -655,14 +656,10 @@ __global__ void __launch_bounds__(kPlanThreads) k_screen_plan(const __grid_const
             float rb = 0.f;
             for (int sc = 0; sc < NS; sc++) {
                 const MsScale &S = J.sc[sc];
-                const float xp = __int_as_float(S.lox[J.W]), xn = __int_as_float(S.lox[J.W + 1]);
                 const int lo = s_loy[sc][t] - s_rng[sc][0], nrows = s_rng[sc][1] - s_rng[sc][0] + 1;
                 const float *ky = S.Ky + (size_t)y * S.kwy;
                 for (int k = 0; k < S.kwy; k++)
-                    if (lo + k < nrows) {
-                        const float bp = __int_as_float(s_rp[sc][lo + k][part]), bn = __int_as_float(s_rn[sc][lo + k][part]);
-                        rb = fmaf(fabsf(ky[k]), fmaxf(xp * bp + xn * bn, xn * bp + xp * bn), rb);
-                    }
+                    if (lo + k < nrows) rb = fmaf(fabsf(ky[k]), s_zy[slot][sc][lo + k], rb);
             }
             atomicMax(&s_rb[part], __float_as_int(rb));
         }
