@@ -2128,9 +2128,9 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                 int32_t *nxt = cand_count + 16 + slot;     // next item k_screen_pairs hands out
                 ActEntry *lst = act + (size_t)slot * act_cap;
                 float *lstA = act_A + (size_t)slot * act_cap * kParts;
-                // parts per work item (measured): single-scale items are cheap to set up (three parts), multi-scale items
-                // stage the operators of four scales (amortise them over up to six active parts of the tile)
-                static const int ms_group = [] {      // 256 COCO-val-shaped frames with the culling kernel: 6 parts per item 7.23 ms, 9: 7.09, 12: 7.13, 18: 7.23
+                // parts per work item (measured): single-scale items are cheap to set up, multi-scale items stage the operators
+                // of four scales (amortise them over up to nine active parts of the tile)
+                static const int ms_group = [] {      // 256 COCO-val-shaped frames: 6 parts per item 7.23 ms, 9: 7.09, 12: 7.13, 18: 7.23 (before the plan refinement; 5.78 / 5.86 with it)
                     const char *e = getenv("RMPE_MS_GROUP");
                     int v = e ? atoi(e) : 9;
                     return (v >= 1 && v <= kParts) ? v : 9;
@@ -2142,7 +2142,8 @@ extern "C" int rmpe_decode_batch(const RmpeDecodeBatch *b, void *stream_) {
                 }();
                 // few frames: small items spread better over the SMs; many: larger items amortise the set-up of a tile
                 const int group = std::min(16, (variant >= 2) ? ms_group : (ss_group ? ss_group : (nj > 16 ? 6 : 3)));   // 16 nibbles of ActEntry::live
-                // column-group culling inside k_screen_pairs (RMPE_SCREEN_CULL=0: every group of an active tile is evaluated)
+                // row / column refinement in k_screen_plan and column-group skipping in k_screen_pairs (RMPE_SCREEN_CULL=0: the
+                // tile bound alone decides and every column group of an active tile is evaluated)
                 static const int cull = [] { const char *e = getenv("RMPE_SCREEN_CULL"); return (e && atoi(e) == 0) ? 0 : 1; }();
                 {
                     ProfScope ps("k_screen_plan", st);
